@@ -1,0 +1,66 @@
+"""Oracle (test infrastructure only): MCA.fit (= CPCCA with alpha=1) on numpy arrays, use_pca=False
+or the default PCA pre-projection.
+
+Reference lines followed (/root/reference/xeofs):
+  cross/mca.py:104-123                      MCA = CPCCA(alpha=1.0)
+  cross/cpcca.py:143-146                    center=True hard-coded
+  cross/base_model_cross_set.py:304-315     preprocess -> PCA -> (augment) -> whiten -> _fit_algorithm
+  preprocessing/whitener.py:96-98           alpha == 1 -> identity
+  preprocessing/pca.py:94-131               optional PCA: rSVD with int(rank*0.3) modes, 99.9 % truncation, X <- X V
+  cross/cpcca.py:176-184, 1008-1015         C = X^H Y / (n - 1)
+  cross/cpcca.py:187-194                    Decomposer.fit(C) -> s, Q1 = U_, Q2 = V_
+  cross/cpcca.py:197, 991-1000              total_squared_covariance = sum |C|^2
+  cross/cpcca.py:200                        idx_modes_sorted = argsort(s)[::-1]
+  cross/cpcca.py:204-208                    scores = X Q, norm = sqrt(diag(scores^H scores))
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import preprocess as pp
+from .decomposer import decompose
+
+
+def cross_covariance(X, Y):
+    """cross/cpcca.py:1008-1015 (assumes centred data)."""
+    if X.shape[0] != Y.shape[0]:
+        raise ValueError(
+            f"Both data matrices must have the same number of samples but found {X.shape[0]} in the first and {Y.shape[0]} in the second."
+        )
+    return X.conj().T @ Y / (X.shape[0] - 1)
+
+
+def mca_fit(
+    X, Y, dims_x, dims_y, sample_dims,
+    coords_x=None, coords_y=None,
+    n_modes=2, standardize=False, use_coslat=False, check_nans=True,
+    weights_x=None, weights_y=None,
+    random_state=None, solver="auto", solver_kwargs=None,
+):
+    """use_pca=False path (the configuration BASELINE.json config 3 is built on; the default
+    use_pca=True path is unseeded in the reference, cross/base_model_cross_set.py:165-179)."""
+    def _pair(v):
+        return (v, v) if not isinstance(v, (list, tuple)) else tuple(v)
+    std, cos, chk = _pair(standardize), _pair(use_coslat), _pair(check_nans)
+    f1 = pp.preprocess(X, dims_x, sample_dims, coords=coords_x, center=True, standardize=std[0],
+                       use_coslat=cos[0], weights=weights_x, check_nans=chk[0])
+    f2 = pp.preprocess(Y, dims_y, sample_dims, coords=coords_y, center=True, standardize=std[1],
+                       use_coslat=cos[1], weights=weights_y, check_nans=chk[1])
+    A1, A2 = f1["A"], f2["A"]
+    C = cross_covariance(A1, A2)
+    Q1, s, Q2 = decompose(C, n_modes=n_modes, solver=solver, random_state=random_state,
+                          solver_kwargs=solver_kwargs)
+    tsc = (np.abs(C) ** 2).sum()
+    scores1 = A1 @ Q1
+    scores2 = A2 @ Q2
+    return {
+        "A1": A1, "A2": A2, "fitted1": f1, "fitted2": f2, "C": C,
+        "components1_2d": Q1, "components2_2d": Q2,
+        "scores1": scores1, "scores2": scores2,
+        "singular_values": s,
+        "squared_covariance": s**2,
+        "total_squared_covariance": tsc,
+        "idx_modes_sorted": np.argsort(s)[::-1],
+        "norm1": np.sqrt((scores1.conj() * scores1).sum(axis=0)).real,
+        "norm2": np.sqrt((scores2.conj() * scores2).sum(axis=0)).real,
+    }
