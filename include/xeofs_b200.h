@@ -1,0 +1,150 @@
+/*
+ * xeofs_b200.h — C-ABI of libxeofs_b200.so: the B200 (sm_100a) kernels behind
+ * xeofs.single.EOF.fit / xeofs.cross.MCA.fit / xeofs.single.EOFRotator.fit.
+ *
+ * The reference (xeofs v3.0.4) is pure Python and has no FFI; every entry point below therefore
+ * replaces a span of Python/numpy/scikit-learn code, cited per function as file:line under
+ * /root/reference/xeofs.  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer (cudaMalloc / torch.cuda tensor .data_ptr()) unless the
+ *    parameter name ends in _host; the library never allocates persistent memory and never frees
+ *    caller memory; scratch is the caller-provided workspace (query the size first);
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*), nothing synchronises;
+ *  - return value: 0 = ok, <0 = error class (XEOFS_E_*); the message is thread-local, see
+ *    xeofs_b200_last_error();
+ *  - layouts (row-major, leading dimension in ELEMENTS):
+ *      X      "field"           T x S   fp32, ldx >= S          (time x space, space contiguous)
+ *      Yt     "space-side"      lp x S  fp32, ldy >= S          (mode-major: row j = column j of the S x l matrix)
+ *      W / Z  "time-side"       T x lp  fp32, ldw >= lp
+ *      lp = l rounded up to a multiple of 16; pad rows/columns are zero and stay zero;
+ *  - per-feature vectors (length S): pivot (subtracted before tensor-core rounding), dscale
+ *    (= valid * coslat * weight / std), ccorr (rank-1 correction (pivot - mean_eff) * dscale, may be NULL = 0).
+ *    Effective matrix:  A[t,s] = (X[t,s] - pivot[s]) * dscale[s] + ccorr[s],  NaN entries count as 0.
+ */
+#ifndef XEOFS_B200_H
+#define XEOFS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XEOFS_OK 0
+#define XEOFS_E_INVALID (-1)   /* bad argument (maps to ValueError)            */
+#define XEOFS_E_CUDA (-2)      /* CUDA runtime / launch failure (RuntimeError) */
+#define XEOFS_E_WORKSPACE (-3) /* workspace too small (ValueError)             */
+#define XEOFS_E_UNSUPPORTED (-4)
+
+/* algo selector for the two streaming products */
+#define XEOFS_ALGO_AUTO 0
+#define XEOFS_ALGO_SIMT 1   /* fp32 CUDA-core kernels (validation path, any alignment)          */
+#define XEOFS_ALGO_TF32X1 2 /* tcgen05 kind::tf32, one product (power iterations)               */
+#define XEOFS_ALGO_TF32X3 3 /* tcgen05 kind::tf32, hi/lo split, 3 products (~fp32 accuracy)     */
+#define XEOFS_ALGO_AUTO_FAST 4 /* TF32X1 where the tcgen05 path applies, else SIMT (power iterations) */
+
+/* flags for xeofs_b200_scaling_finalize */
+#define XEOFS_F_CENTER 1
+#define XEOFS_F_STANDARDIZE 2
+
+int xeofs_b200_version(void);
+const char* xeofs_b200_last_error(void);
+/* 1 if the running device is sm_100 and the tcgen05 kernels can be used */
+int xeofs_b200_has_tcgen05(void);
+
+/* ---- P1/P4/P5: one streaming pass of column statistics -------------------------------------------
+ * Replaces Scaler.fit's X.mean / X.std (preprocessing/scaler.py:100-108), Sanitizer's three notnull
+ * reductions (preprocessing/sanitizer.py:46-56) and feeds total_variance (utils/xarray_utils.py:236-253).
+ * Outputs (caller zero-initialises nothing; the call clears them):
+ *   shift[S]   fp32  the per-column shift used for the sums (first row, 0 where that is NaN)
+ *   sum[S]     fp64  sum over non-NaN t of (x - shift)
+ *   sumsq[S]   fp64  sum over non-NaN t of (x - shift)^2
+ *   cnt[S]     i32   number of non-NaN samples
+ *   row_nan[T] i32   number of NaN features in each sample                                            */
+int xeofs_b200_col_stats(const float* X, int64_t T, int64_t S, int64_t ldx, float* shift, double* sum,
+                         double* sumsq, int32_t* cnt, int32_t* row_nan, void* stream);
+
+/* ---- Scaler.fit tail + what Scaler.transform needs (preprocessing/scaler.py:100-153) -------------
+ * From the raw statistics: mean (fp32), std (ddof 0, clipped at FLT_EPSILON, fp32), valid mask, and the
+ * three vectors the streaming kernels consume.  featw[S] = coslat*weights per feature (NULL = 1).
+ * scalars_out[0] = total variance  sum_s dscale^2 * M2_s / (cnt_s - 1)   (utils/xarray_utils.py:236-253)
+ * scalars_out[1] = number of valid features, scalars_out[2] = max cnt, scalars_out[3] = min cnt over valid.  */
+int xeofs_b200_scaling_finalize(int64_t S, const float* shift, const double* sum, const double* sumsq,
+                                const int32_t* cnt, const double* featw, int flags, float* mean, float* std,
+                                uint8_t* valid, float* pivot, float* dscale, float* ccorr,
+                                double* scalars_out, void* stream);
+
+/* ---- D2: the tall-skinny products of the randomized range finder ---------------------------------
+ * sklearn.utils.extmath.randomized_range_finder's  M @ Q  and  M.T @ Q  (called from
+ * linalg/decomposer.py:141-146), and cpcca.py:204-205's X.Q, with the Scaler arithmetic
+ * (scaler.py:146-153) folded into the operand load so X is read once per pass.
+ *
+ * project_S:  Yt[j,s] = sum_t A[t,s] * W[t,j]          (A^T W, output space-side,  lp x S)
+ * project_T:  Z[t,j]  = sum_s A[t,s] * Yt[j,s]         (A Y,   output time-side,   T x lp)
+ * l is the live column count, lp = round_up(l,16) the stored one.                                    */
+int64_t xeofs_b200_project_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo);
+int xeofs_b200_project_S(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
+                         const float* dscale, const float* ccorr, const float* W, int64_t ldw, int64_t l,
+                         float* Yt, int64_t ldy, void* workspace, int64_t workspace_bytes, int algo,
+                         void* stream);
+int xeofs_b200_project_T(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
+                         const float* dscale, const float* ccorr, const float* Yt, int64_t ldy, int64_t l,
+                         float* Z, int64_t ldz, void* workspace, int64_t workspace_bytes, int algo,
+                         void* stream);
+
+/* ---- D2: the k-column orthonormalisation (sklearn's LU / QR normalizers) as CholeskyQR -----------
+ * gram:      G[i,j] (+)= sum_n M(n,i) M(n,j), fp64, l x l row-major.  side 0: M is time-side (n x ld),
+ *            side 1: M is space-side (lp x ld, n along the contiguous axis).  accumulate=0 clears G first.
+ * chol_inv:  G = R^T R (upper R);  Rinv = R^-1 (l x l fp64 row-major, upper).  A column whose pivot falls
+ *            below the fp32 noise floor of G (4 eps32^2 G[k][k]) is linearly dependent to working precision and
+ *            is dropped: its column of Rinv is zero.  info[0] = number of dropped columns, info[1] = 1 if a
+ *            non-finite pivot was met (numpy.linalg.LinAlgError at the boundary, decomposer.py:265-270).
+ * apply:     Out(n, j') = sum_j In(n, j) * Mat[j, j'] * colscale[j']   for j < l, j' < k; Mat is l x k fp64
+ *            row-major (ldm), colscale NULL = 1.  side as in gram; In/Out may alias only if identical.    */
+int xeofs_b200_gram(const float* M, int64_t n, int64_t l, int64_t ld, int side, double* G, int accumulate,
+                    void* stream);
+int xeofs_b200_chol_inv(const double* G, int64_t l, double* Rinv, int32_t* info, void* stream);
+int xeofs_b200_apply(const float* In, int64_t n, int64_t l, int64_t ld_in, int side, const double* Mat,
+                     int64_t ldm, int64_t k, const double* colscale, float* Out, int64_t ld_out, void* stream);
+
+/* ---- D2/D3: the small SVD and the sign rule ------------------------------------------------------
+ * sym_eig: cyclic Jacobi on the l x l Gram (replaces scipy.linalg.svd(B) inside randomized_svd via
+ *          B B^T = U diag(s^2) U^T).  evals[l] descending, evecs l x l row-major with eigenvector i in
+ *          COLUMN i.  work: l*l doubles.
+ * row_minmax: per row of a (k x n) matrix the max and the min (utils/xarray_utils.py:273-301 needs both).
+ * finish_components: Vt[m,s] = valid[s] ? sign[m] * Vt[m,s] : NaN   (decomposer.py:219-222 and
+ *          sanitizer.py:128-153's reindex).                                                          */
+int xeofs_b200_sym_eig(const double* G, int64_t l, double* evals, double* evecs, double* work, int32_t* info,
+                       void* stream);
+int xeofs_b200_row_minmax(const float* Vt, int64_t k, int64_t n, int64_t ld, float* vmax, float* vmin,
+                          void* stream);
+int xeofs_b200_finish_components(float* Vt, int64_t k, int64_t n, int64_t ld, const float* sign,
+                                 const uint8_t* valid, void* stream);
+
+/* ---- R1: one varimax/promax sweep over the loadings (linalg/_numpy/_rotation.py:57-62, 166-177) ----
+ * L is space-side (mp x S, mode-major), rownorm[S] the Kaiser normaliser 1/(h+eps) (NULL = 1).
+ * With B = diag(rownorm) L^T R (S x m) and Ln = diag(rownorm) L^T:
+ *   Gout[i,j] (+)= sum_s Ln[s,i] * f(B[s,j]),   f(b) = (b c_j) |b c_j|^(power-1),  c = colscale (NULL = 1)
+ *   Wout[j]   (+)= sum_s B[s,j]^2,              absmax[j] = max_s |B[s,j]|  (fp32, may be NULL)
+ * varimax: power = 3, colscale NULL; the caller forms G = Gout - (gamma/S) (Ln^T Ln) R diag(W).
+ * promax target regression: power = p, colscale = 1/absmax, caller forms R^T Gout = Z^T P.               */
+int xeofs_b200_varimax_accumulate(const float* L, int64_t S, int64_t m, int64_t ld, const float* rownorm,
+                                  const double* R, double power, const double* colscale, double* Gout,
+                                  double* Wout, float* absmax, int accumulate, void* stream);
+/* Kaiser norms (_rotation.py:155-160): h[s] = sqrt(sum_j L[j,s]^2); rownorm[s] = 1/(h+eps);
+ * Ln[j,s] = L[j,s] * rownorm[s] (space-side, ldn >= S).  Any of h / rownorm / Ln may be NULL.             */
+int xeofs_b200_col_norms(const float* L, int64_t S, int64_t m, int64_t ld, float* h, float* rownorm, float* Ln,
+                         int64_t ldn, void* stream);
+
+/* ---- (f1) EOF.inverse_transform (single/eof.py:134-156 + scaler.py:165-190 + sanitizer.py:128-153) ----------
+ * out[t,s] = (sum_i scores[t,i] * Vt[modes[i], s] - ccorr[s]) / dscale[s] + pivot[s], NaN where valid[s] == 0.
+ * scores T x lds (time-side), Vt space-side (rows = modes), modes[m] int32 row indices into Vt.              */
+int xeofs_b200_reconstruct(const float* scores, int64_t T, int64_t lds, const float* Vt, int64_t S, int64_t ldv,
+                           const int32_t* modes, int64_t m, const float* pivot, const float* dscale,
+                           const float* ccorr, const uint8_t* valid, float* out, int64_t ldo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XEOFS_B200_H */

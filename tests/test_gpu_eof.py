@@ -1,0 +1,106 @@
+"""GPU parity: xeofs_b200.single.EOF through the C-ABI against the oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): singular values and explained_variance_ratio rtol 1e-4; components and
+scores equal up to the reference's own sign rule (so compared directly), |<v_ref, v>| >= 1 - 1e-4 per mode.
+"""
+import numpy as np
+import pytest
+
+from _inputs import MOCK_LAT, MOCK_LON, mock_data_array, planted
+from oracle import eof as oeof
+
+pytestmark = pytest.mark.gpu
+
+DIMS = ("time", "lat", "lon")
+RTOL_S = 1e-4
+
+
+def _fit_both(X, coords, k, **kw):
+    import xeofs_b200 as xb
+    o = oeof.eof_fit(X, DIMS, "time", coords=coords, n_modes=k, **kw)
+    m = xb.single.EOF(n_modes=k, **kw).fit(xb.DataArray(X, DIMS, coords), dim="time")
+    return o, m
+
+
+def _compare(o, m, k, vec_tol=1e-4, elem_atol=2e-3):
+    s = m.singular_values().values
+    np.testing.assert_allclose(s, o["singular_values"], rtol=RTOL_S)
+    np.testing.assert_allclose(m.explained_variance_ratio().values, o["explained_variance_ratio"], rtol=RTOL_S)
+    np.testing.assert_allclose(m.total_variance(), o["total_variance"], rtol=1e-5)
+    comps = m.components().values
+    assert comps.shape == o["components"].shape
+    np.testing.assert_array_equal(np.isnan(comps), np.isnan(o["components"]))
+    vf = o["fitted"]["is_valid_feature"]
+    V = comps.reshape(-1, k)[vf]
+    Vo = o["components_2d"]
+    dots = (V * Vo).sum(axis=0)          # same sign rule on both sides -> positive and ~1
+    assert (dots >= 1 - vec_tol).all(), dots
+    sc = m.scores().values.reshape(-1, k)
+    vs = o["fitted"]["is_valid_sample"]
+    np.testing.assert_allclose(sc[vs], o["scores"], atol=elem_atol * np.abs(o["scores"]).max(axis=0))
+    assert np.isnan(sc[~vs]).all()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(standardize=True), dict(standardize=True, use_coslat=True),
+                                dict(center=False)])
+@pytest.mark.parametrize("k", [3, 10, 18])
+def test_mock_data_array(kw, k):
+    """The reference's canonical 25x5x4 fixture (tests/conftest.py:225-240); k=18 takes the exact policy."""
+    X = mock_data_array().astype(np.float32)
+    o, m = _fit_both(X, {"lat": MOCK_LAT, "lon": MOCK_LON}, k, random_state=5, **kw)
+    _compare(o, m, k, vec_tol=1e-3, elem_atol=5e-3)
+
+
+def test_planted_config1_shape():
+    """BASELINE configs[0]: EOF n_modes=10 on 2920 x (25 x 53) fp32 (T > S: no transpose in the range finder)."""
+    T, nlat, nlon, k = 2920, 25, 53, 10
+    X = planted(T, nlat * nlon, 2 * k, seed=0).reshape(T, nlat, nlon)
+    coords = {"lat": np.linspace(75, 15, nlat), "lon": np.arange(nlon) * 2.5}
+    o, m = _fit_both(X, coords, k, random_state=5, use_coslat=True)
+    _compare(o, m, k)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(standardize=True, use_coslat=True)])
+def test_planted_wide_with_land_mask(kw):
+    """T < S (sklearn transposes), n_iter=4 as in configs[1], 10 % of the columns all-NaN (Sanitizer)."""
+    T, nlat, nlon, k = 600, 40, 90, 12
+    X = planted(T, nlat * nlon, 2 * k, seed=1).reshape(T, nlat, nlon)
+    rng = np.random.default_rng(9)
+    land = rng.random((nlat, nlon)) < 0.1
+    X[:, land] = np.nan
+    X[17] = np.nan  # a fully missing sample is dropped too
+    coords = {"lat": np.linspace(88, -88, nlat), "lon": np.arange(nlon) * 4.0}
+    o, m = _fit_both(X, coords, k, random_state=5, solver_kwargs={"n_iter": 4}, **kw)
+    _compare(o, m, k)
+
+
+def test_isolated_nan_raises():
+    import xeofs_b200 as xb
+    X = mock_data_array().astype(np.float32)
+    X[3, 2, 1] = np.nan
+    with pytest.raises(ValueError, match="partial NaN"):
+        xb.single.EOF(n_modes=2).fit(xb.DataArray(X, DIMS, {"lat": MOCK_LAT, "lon": MOCK_LON}), dim="time")
+
+
+def test_n_modes_exceeds_rank_raises():
+    import xeofs_b200 as xb
+    X = mock_data_array().astype(np.float32)
+    with pytest.raises(ValueError, match="rank"):
+        xb.single.EOF(n_modes=21).fit(xb.DataArray(X, DIMS), dim="time")
+
+
+def test_transform_and_inverse_transform():
+    """tests/models/single/test_eof.py:364-408 (transform(data) == scores, rtol 1e-3) and :455-488 (full-rank
+    reconstruction)."""
+    import xeofs_b200 as xb
+    X = mock_data_array().astype(np.float32)
+    coords = {"lat": MOCK_LAT, "lon": MOCK_LON}
+    da = xb.DataArray(X, DIMS, coords)
+    m = xb.single.EOF(n_modes=20, standardize=True, use_coslat=True, solver="full").fit(da, dim="time")
+    sc = m.scores()
+    np.testing.assert_allclose(m.transform(da).values, sc.values, rtol=1e-3, atol=1e-4)
+    rec = m.inverse_transform(sc)
+    assert rec.dims == DIMS
+    np.testing.assert_allclose(rec.values, X, rtol=1e-4)
+    o = oeof.eof_fit(X, DIMS, "time", coords=coords, n_modes=20, standardize=True, use_coslat=True, solver="full")
+    np.testing.assert_allclose(m.singular_values().values[:19], o["singular_values"][:19], rtol=RTOL_S)

@@ -1,0 +1,161 @@
+"""GPU: every C-ABI kernel against a float64 numpy/torch statement of the same operation."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from xeofs_b200._cuda_ops import CudaOps
+    return CudaOps(algo="simt")
+
+
+def _field(ops, X, featw=None, center=True, standardize=False):
+    from xeofs_b200._cuda_ops import Field
+    Xd = torch.as_tensor(X, dtype=torch.float32).cuda()
+    st = ops.col_stats(Xd)
+    fw = None if featw is None else torch.as_tensor(featw, dtype=torch.float64).cuda()
+    fin = ops.scaling_finalize(st, fw, center, standardize)
+    return Field(Xd, fin["pivot"], fin["dscale"], fin["ccorr"], fin["valid"], fin["mean"], fin["std"]), st, fin
+
+
+def _A_ref(X, featw=None, center=True, standardize=False):
+    X = X.astype(np.float64)
+    A = X.copy()
+    if center:
+        A = A - np.nanmean(X, axis=0)
+    if standardize:
+        A = A / np.clip(np.nanstd(X, axis=0).astype(np.float32), np.finfo(np.float32).eps, None)
+    if featw is not None:
+        A = A * featw
+    return A
+
+
+@pytest.mark.parametrize("T,S", [(25, 20), (300, 1001), (1000, 4096), (77, 130)])
+@pytest.mark.parametrize("standardize", [False, True])
+def test_col_stats_and_scaling(ops, T, S, standardize):
+    rng = np.random.default_rng(T * S)
+    X = (280 + 3 * rng.standard_normal((T, S))).astype(np.float32)
+    X[:, 3] = np.nan
+    if S > 100:
+        X[:, 97] = np.nan
+    featw = rng.uniform(0.5, 1.5, S)
+    f, st, fin = _field(ops, X, featw, True, standardize)
+    mean_ref = np.nanmean(X.astype(np.float64), axis=0)
+    valid = ~np.isnan(X).all(axis=0)
+    np.testing.assert_array_equal(fin["valid"].cpu().numpy().astype(bool), valid)
+    np.testing.assert_allclose(fin["mean"].cpu().numpy()[valid], mean_ref[valid], rtol=2e-7)
+    std_ref = np.nanstd(X.astype(np.float64), axis=0)
+    np.testing.assert_allclose(fin["std"].cpu().numpy()[valid], std_ref[valid], rtol=1e-5)
+    A = _A_ref(X, featw, True, standardize)[:, valid]
+    tv = np.var(A, axis=0, ddof=1).sum()
+    sc = fin["scalars"].cpu().numpy()
+    np.testing.assert_allclose(sc[0], tv, rtol=1e-5)
+    assert int(sc[1]) == valid.sum() and int(sc[2]) == T and int(sc[3]) == T
+    rn = st["row_nan"].cpu().numpy()
+    assert (rn == (~valid).sum()).all()
+
+
+@pytest.mark.parametrize("T,S,l", [(25, 20, 12), (300, 1001, 20), (1000, 4096, 60), (520, 777, 110), (64, 130, 5)])
+@pytest.mark.parametrize("center", [True, False])
+def test_project_simt(ops, T, S, l, center):
+    from xeofs_b200._lib import lpad
+    rng = np.random.default_rng(l)
+    X = (280 + 3 * rng.standard_normal((T, S))).astype(np.float32)
+    X[:, 1] = np.nan
+    featw = rng.uniform(0.5, 1.5, S)
+    f, st, fin = _field(ops, X, featw, center, True)
+    A = np.nan_to_num(_A_ref(X, featw, center, True), nan=0.0)
+    lp = lpad(l)
+    W = np.zeros((T, lp), np.float32)
+    W[:, :l] = rng.standard_normal((T, l))
+    Yt = ops.project_S(f, torch.from_numpy(W).cuda(), l).cpu().numpy()
+    ref = (A.T @ W[:, :l].astype(np.float64)).T
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(Yt[:l], ref, atol=2e-5 * scale)
+    assert (Yt[l:] == 0).all()
+    Y = np.zeros((lp, S), np.float32)
+    Y[:l] = rng.standard_normal((l, S))
+    Z = ops.project_T(f, torch.from_numpy(Y).cuda(), l).cpu().numpy()
+    ref = A @ Y[:l].astype(np.float64).T
+    np.testing.assert_allclose(Z[:, :l], ref, atol=2e-5 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("n,l,side", [(1000, 20, 0), (5000, 60, 1), (333, 110, 1), (40, 7, 0), (100000, 33, 1)])
+def test_gram_chol_apply(ops, n, l, side):
+    from xeofs_b200._lib import lpad
+    rng = np.random.default_rng(n + l)
+    M = rng.standard_normal((n, l)) @ np.diag(np.logspace(0, -3, l)) @ rng.standard_normal((l, l))
+    lp = lpad(l)
+    buf = np.zeros((n, lp) if side == 0 else (lp, n), np.float32)
+    if side == 0:
+        buf[:, :l] = M
+    else:
+        buf[:l] = M.T
+    Md = torch.from_numpy(buf).cuda()
+    M32 = (buf[:, :l] if side == 0 else buf[:l].T).astype(np.float64)
+    G = ops.gram(Md, n, l, side)
+    np.testing.assert_allclose(G.cpu().numpy(), M32.T @ M32, rtol=1e-10, atol=1e-10 * np.abs(M32.T @ M32).max())
+    Rinv, info = ops.chol_inv(G)
+    assert info.cpu().numpy().tolist() == [0, 0]
+    R = np.linalg.cholesky(M32.T @ M32).T
+    np.testing.assert_allclose(Rinv.cpu().numpy(), np.linalg.inv(R), rtol=1e-6, atol=1e-8 * np.abs(np.linalg.inv(R)).max())
+    Q = ops.apply(Md, n, l, side, Rinv, l)
+    Q = ops.apply(Q, n, l, side, *ops.chol_inv(ops.gram(Q, n, l, side))[:1], l)  # second pass
+    Qh = Q.cpu().numpy()
+    Qh = Qh[:, :l] if side == 0 else Qh[:l].T
+    np.testing.assert_allclose(Qh.T @ Qh, np.eye(l), atol=5e-6)
+
+
+def test_chol_drops_dependent_columns(ops):
+    rng = np.random.default_rng(0)
+    M = rng.standard_normal((500, 8)).astype(np.float32)
+    M[:, 5] = M[:, 1] + M[:, 2]      # exactly dependent in fp32 up to rounding
+    M[:, 7] = 0
+    Md = torch.zeros((500, 16), device="cuda")
+    Md[:, :8] = torch.from_numpy(M).cuda()
+    G = ops.gram(Md, 500, 8, 0)
+    Rinv, info = ops.chol_inv(G)
+    assert info.cpu().numpy().tolist() == [2, 0]
+    Q = ops.apply(Md, 500, 8, 0, Rinv, 8).cpu().numpy()[:, :8]
+    assert np.abs(Q[:, 5]).max() == 0 and np.abs(Q[:, 7]).max() == 0
+    keep = [0, 1, 2, 3, 4, 6]
+    np.testing.assert_allclose(Q[:, keep].T @ Q[:, keep], np.eye(6), atol=1e-5)
+
+
+@pytest.mark.parametrize("l", [2, 5, 30, 60, 110, 128])
+def test_sym_eig(ops, l):
+    rng = np.random.default_rng(l)
+    B = rng.standard_normal((l, 3 * l)) * np.logspace(0, -4, l)[:, None]
+    G = B @ B.T
+    ev, V = ops.sym_eig(torch.from_numpy(G).cuda())
+    ev, V = ev.cpu().numpy(), V.cpu().numpy()
+    ref = np.linalg.eigvalsh(G)[::-1]
+    np.testing.assert_allclose(ev, ref, rtol=1e-9, atol=1e-14 * ref[0])
+    np.testing.assert_allclose(V.T @ V, np.eye(l), atol=1e-12)
+    np.testing.assert_allclose(V @ np.diag(ev) @ V.T, G, atol=1e-12 * ref[0])
+
+
+def test_minmax_finish_reconstruct(ops):
+    rng = np.random.default_rng(3)
+    k, S, T = 7, 1000, 90
+    Vt = rng.standard_normal((16, S)).astype(np.float32)
+    Vd = torch.from_numpy(Vt).cuda()
+    mx, mn = ops.row_minmax(Vd, k, S)
+    np.testing.assert_array_equal(mx.cpu().numpy(), Vt[:k].max(axis=1))
+    np.testing.assert_array_equal(mn.cpu().numpy(), Vt[:k].min(axis=1))
+    sign = torch.tensor([1, -1, 1, -1, -1, 1, 1], dtype=torch.float32).cuda()
+    ops.finish_components(Vd, k, S, sign, None)
+    np.testing.assert_array_equal(Vd.cpu().numpy()[:k], Vt[:k] * sign.cpu().numpy()[:, None])
+    X = (5 + rng.standard_normal((T, S))).astype(np.float32)
+    X[:, 10] = np.nan
+    f, st, fin = _field(ops, X, None, True, True)
+    sc = rng.standard_normal((T, 3)).astype(np.float32)
+    rec = ops.reconstruct(f, torch.from_numpy(sc).cuda(), Vd, [0, 2, 5]).cpu().numpy()
+    V = Vd.cpu().numpy()[[0, 2, 5]].astype(np.float64)
+    ref = (sc.astype(np.float64) @ V) * np.nanstd(X.astype(np.float64), axis=0) + np.nanmean(X.astype(np.float64), axis=0)
+    assert np.isnan(rec[:, 10]).all()
+    ok = np.arange(S) != 10
+    np.testing.assert_allclose(rec[:, ok], ref[:, ok], rtol=1e-5, atol=1e-5)

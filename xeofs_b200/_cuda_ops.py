@@ -1,0 +1,203 @@
+"""Thin Python layer over the C-ABI: allocates torch CUDA tensors and passes raw pointers.
+
+Nothing here computes on the host; every method enqueues kernels of libxeofs_b200.so on the current
+torch CUDA stream.  ``CudaOps`` is the only implementation the product ships (tests inject a numpy
+test double with the same interface to exercise the host logic on CPU boxes).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, lpad, ptr
+
+
+class Field:
+    """One preprocessed field resident in HBM: raw X (T x S fp32, row-major) plus the per-feature
+    vectors that fold Scaler.transform (preprocessing/scaler.py:146-153) into the operand load:
+    A[t,s] = (X[t,s] - pivot[s]) * dscale[s] + ccorr[s]."""
+
+    def __init__(self, X, pivot, dscale, ccorr, valid, mean=None, std=None):
+        self.X = X
+        self.T, self.S = int(X.shape[0]), int(X.shape[1])
+        self.ldx = int(X.stride(0))
+        self.pivot, self.dscale, self.ccorr = pivot, dscale, ccorr
+        self.valid = valid
+        self.mean, self.std = mean, std
+
+
+class CudaOps:
+    name = "cuda"
+
+    def __init__(self, device=None, algo="auto"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("xeofs_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback.")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        a = _lib.ALGO_NAMES[algo] if isinstance(algo, str) else int(algo)
+        # algo: arithmetic of the power-iteration products; accurate_algo: of the two products the singular
+        # values are read from (the final range basis and B = Q^T M)
+        if a == _lib.ALGO_AUTO:
+            self.algo, self.accurate_algo = _lib.ALGO_AUTO_FAST, _lib.ALGO_AUTO
+        elif a == _lib.ALGO_TF32X1:
+            self.algo, self.accurate_algo = _lib.ALGO_TF32X1, _lib.ALGO_TF32X3
+        else:
+            self.algo = self.accurate_algo = a
+        self._ws = None
+        self.launches = 0  # kernels enqueued through this object (bench.py reports it)
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return _lib.C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype=torch.float32):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def to_device(self, a, dtype=None):
+        t = torch.as_tensor(a)
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=True)
+
+    def workspace(self, T, S, l, algo):
+        need = int(self.lib.xeofs_b200_project_workspace_bytes(T, S, l, algo))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------ preprocessing
+    def col_stats(self, X):
+        T, S = int(X.shape[0]), int(X.shape[1])
+        st = {
+            "shift": self.empty(S), "sum": self.empty(S, torch.float64), "sumsq": self.empty(S, torch.float64),
+            "cnt": self.empty(S, torch.int32), "row_nan": self.empty(T, torch.int32),
+        }
+        check(self.lib.xeofs_b200_col_stats(ptr(X), T, S, int(X.stride(0)), ptr(st["shift"]), ptr(st["sum"]),
+                                            ptr(st["sumsq"]), ptr(st["cnt"]), ptr(st["row_nan"]), self._stream()),
+              "col_stats")
+        self.launches += 5
+        return st
+
+    def scaling_finalize(self, st, featw, center, standardize):
+        S = int(st["shift"].shape[0])
+        out = {
+            "mean": self.empty(S), "std": self.empty(S), "valid": self.empty(S, torch.uint8),
+            "pivot": self.empty(S), "dscale": self.empty(S), "ccorr": self.empty(S),
+            "scalars": self.empty(4, torch.float64),
+        }
+        flags = (_lib.F_CENTER if center else 0) | (_lib.F_STANDARDIZE if standardize else 0)
+        check(self.lib.xeofs_b200_scaling_finalize(S, ptr(st["shift"]), ptr(st["sum"]), ptr(st["sumsq"]),
+                                                   ptr(st["cnt"]), ptr(featw), flags, ptr(out["mean"]),
+                                                   ptr(out["std"]), ptr(out["valid"]), ptr(out["pivot"]),
+                                                   ptr(out["dscale"]), ptr(out["ccorr"]), ptr(out["scalars"]),
+                                                   self._stream()), "scaling_finalize")
+        self.launches += 2
+        return out
+
+    # ------------------------------------------------------------------ streaming products
+    def project_S(self, f: Field, W, l, algo=None, out=None):
+        """Yt (lp x S) = A^T W,  W time-side (T x lp)."""
+        algo = self.algo if algo is None else algo
+        lp = lpad(l)
+        Yt = out if out is not None else self.empty((lp, f.S))
+        ws = self.workspace(f.T, f.S, l, algo)
+        check(self.lib.xeofs_b200_project_S(ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr),
+                                            ptr(W), int(W.stride(0)), l, ptr(Yt), int(Yt.stride(0)), ptr(ws),
+                                            ws.numel(), algo, self._stream()), "project_S")
+        self.launches += 2
+        return Yt
+
+    def project_T(self, f: Field, Yt, l, algo=None, out=None):
+        """Z (T x lp) = A Y,  Y space-side (lp x S)."""
+        algo = self.algo if algo is None else algo
+        lp = lpad(l)
+        Z = out if out is not None else self.empty((f.T, lp))
+        ws = self.workspace(f.T, f.S, l, algo)
+        check(self.lib.xeofs_b200_project_T(ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr),
+                                            ptr(Yt), int(Yt.stride(0)), l, ptr(Z), int(Z.stride(0)), ptr(ws),
+                                            ws.numel(), algo, self._stream()), "project_T")
+        self.launches += 2 + (2 if f.ccorr is not None else 0)
+        return Z
+
+    # ------------------------------------------------------------------ k-column linear algebra
+    def gram(self, M, n, l, side, out=None, accumulate=False):
+        G = out if out is not None else self.empty((l, l), torch.float64)
+        check(self.lib.xeofs_b200_gram(ptr(M), n, l, int(M.stride(0)), side, ptr(G), int(accumulate), self._stream()),
+              "gram")
+        self.launches += 2
+        return G
+
+    def chol_inv(self, G, info=None):
+        l = int(G.shape[0])
+        Rinv = self.empty((l, l), torch.float64)
+        info = info if info is not None else self.empty(1, torch.int32)
+        check(self.lib.xeofs_b200_chol_inv(ptr(G), l, ptr(Rinv), ptr(info), self._stream()), "chol_inv")
+        self.launches += 1
+        return Rinv, info
+
+    def apply(self, In, n, l, side, Mat, k, colscale=None, out=None):
+        """Out(n, j') = sum_j In(n, j) Mat[j, j'] colscale[j'];  same side/layout as In, kp = lpad(k) columns."""
+        kp = lpad(k)
+        if out is None:
+            out = self.empty((kp, n)) if side == 1 else self.zeros((n, kp))
+        check(self.lib.xeofs_b200_apply(ptr(In), n, l, int(In.stride(0)), side, ptr(Mat), int(Mat.stride(0)), k,
+                                        ptr(colscale), ptr(out), int(out.stride(0)), self._stream()), "apply")
+        self.launches += 1
+        return out
+
+    def sym_eig(self, G):
+        l = int(G.shape[0])
+        evals = self.empty(l, torch.float64)
+        evecs = self.empty((l, l), torch.float64)
+        work = self.empty((l + 1) * (l + 1), torch.float64)
+        info = self.empty(1, torch.int32)
+        check(self.lib.xeofs_b200_sym_eig(ptr(G), l, ptr(evals), ptr(evecs), ptr(work), ptr(info), self._stream()),
+              "sym_eig")
+        self.launches += 1
+        return evals, evecs
+
+    def row_minmax(self, Vt, k, n):
+        vmax, vmin = self.empty(k), self.empty(k)
+        check(self.lib.xeofs_b200_row_minmax(ptr(Vt), k, n, int(Vt.stride(0)), ptr(vmax), ptr(vmin), self._stream()),
+              "row_minmax")
+        self.launches += 2
+        return vmax, vmin
+
+    def finish_components(self, Vt, k, n, sign, valid):
+        check(self.lib.xeofs_b200_finish_components(ptr(Vt), k, n, int(Vt.stride(0)), ptr(sign), ptr(valid),
+                                                    self._stream()), "finish_components")
+        self.launches += 1
+
+    def reconstruct(self, f: Field, scores, Vt, modes):
+        """(T x S) = scores . V^T un-scaled (EOF.inverse_transform)."""
+        T, m = int(scores.shape[0]), int(scores.shape[1])
+        scores = scores.contiguous()
+        idx = torch.as_tensor(modes, dtype=torch.int32).to(self.device)
+        out = self.empty((T, f.S))
+        check(self.lib.xeofs_b200_reconstruct(ptr(scores), T, int(scores.stride(0)), ptr(Vt), f.S, int(Vt.stride(0)),
+                                              ptr(idx), m, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr), ptr(f.valid),
+                                              ptr(out), int(out.stride(0)), self._stream()), "reconstruct")
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ rotation
+    def col_norms(self, L, S, m, normalized_out=False):
+        h, rn = self.empty(S), self.empty(S)
+        Ln = self.zeros((lpad(m), S)) if normalized_out else None
+        check(self.lib.xeofs_b200_col_norms(ptr(L), S, m, int(L.stride(0)), ptr(h), ptr(rn), ptr(Ln),
+                                            S if Ln is None else int(Ln.stride(0)), self._stream()), "col_norms")
+        self.launches += 1
+        return h, rn, Ln
+
+    def varimax_accumulate(self, L, S, m, R, power=3.0, colscale=None, want_absmax=False):
+        G = self.empty((m, m), torch.float64)
+        Wv = self.empty(m, torch.float64)
+        amax = self.empty(m) if want_absmax else None
+        check(self.lib.xeofs_b200_varimax_accumulate(ptr(L), S, m, int(L.stride(0)), None, ptr(R), float(power),
+                                                     ptr(colscale), ptr(G), ptr(Wv), ptr(amax), 0, self._stream()),
+              "varimax_accumulate")
+        self.launches += 3
+        return G, Wv, amax

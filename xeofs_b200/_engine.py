@@ -1,0 +1,286 @@
+"""Host-side driver of the device kernels: preprocessing state, the randomized range finder and the small
+SVD that follows it.  Nothing here touches array *values* on the host except k-length vectors.
+
+What it stands in for (all paths under /root/reference/xeofs):
+  preprocessing/scaler.py:69-154 + sanitizer.py:46-124      -> fit_field()
+  linalg/decomposer.py:76-226 (policy, randomized_svd call, sign rule, U_/s_/V_)  -> decompose()
+  sklearn.utils.extmath.randomized_svd (third party; call site decomposer.py:141-146) -> randomized_svd()
+
+Layout vocabulary (see include/xeofs_b200.h): a *time-side* matrix is (n x lp) fp32 row-major, a
+*space-side* matrix is (lp x n) fp32 (mode-major).  Side 0 = time, side 1 = space.  With several GPUs the
+space (feature) axis is sharded across ranks, time-side matrices are replicated.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._lib import lpad
+
+MAX_L = 128  # widest k-column block the kernels take
+
+
+# ---------------------------------------------------------------------------------------------- comm
+class Comm:
+    """Feature-axis sharding over torch.distributed.  ``Comm(None)`` is the single-GPU no-op."""
+
+    def __init__(self, group="auto"):
+        import torch.distributed as dist
+
+        self.dist = dist if (dist.is_available() and dist.is_initialized() and group is not None) else None
+        self.group = None if group == "auto" else group
+        self.world = self.dist.get_world_size(self.group) if self.dist else 1
+        self.rank = self.dist.get_rank(self.group) if self.dist else 0
+        self.collectives = 0
+
+    @property
+    def active(self):
+        return self.world > 1
+
+    def _reduce(self, t, op):
+        if self.active:
+            self.dist.all_reduce(t, op=op, group=self.group)
+            self.collectives += 1
+        return t
+
+    def sum_(self, t):
+        return self._reduce(t, self.dist.ReduceOp.SUM) if self.active else t
+
+    def max_(self, t):
+        return self._reduce(t, self.dist.ReduceOp.MAX) if self.active else t
+
+    def min_(self, t):
+        return self._reduce(t, self.dist.ReduceOp.MIN) if self.active else t
+
+
+NO_COMM = Comm(None)
+
+
+# ---------------------------------------------------------------------------------------------- preprocessing
+class FittedField:
+    """Device-resident field plus everything Scaler/Sanitizer would have fitted for it."""
+
+    def __init__(self):
+        self.field = None            # _cuda_ops.Field
+        self.mean = self.std = None  # (S,) fp32 (NaN at invalid features)
+        self.valid = None            # (S,) uint8
+        self.featw = None            # (S,) fp64 coslat*weights or None
+        self.valid_sample = None     # (T,) bool tensor
+        self.n_samples = 0           # T' (samples kept)
+        self.n_features = 0          # S' (features kept, global over ranks)
+        self.total_variance = 0.0
+        self.T = self.S = 0          # local shape
+        self.S_global = 0
+        self.center = self.standardize = False
+
+
+def fit_field(ops, X, featw=None, center=True, standardize=False, check_nans=True, comm=NO_COMM):
+    """One streaming pass of column statistics + the Scaler vectors (scaler.py:100-153), the Sanitizer
+    masks and its isolated-NaN check (sanitizer.py:46-56, 108-122), total variance (utils/xarray_utils.py:236-253).
+
+    X: (T, S_local) fp32 CUDA tensor (row stride arbitrary), featw: (S_local,) fp64 CUDA tensor or None.
+    """
+    from ._cuda_ops import Field
+
+    T, S = int(X.shape[0]), int(X.shape[1])
+    st = ops.col_stats(X)
+    fin = ops.scaling_finalize(st, featw, center, standardize)
+    # scalars: total variance, number of valid features, max / min non-NaN count over valid features
+    sc = fin["scalars"].clone()
+    if comm.active:
+        head = sc[:2].clone()
+        comm.sum_(head)
+        mx = sc[2:3].clone()
+        comm.max_(mx)
+        mn = sc[3:4].clone()
+        comm.min_(mn)
+        sc = torch.cat([head, mx, mn])
+    row_nan = st["row_nan"].to(torch.int64)
+    n_feat_local = torch.tensor([S], dtype=torch.int64, device=row_nan.device)
+    if comm.active:
+        comm.sum_(row_nan)
+        comm.sum_(n_feat_local)
+    S_global = int(n_feat_local.item())
+    sc_h = sc.cpu().numpy()  # the one host sync of the preprocessing
+    total_variance, n_valid = float(sc_h[0]), int(round(sc_h[1]))
+    n_invalid = S_global - n_valid
+    if n_valid == 0:
+        raise ValueError("Input data contains no valid (non-NaN) feature.")
+    # a sample is valid when it holds at least one non-NaN value (sanitizer.py:49-50)
+    valid_sample = row_nan < S_global
+    if check_nans:
+        # sanitizer.py:115-122: every sample has either 0 or all-valid-features non-NaN entries
+        ok = (row_nan == n_invalid) | (row_nan == S_global)
+        if not bool(ok.all().item()):
+            raise ValueError(
+                "Input data contains partial NaN entries, which will cause the the SVD to fail."
+            )
+    n_samples = int(valid_sample.sum().item())
+    ff = FittedField()
+    ff.field = Field(X, fin["pivot"], fin["dscale"], fin["ccorr"], fin["valid"], fin["mean"], fin["std"])
+    ff.mean, ff.std, ff.valid, ff.featw = fin["mean"], fin["std"], fin["valid"], featw
+    ff.valid_sample, ff.n_samples, ff.n_features = valid_sample, n_samples, n_valid
+    ff.total_variance = total_variance
+    ff.T, ff.S, ff.S_global = T, S, S_global
+    ff.center, ff.standardize = center, standardize
+    return ff
+
+
+# ---------------------------------------------------------------------------------------------- operators
+class FieldOperator:
+    """M = A^T when n_samples < n_features (what sklearn's ``transpose='auto'`` does), else M = A."""
+
+    def __init__(self, ops, ff, comm=NO_COMM, algo=None):
+        self.ops, self.ff, self.comm, self.algo = ops, ff, comm, algo
+        self.n_rows_A, self.n_cols_A = ff.n_samples, ff.n_features
+        self.transposed = ff.n_samples < ff.n_features
+        # (global length, local length, side) of M's row and column spaces
+        t_dim, s_dim = (ff.T, ff.T, 0), (ff.S_global, ff.S, 1)
+        self.r, self.c = (s_dim, t_dim) if self.transposed else (t_dim, s_dim)
+        self.shape = (ff.n_features, ff.n_samples) if self.transposed else (ff.n_samples, ff.n_features)
+
+    def _proj_S(self, W, l, algo):
+        return self.ops.project_S(self.ff.field, W, l, algo=algo)
+
+    def _proj_T(self, Yt, l, algo):
+        Z = self.ops.project_T(self.ff.field, Yt, l, algo=algo)
+        self.comm.sum_(Z)
+        return Z
+
+    def mul(self, Q, l, accurate=False):
+        algo = self.ops.accurate_algo if accurate else self.algo
+        return self._proj_S(Q, l, algo) if self.transposed else self._proj_T(Q, l, algo)
+
+    def mul_t(self, Q, l, accurate=False):
+        algo = self.ops.accurate_algo if accurate else self.algo
+        return self._proj_T(Q, l, algo) if self.transposed else self._proj_S(Q, l, algo)
+
+    def sketch_rows(self):
+        """Rows of the Gaussian test matrix: M.shape[1] (global)."""
+        return self.c[0]
+
+
+class CrossOperator:
+    """Implicit cross-covariance C = X^T Y / (n - 1) (cross/cpcca.py:1008-1015) — never materialised:
+    C Q = X^T (Y Q) / (n-1), C^T Q = Y^T (X Q) / (n-1).  M = C^T when S1 < S2 (sklearn's transpose rule)."""
+
+    def __init__(self, ops, fx, fy, comm=NO_COMM, algo=None):
+        self.ops, self.fx, self.fy, self.comm, self.algo = ops, fx, fy, comm, algo
+        if fx.n_samples != fy.n_samples or fx.T != fy.T:
+            raise ValueError(
+                f"Both data matrices must have the same number of samples but found {fx.n_samples} in the "
+                f"first and {fy.n_samples} in the second."
+            )
+        self.scale = 1.0 / (fx.n_samples - 1)
+        self.transposed = fx.n_features < fy.n_features
+        x_dim, y_dim = (fx.S_global, fx.S, 1), (fy.S_global, fy.S, 1)
+        self.r, self.c = (y_dim, x_dim) if self.transposed else (x_dim, y_dim)
+        self.shape = (self.r[0], self.c[0]) if False else (
+            (fy.n_features, fx.n_features) if self.transposed else (fx.n_features, fy.n_features))
+
+    def _through(self, f_in, f_out, Q, l, algo):
+        Z = self.ops.project_T(f_in.field, Q, l, algo=algo)
+        self.comm.sum_(Z)
+        Z.mul_(self.scale)
+        return self.ops.project_S(f_out.field, Z, l, algo=algo)
+
+    def mul(self, Q, l, accurate=False):   # M @ Q, Q on M's column space
+        algo = self.ops.accurate_algo if accurate else self.algo
+        return self._through(self.fx, self.fy, Q, l, algo) if self.transposed else self._through(self.fy, self.fx, Q, l, algo)
+
+    def mul_t(self, Q, l, accurate=False):
+        algo = self.ops.accurate_algo if accurate else self.algo
+        return self._through(self.fy, self.fx, Q, l, algo) if self.transposed else self._through(self.fx, self.fy, Q, l, algo)
+
+    def sketch_rows(self):
+        return self.c[0]
+
+
+# ---------------------------------------------------------------------------------------------- k-column algebra
+def _gram(ops, M, dim, l, comm):
+    G = ops.gram(M, dim[1], l, dim[2])
+    if dim[2] == 1:
+        comm.sum_(G)  # space-side matrices are sharded over ranks
+    return G
+
+
+def orthonormalize(ops, M, dim, l, comm, passes, infos):
+    """CholeskyQR (passes=1: the role of sklearn's LU normalizer; passes=2: its final QR), in place."""
+    for _ in range(passes):
+        G = _gram(ops, M, dim, l, comm)
+        Rinv, info = ops.chol_inv(G)
+        infos.append(info)
+        ops.apply(M, dim[1], l, dim[2], Rinv, l, out=M)
+    return M
+
+
+def sketch_matrix(ops, n_global, n_local, offset, side, l, random_state):
+    """sklearn.utils.extmath.randomized_range_finder: Q = rng.normal(size=(M.shape[1], l)), generated on
+    the host with numpy's RandomState so that the oracle and the device path share the sketch."""
+    rng = random_state if isinstance(random_state, np.random.RandomState) else np.random.RandomState(random_state)
+    Om = rng.normal(size=(n_global, l))[offset:offset + n_local].astype(np.float32)
+    lp = lpad(l)
+    buf = np.zeros((n_local, lp) if side == 0 else (lp, n_local), dtype=np.float32)
+    if side == 0:
+        buf[:, :l] = Om
+    else:
+        buf[:l, :] = Om.T
+    return ops.to_device(buf)
+
+
+def randomized_svd(ops, op, k, n_oversamples=10, n_iter="auto", random_state=None, comm=NO_COMM,
+                   shard_offset=0, Omega=None):
+    """Halko et al. range finder + small SVD, the arithmetic of sklearn.utils.extmath.randomized_svd
+    (power_iteration_normalizer='auto', transpose='auto') with CholeskyQR as the normalizer.
+
+    Returns (Ur, s, Vc, infos): Ur r-side (lp x n or n x lp) left singular vectors of M, s (k,) fp64 device,
+    Vc c-side right singular vectors of M, all un-flipped.
+    """
+    n_r, n_c = op.shape
+    l = min(k + n_oversamples, n_r, n_c)
+    if l > MAX_L:
+        raise NotImplementedError(
+            f"n_modes + n_oversamples = {k + n_oversamples} exceeds the kernels' block width {MAX_L}"
+        )
+    if n_iter == "auto":
+        n_iter = 7 if k < 0.1 * min(n_r, n_c) else 4
+    infos = []
+    if Omega is None:
+        off = shard_offset if op.c[2] == 1 else 0
+        Q = sketch_matrix(ops, op.sketch_rows(), op.c[1], off, op.c[2], l, random_state)
+    else:
+        Q = Omega
+    for _ in range(int(n_iter)):
+        Q = orthonormalize(ops, op.mul(Q, l), op.r, l, comm, 1, infos)
+        Q = orthonormalize(ops, op.mul_t(Q, l), op.c, l, comm, 1, infos)
+    Q = orthonormalize(ops, op.mul(Q, l, accurate=True), op.r, l, comm, 2, infos)   # r-side, orthonormal
+    Bt = op.mul_t(Q, l, accurate=True)                                          # c-side: B^T = M^T Q
+    # svd(B) through the l x l Gram of B^T: B B^T = Uh diag(s^2) Uh^T; V = B^T Uh / s; U = Q Uh
+    G = _gram(ops, Bt, op.c, l, comm)
+    evals, Uh = ops.sym_eig(G)
+    s = torch.sqrt(torch.clamp(evals[:k], min=0.0))
+    inv_s = torch.where(s > 0, 1.0 / s, torch.zeros_like(s))
+    Uh_k = Uh[:, :k].contiguous()
+    Vc = ops.apply(Bt, op.c[1], l, op.c[2], Uh_k, k, colscale=inv_s)
+    Ur = ops.apply(Q, op.r[1], l, op.r[2], Uh_k, k)
+    return Ur, s, Vc, infos
+
+
+def check_infos(infos):
+    """Raise the reference's LinAlgError (decomposer.py:265-270) when a non-finite pivot was met."""
+    if not infos:
+        return
+    flags = torch.stack(infos)[:, 1]
+    if bool(flags.any().item()):
+        raise np.linalg.LinAlgError(
+            "SVD failed: non-finite values met during the decomposition. Check the input for NaN / Inf "
+            "entries that the NaN policy did not remove."
+        )
+
+
+def sign_flip(ops, Vt, k, n, comm):
+    """utils/xarray_utils.py:273-301: +1 where |max| >= |min| over the feature axis, else -1 (fp32 device)."""
+    vmax, vmin = ops.row_minmax(Vt, k, n)
+    comm.max_(vmax)
+    comm.min_(vmin)
+    return torch.where(vmax.abs() >= vmin.abs(), 1.0, -1.0).to(torch.float32)

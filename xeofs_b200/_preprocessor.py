@@ -1,0 +1,155 @@
+"""Host-side mirror of xeofs.preprocessing.Preprocessor for ONE DataArray input
+(preprocessing/preprocessor.py:119-142, 191-354): Scaler -> Stacker -> Sanitizer, with the arithmetic on the
+device (fit_field) and only the label bookkeeping here.
+
+The reference materialises the scaled 2D matrix; here the raw field stays as it is in HBM and the fitted
+per-feature vectors (pivot / dscale / ccorr) are applied inside the streaming kernels.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _labels as L
+from ._engine import NO_COMM, fit_field
+
+
+class Preprocessor:
+    def __init__(self, ops, with_center=True, with_std=False, with_coslat=False, check_nans=True,
+                 sample_name="sample", feature_name="feature", comm=NO_COMM):
+        self.ops, self.comm = ops, comm
+        self.with_center, self.with_std, self.with_coslat = with_center, with_std, with_coslat
+        self.check_nans = check_nans
+        self.sample_name, self.feature_name = sample_name, feature_name
+        self.fitted = None
+
+    # ------------------------------------------------------------------ stacking (stacker.py:157-214)
+    def _to_2d(self, data, dims, fit):
+        """(sample..., feature...) order, flattened to 2D on the device.  A view when the sample dims lead."""
+        if fit:
+            self.sample_dims, self.feature_dims = L.split_dims(dims, self._dim)
+            self.dims_in = tuple(dims)
+        elif tuple(dims) != self.dims_in and set(dims) != set(self.dims_in):
+            raise ValueError(f"Data dimensions {dims} do not match the fitted ones {self.dims_in}.")
+        order = [dims.index(d) for d in self.sample_dims] + [dims.index(d) for d in self.feature_dims]
+        if isinstance(data, torch.Tensor):
+            t = data
+            if t.dtype != torch.float32:
+                t = t.to(torch.float32)
+            if t.device != self.ops.device:
+                t = t.to(self.ops.device, non_blocking=True)
+        else:
+            a = np.asarray(data)
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.ops.device)
+        if order != list(range(len(dims))):
+            t = t.permute(order)
+        ns = len(self.sample_dims)
+        sample_shape, feature_shape = tuple(t.shape[:ns]), tuple(t.shape[ns:])
+        T, S = int(np.prod(sample_shape)), int(np.prod(feature_shape))
+        t2 = t.reshape(T, S)  # copies only when the permutation made it non-viewable
+        if t2.stride(1) != 1 or (T > 1 and t2.stride(0) < S):
+            t2 = t2.contiguous()
+        return t2, sample_shape, feature_shape
+
+    # ------------------------------------------------------------------ fit
+    def fit_transform(self, X, sample_dims, weights=None):
+        data, dims, coords, self.as_xarray = L.unpack(X)
+        self._dim = sample_dims
+        X2, self.sample_shape, self.feature_shape = self._to_2d(data, dims, fit=True)
+        self.coords = {d: coords[d] for d in dims if d in coords}
+        featw = None
+        if self.with_coslat:
+            featw = np.array(L.sqrt_cos_lat_weights(self.feature_dims, self.feature_shape, self.coords), dtype=np.float64)
+        if weights is not None:
+            wdata, wdims, _, _ = L.unpack(weights)
+            w = wdata.detach().cpu().numpy() if isinstance(wdata, torch.Tensor) else np.asarray(wdata)
+            extra = [d for d in wdims if d not in self.feature_dims]
+            if extra:
+                raise ValueError(f"Weights have dimensions {extra} that are not feature dimensions.")
+            # broadcast over the feature dims in data order (scaler.py:116, utils/xarray_utils.py:78-100)
+            shape = [1] * len(self.feature_dims)
+            perm = sorted(range(len(wdims)), key=lambda i: self.feature_dims.index(wdims[i]))
+            w = np.transpose(w, perm)
+            for i, d in enumerate(sorted(wdims, key=self.feature_dims.index)):
+                shape[self.feature_dims.index(d)] = w.shape[i]
+            w = np.broadcast_to(w.reshape(shape).astype(np.float64), self.feature_shape)
+            featw = w if featw is None else featw * w
+        self.featw_host = None if featw is None else np.ascontiguousarray(featw.reshape(-1))
+        featw_dev = None if featw is None else self.ops.to_device(self.featw_host, torch.float64)
+        self.fitted = fit_field(self.ops, X2, featw_dev, center=self.with_center, standardize=self.with_std,
+                                check_nans=self.check_nans, comm=self.comm)
+        return self.fitted
+
+    # ------------------------------------------------------------------ transform of unseen data
+    def transform(self, X):
+        """preprocessor.py:232-259: re-apply the fitted scaling; sanitizer.py:108-113 NaN-pattern check."""
+        from ._cuda_ops import Field
+
+        if self.fitted is None:
+            raise ValueError("The preprocessor has not been fitted.")
+        data, dims, coords, _ = L.unpack(X)
+        X2, sample_shape, feature_shape = self._to_2d(data, dims, fit=False)
+        if feature_shape != self.feature_shape:
+            raise ValueError(f"Feature shape {feature_shape} differs from the fitted one {self.feature_shape}.")
+        ff = self.fitted
+        f = ff.field
+        new = Field(X2, f.pivot, f.dscale, f.ccorr, f.valid, f.mean, f.std)
+        valid_sample = None
+        if self.check_nans:
+            st = self.ops.col_stats(X2)
+            new_valid = st["cnt"] > 0
+            row_nan = st["row_nan"].to(torch.int64)
+            if self.comm.active:
+                self.comm.sum_(row_nan)
+            mism = (new_valid != ff.valid.bool()).any().to(torch.int32)
+            if self.comm.active:
+                self.comm.max_(mism)
+            if bool(mism.item()):
+                raise ValueError("Input data had NaN features in different locations than the original data.")
+            n_invalid = ff.S_global - ff.n_features
+            ok = (row_nan == n_invalid) | (row_nan == ff.S_global)
+            if not bool(ok.all().item()):
+                raise ValueError("Input data contains partial NaN entries, which will cause the the SVD to fail.")
+            valid_sample = row_nan < ff.S_global
+        sample_coords = {d: coords[d] for d in self.sample_dims if d in coords}
+        return new, sample_shape, sample_coords, valid_sample
+
+    # ------------------------------------------------------------------ inverse transforms (labels only)
+    def components_to_nd(self, Vt, k, name="components", nan_invalid=True):
+        """(kp x S) device, mode-major -> DataArray feature_dims + ('mode',); NaN at dropped features
+        (sanitizer.py:128-153 reindex)."""
+        V = Vt[:k].detach().clone()
+        if nan_invalid:
+            V[:, ~self.fitted.valid.bool()] = float("nan")
+        arr = V.t().reshape(*self.feature_shape, k).cpu().numpy()
+        dims = self.feature_dims + ("mode",)
+        coords = dict(self.coords)
+        coords["mode"] = np.arange(1, k + 1)
+        return L.wrap(arr, dims, coords, name, self.as_xarray)
+
+    def scores_to_nd(self, Sc, k, name="scores", sample_shape=None, sample_coords=None, valid_sample=None):
+        sample_shape = self.sample_shape if sample_shape is None else sample_shape
+        Sc = Sc[:, :k].detach().clone()
+        vs = self.fitted.valid_sample if (valid_sample is None and sample_coords is None) else valid_sample
+        if vs is not None:
+            Sc[~vs] = float("nan")
+        arr = Sc.reshape(*sample_shape, k).cpu().numpy()
+        dims = self.sample_dims + ("mode",)
+        coords = dict(self.coords if sample_coords is None else sample_coords)
+        coords["mode"] = np.arange(1, k + 1)
+        return L.wrap(arr, dims, coords, name, self.as_xarray)
+
+    def data_to_nd(self, A2d, sample_shape, sample_coords=None, name="reconstructed_data"):
+        arr = A2d.reshape(*sample_shape, *self.feature_shape)
+        nd_dims = self.sample_dims + self.feature_dims
+        coords = dict(self.coords)
+        if sample_coords is not None:
+            for d in self.sample_dims:
+                coords.pop(d, None)
+            coords.update(sample_coords)
+        # back to the input dim order (stacker.py:216-275)
+        perm = [nd_dims.index(d) for d in self.dims_in]
+        arr = arr.permute(perm) if isinstance(arr, torch.Tensor) else np.transpose(arr, perm)
+        if isinstance(arr, torch.Tensor):
+            arr = arr.cpu().numpy()
+        return L.wrap(arr, self.dims_in, coords, name, self.as_xarray)

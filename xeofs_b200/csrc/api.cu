@@ -1,0 +1,124 @@
+// C-ABI glue: error state, device query, dispatch of the streaming products between the tcgen05 and the
+// SIMT implementations.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace xb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static thread_local int cached_dev = -1, cached = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// project_simt.cu
+int project_S_simt(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const float*,
+                   int64_t, int64_t, float*, int64_t, float*, cudaStream_t);
+int project_T_simt(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const float*,
+                   int64_t, int64_t, float*, int64_t, float*, cudaStream_t);
+// project_tc.cu
+bool tc_supported(int64_t T, int64_t S, int64_t ldx, const float* X, int64_t l);
+int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo);
+int project_S_tc(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const float*,
+                 int64_t, int64_t, float*, int64_t, void*, int64_t, int, cudaStream_t);
+int project_T_tc(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const float*,
+                 int64_t, int64_t, float*, int64_t, void*, int64_t, int, cudaStream_t);
+
+}  // namespace xb
+
+using namespace xb;
+
+extern "C" int xeofs_b200_version(void) { return 100; }
+extern "C" const char* xeofs_b200_last_error(void) { return g_err; }
+
+extern "C" int xeofs_b200_has_tcgen05(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+static int resolve_algo(int algo, int64_t T, int64_t S, int64_t ldx, const float* X, int64_t l) {
+  if (algo == XEOFS_ALGO_AUTO || algo == XEOFS_ALGO_AUTO_FAST) {
+    const bool tc = xeofs_b200_has_tcgen05() && tc_supported(T, S, ldx, X, l);
+    if (!tc) return XEOFS_ALGO_SIMT;
+    return algo == XEOFS_ALGO_AUTO ? XEOFS_ALGO_TF32X3 : XEOFS_ALGO_TF32X1;
+  }
+  return algo;
+}
+
+extern "C" int64_t xeofs_b200_project_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo) {
+  int64_t simt = 2 * lpad(l) * (int64_t)sizeof(float) + 256;
+  int64_t tc = tc_workspace_bytes(T, S, l, algo);
+  return simt > tc ? simt : tc;
+}
+
+static int check_project_args(const char* who, const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
+                              const float* dscale, const void* a, const void* b, int64_t lda, int64_t ldb, int64_t l,
+                              void* ws, int64_t ws_bytes, int algo) {
+  XB_CHECK_ARG(X && pivot && dscale && a && b && ws, "%s: null pointer", who);
+  XB_CHECK_ARG(T > 0 && S > 0 && ldx >= S, "%s: bad field shape T=%lld S=%lld ldx=%lld", who, (long long)T, (long long)S, (long long)ldx);
+  XB_CHECK_ARG(l > 0 && l <= 128, "%s: l=%lld must be in 1..128", who, (long long)l);
+  XB_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0, "%s: leading dimensions of the small matrices must be multiples of 4", who);
+  XB_CHECK_ARG(((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)ws % 256 == 0), "%s: misaligned buffer", who);
+  XB_CHECK_ARG(algo >= XEOFS_ALGO_AUTO && algo <= XEOFS_ALGO_AUTO_FAST, "%s: unknown algo %d", who, algo);
+  if (ws_bytes < xeofs_b200_project_workspace_bytes(T, S, l, algo)) {
+    set_error("%s: workspace too small (%lld < %lld bytes)", who, (long long)ws_bytes,
+              (long long)xeofs_b200_project_workspace_bytes(T, S, l, algo));
+    return XEOFS_E_WORKSPACE;
+  }
+  return XEOFS_OK;
+}
+
+extern "C" int xeofs_b200_project_S(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
+                                    const float* dscale, const float* ccorr, const float* W, int64_t ldw, int64_t l,
+                                    float* Yt, int64_t ldy, void* workspace, int64_t workspace_bytes, int algo,
+                                    void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_project_args("project_S", X, T, S, ldx, pivot, dscale, W, Yt, ldw, ldy, l, workspace, workspace_bytes, algo);
+  if (rc) return rc;
+  XB_CHECK_ARG(ldw >= lpad(l) && ldy >= S, "project_S: ldw=%lld must be >= lp and ldy=%lld >= S", (long long)ldw, (long long)ldy);
+  algo = resolve_algo(algo, T, S, ldx, X, l);
+  if (algo == XEOFS_ALGO_SIMT)
+    return project_S_simt(X, T, S, ldx, pivot, dscale, ccorr, W, ldw, l, Yt, ldy, (float*)workspace, stream);
+  if (!xeofs_b200_has_tcgen05() || !tc_supported(T, S, ldx, X, l)) {
+    set_error("project_S: tcgen05 path unavailable for this device/shape (need sm_100, ldx %% 4 == 0, 16-byte aligned X)");
+    return XEOFS_E_UNSUPPORTED;
+  }
+  return project_S_tc(X, T, S, ldx, pivot, dscale, ccorr, W, ldw, l, Yt, ldy, workspace, workspace_bytes, algo, stream);
+}
+
+extern "C" int xeofs_b200_project_T(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
+                                    const float* dscale, const float* ccorr, const float* Yt, int64_t ldy, int64_t l,
+                                    float* Z, int64_t ldz, void* workspace, int64_t workspace_bytes, int algo,
+                                    void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_project_args("project_T", X, T, S, ldx, pivot, dscale, Yt, Z, ldy, ldz, l, workspace, workspace_bytes, algo);
+  if (rc) return rc;
+  XB_CHECK_ARG(ldz >= lpad(l) && ldy >= S, "project_T: ldz=%lld must be >= lp and ldy=%lld >= S", (long long)ldz, (long long)ldy);
+  algo = resolve_algo(algo, T, S, ldx, X, l);
+  if (algo == XEOFS_ALGO_SIMT)
+    return project_T_simt(X, T, S, ldx, pivot, dscale, ccorr, Yt, ldy, l, Z, ldz, (float*)workspace + lpad(l), stream);
+  if (!xeofs_b200_has_tcgen05() || !tc_supported(T, S, ldx, X, l)) {
+    set_error("project_T: tcgen05 path unavailable for this device/shape (need sm_100, ldx %% 4 == 0, 16-byte aligned X)");
+    return XEOFS_E_UNSUPPORTED;
+  }
+  return project_T_tc(X, T, S, ldx, pivot, dscale, ccorr, Yt, ldy, l, Z, ldz, workspace, workspace_bytes, algo, stream);
+}

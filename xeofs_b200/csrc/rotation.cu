@@ -1,0 +1,171 @@
+// Varimax sweep kernels (R1) — see include/xeofs_b200.h.  Reference: linalg/_numpy/_rotation.py:155-177.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace xb {
+
+// h[s] = ||L[:, s]||_2, rownorm[s] = 1 / (h + eps)   (Kaiser normalisation, _rotation.py:155-160)
+__global__ void col_norms_kernel(const float* __restrict__ L, int64_t S, int m, int64_t ld, float* __restrict__ h,
+                                 float* __restrict__ rownorm, float* __restrict__ Ln, int64_t ldn) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) {
+    double a = 0.0;
+    for (int j = 0; j < m; ++j) {
+      const double v = (double)L[(int64_t)j * ld + s];
+      a = fma(v, v, a);
+    }
+    const float hh = (float)sqrt(a);
+    if (h) h[s] = hh;
+    // the reference adds finfo(float64).eps (its loadings are fp64): only there to keep 0/0 out
+    const float rn = 1.0f / (hh + 2.220446e-16f);
+    if (rownorm) rownorm[s] = rn;
+    if (Ln)
+      for (int j = 0; j < m; ++j) Ln[(int64_t)j * ldn + s] = L[(int64_t)j * ld + s] * rn;
+  }
+}
+
+// One pass over the loadings: B = Ln R (chunk of 32 features at a time, fp32 products, fp64 reduction),
+// Gout += Ln^T B^3, Wout += colsum(B^2).  16x16 threads, register tile TI x TI of Gout per thread.
+constexpr int VM_CHUNK = 32;
+
+template <int TI>
+__global__ void __launch_bounds__(256)
+varimax_accumulate_kernel(const float* __restrict__ L, int64_t S, int m, int64_t ld, const float* __restrict__ rownorm,
+                          const double* __restrict__ R, float power, const double* __restrict__ colscale,
+                          double* __restrict__ Gout, double* __restrict__ Wout, float* __restrict__ absmax) {
+  constexpr int MP = 16 * TI;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  float* Rs = reinterpret_cast<float*>(smraw);            // [MP][MP+1]  R (fp32)
+  float* Ls = Rs + MP * (MP + 1);                          // [VM_CHUNK][MP+4]   normalised loadings chunk
+  float* Bs = Ls + VM_CHUNK * (MP + 4);                    // [VM_CHUNK][MP+4]   B^3 chunk
+  const int tid = threadIdx.x;
+  const int ti = tid >> 4, tj = tid & 15;
+  for (int idx = tid; idx < MP * MP; idx += 256) {
+    const int i = idx / MP, j = idx % MP;
+    Rs[i * (MP + 1) + j] = (i < m && j < m) ? (float)R[(int64_t)i * m + j] : 0.f;
+  }
+  double acc[TI][TI];
+#pragma unroll
+  for (int a = 0; a < TI; ++a)
+#pragma unroll
+    for (int b = 0; b < TI; ++b) acc[a][b] = 0.0;
+  double wacc[(MP + 255) / 256 > 0 ? (MP + 255) / 256 : 1];
+  wacc[0] = 0.0;
+  float amax = 0.f;
+  const float cs = (colscale && tid < m) ? (float)colscale[tid] : 1.f;
+  (void)cs;
+
+  const int64_t n_chunks = (S + VM_CHUNK - 1) / VM_CHUNK;
+  for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const int64_t s0 = ch * VM_CHUNK;
+    __syncthreads();
+    {
+      const int lane = tid & 31, w = tid >> 5;
+      const int64_t s = s0 + lane;
+      const float rn = (s < S) ? (rownorm ? rownorm[s] : 1.f) : 0.f;
+      for (int j = w; j < MP; j += 8) {
+        float v = 0.f;
+        if (j < m && s < S) v = L[(int64_t)j * ld + s] * rn;
+        Ls[lane * (MP + 4) + j] = v;
+      }
+    }
+    __syncthreads();
+    // B[r][j] = sum_i Ls[r][i] Rs[i][j];  thread -> (r = tid / 8 -> 32 rows, 8 threads per row, each MP/8 columns)
+    {
+      const int r = tid >> 3, c0 = tid & 7;
+      for (int j = c0; j < MP; j += 8) {
+        float b = 0.f;
+        for (int i = 0; i < m; ++i) b = fmaf(Ls[r * (MP + 4) + i], Rs[i * (MP + 1) + j], b);
+        Bs[r * (MP + 4) + j] = b;
+      }
+    }
+    __syncthreads();
+    // column sums of B^2 (fp64) by the first MP threads, then cube in place
+    if (tid < MP) {
+      double w2 = 0.0;
+#pragma unroll 4
+      for (int r = 0; r < VM_CHUNK; ++r) {
+        const float bf = Bs[r * (MP + 4) + tid];
+        const double b = (double)bf;
+        w2 = fma(b, b, w2);
+        amax = fmaxf(amax, fabsf(bf));
+        // f(b): varimax b^3; promax target (b c)|b c|^(power-1)   (_rotation.py:57-62, 166-170)
+        float fb;
+        if (power == 3.f && !colscale) fb = bf * bf * bf;
+        else { const float u = bf * cs; fb = (power == 1.f) ? u : u * powf(fabsf(u), power - 1.f); }
+        Bs[r * (MP + 4) + tid] = fb;
+      }
+      wacc[0] += w2;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int r = 0; r < VM_CHUNK; ++r) {
+      double a[TI], b[TI];
+#pragma unroll
+      for (int x = 0; x < TI; ++x) {
+        a[x] = (double)Ls[r * (MP + 4) + ti * TI + x];
+        b[x] = (double)Bs[r * (MP + 4) + tj * TI + x];
+      }
+#pragma unroll
+      for (int x = 0; x < TI; ++x)
+#pragma unroll
+        for (int y = 0; y < TI; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < TI; ++x)
+#pragma unroll
+    for (int y = 0; y < TI; ++y) {
+      const int i = ti * TI + x, j = tj * TI + y;
+      if (i < m && j < m) atomicAdd(&Gout[(int64_t)i * m + j], acc[x][y]);
+    }
+  if (tid < m) {
+    atomicAdd(&Wout[tid], wacc[0]);
+    if (absmax) atomicMax(reinterpret_cast<int*>(&absmax[tid]), __float_as_int(amax));  // non-negative floats
+  }
+}
+
+}  // namespace xb
+
+using namespace xb;
+
+extern "C" int xeofs_b200_col_norms(const float* L, int64_t S, int64_t m, int64_t ld, float* h, float* rownorm,
+                                    float* Ln, int64_t ldn, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(L && S > 0 && m > 0 && ld >= S, "col_norms: bad arguments");
+  const int blocks = (int)imin(ceil_div(S, 256), 8 * (int64_t)num_sms());
+  XB_CHECK_ARG(!Ln || ldn >= S, "col_norms: ldn < S");
+  col_norms_kernel<<<blocks, 256, 0, stream>>>(L, S, (int)m, ld, h, rownorm, Ln, ldn);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
+extern "C" int xeofs_b200_varimax_accumulate(const float* L, int64_t S, int64_t m, int64_t ld, const float* rownorm,
+                                             const double* R, double power, const double* colscale, double* Gout,
+                                             double* Wout, float* absmax, int accumulate, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(L && R && Gout && Wout && S > 0 && ld >= S, "varimax_accumulate: bad arguments");
+  XB_CHECK_ARG(m >= 2 && m <= 128, "varimax_accumulate: m=%lld must be in 2..128", (long long)m);
+  if (!accumulate) {
+    XB_CUDA(cudaMemsetAsync(Gout, 0, (size_t)m * m * sizeof(double), stream));
+    XB_CUDA(cudaMemsetAsync(Wout, 0, (size_t)m * sizeof(double), stream));
+    if (absmax) XB_CUDA(cudaMemsetAsync(absmax, 0, (size_t)m * sizeof(float), stream));
+  }
+  XB_CHECK_ARG(power >= 1.0, "varimax_accumulate: power must be >= 1");
+  const int ti = m <= 16 ? 1 : m <= 32 ? 2 : m <= 64 ? 4 : 8;
+  const int MP = 16 * ti;
+  const size_t smem = ((size_t)MP * (MP + 1) + 2 * (size_t)VM_CHUNK * (MP + 4)) * sizeof(float);
+  const int blocks = (int)imin(ceil_div(S, VM_CHUNK), 2 * (int64_t)num_sms());
+#define XB_VM(TI)                                                                                                  \
+  XB_CUDA(cudaFuncSetAttribute(varimax_accumulate_kernel<TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+  varimax_accumulate_kernel<TI><<<blocks, 256, smem, stream>>>(L, S, (int)m, ld, rownorm, R, (float)power, colscale, Gout, Wout, absmax)
+  switch (ti) {
+    case 1: XB_VM(1); break;
+    case 2: XB_VM(2); break;
+    case 4: XB_VM(4); break;
+    default: XB_VM(8); break;
+  }
+#undef XB_VM
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}

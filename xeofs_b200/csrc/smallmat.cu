@@ -1,0 +1,483 @@
+// The k-column linear algebra around the streaming passes: Gram (fp64), Cholesky + triangular inverse,
+// right-multiplication by a small matrix, Jacobi eigen-solver, sign-rule reductions.
+// Together they stand in for sklearn's LU/QR normalizers and scipy.linalg.svd(B) inside
+// sklearn.utils.extmath.randomized_svd (reference call site linalg/decomposer.py:141-146) and for
+// get_deterministic_sign_multiplier (utils/xarray_utils.py:273-301).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace xb {
+
+// ------------------------------------------------------------------------------------------------
+// Gram matrix in fp64.  Persistent blocks sweep chunks of n; each thread keeps a TI x TI register tile
+// of the l x l result (16 x 16 threads), so the global atomics are one per entry per block.
+constexpr int GR_CHUNK = 32;
+
+template <int TI, int SIDE>
+__global__ void __launch_bounds__(256)
+gram_kernel(const float* __restrict__ M, int64_t n, int l, int64_t ld, double* __restrict__ G) {
+  constexpr int LP = 16 * TI;
+  __shared__ __align__(16) float sm[GR_CHUNK][LP + 4];  // [n_local][column]
+  const int tid = threadIdx.x;
+  const int ti = tid >> 4, tj = tid & 15;
+  double acc[TI][TI];
+#pragma unroll
+  for (int a = 0; a < TI; ++a)
+#pragma unroll
+    for (int b = 0; b < TI; ++b) acc[a][b] = 0.0;
+
+  const int64_t n_chunks = (n + GR_CHUNK - 1) / GR_CHUNK;
+  for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const int64_t n0 = ch * GR_CHUNK;
+    if (SIDE == 1) {
+      // space-side: element (n, j) at M[j*ld + n]; 32 lanes read 32 consecutive n of one row j
+      const int lane = tid & 31, w = tid >> 5;
+      for (int j = w; j < LP; j += 8) {
+        float v = 0.f;
+        if (j < l && n0 + lane < n) v = M[(int64_t)j * ld + n0 + lane];
+        sm[lane][j] = v;
+      }
+    } else {
+      // time-side: element (n, j) at M[n*ld + j]
+      for (int idx = tid; idx < GR_CHUNK * LP; idx += 256) {
+        const int r = idx / LP, j = idx % LP;
+        float v = 0.f;
+        if (j < l && n0 + r < n) v = M[(n0 + r) * ld + j];
+        sm[r][j] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < GR_CHUNK; ++r) {
+      double a[TI], b[TI];
+#pragma unroll
+      for (int x = 0; x < TI; ++x) {
+        a[x] = (double)sm[r][ti * TI + x];
+        b[x] = (double)sm[r][tj * TI + x];
+      }
+#pragma unroll
+      for (int x = 0; x < TI; ++x)
+#pragma unroll
+        for (int y = 0; y < TI; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int x = 0; x < TI; ++x)
+#pragma unroll
+    for (int y = 0; y < TI; ++y) {
+      const int i = ti * TI + x, j = tj * TI + y;
+      if (i < l && j < l) atomicAdd(&G[(int64_t)i * l + j], acc[x][y]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cholesky G = R^T R and Rinv = R^-1, one block, fp64 (full l x l in dynamic smem for R, Rinv written to
+// global).  l <= 128.  A column whose pivot has fallen below the fp32 noise floor of the matrix it was
+// accumulated from (4 * FLT_EPSILON^2 * G[k][k]) is linearly dependent on the earlier ones to working
+// precision: it is dropped from the basis (its column of Rinv is zero, so the orthonormalised matrix gets
+// a zero column there) instead of being normalised into noise.  info[0] = number of dropped columns,
+// info[1] = 1 if a NaN/Inf pivot was met (numpy.linalg.LinAlgError at the boundary).
+__global__ void __launch_bounds__(256)
+chol_inv_kernel(const double* __restrict__ G, int l, double* __restrict__ Rinv, int32_t* __restrict__ info) {
+  extern __shared__ double sh[];  // A: l x (l+1), then diag0[l], dead[l] (as doubles)
+  const int ldA = l + 1;
+  double* A = sh;
+  double* diag0 = A + (size_t)l * ldA;
+  double* dead = diag0 + l;
+  __shared__ int n_dead, bad;
+  const int tid = threadIdx.x;
+  if (tid == 0) { n_dead = 0; bad = 0; }
+  for (int idx = tid; idx < l * l; idx += blockDim.x) A[(idx / l) * ldA + (idx % l)] = G[idx];
+  __syncthreads();
+  for (int i = tid; i < l; i += blockDim.x) { diag0[i] = A[i * ldA + i]; dead[i] = 0.0; }
+  __syncthreads();
+  // right-looking upper Cholesky: row k of R, then trailing update A[i][j] -= R[k][i] R[k][j]
+  for (int k = 0; k < l; ++k) {
+    const double d = A[k * ldA + k];
+    const bool finite = (d == d) && fabs(d) < 1e300;
+    const bool drop = !finite || !(d > 5.7e-14 * diag0[k]) || !(d > 0.0);
+    __syncthreads();
+    if (drop) {
+      if (tid == 0) { dead[k] = 1.0; n_dead += 1; if (!finite) bad = 1; }
+      for (int j = k + tid; j < l; j += blockDim.x) A[k * ldA + j] = (j == k) ? 1.0 : 0.0;
+      __syncthreads();
+      continue;
+    }
+    const double rkk = sqrt(d);
+    for (int j = k + tid; j < l; j += blockDim.x) A[k * ldA + j] = (j == k) ? rkk : A[k * ldA + j] / rkk;
+    __syncthreads();
+    const int m = l - k - 1;
+    for (int idx = tid; idx < m * m; idx += blockDim.x) {
+      const int i = k + 1 + idx / m, j = k + 1 + idx % m;
+      if (j >= i) A[i * ldA + j] -= A[k * ldA + i] * A[k * ldA + j];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) { info[0] = n_dead; info[1] = bad; }
+  // inverse of upper-triangular R, row by row from the bottom:
+  //   Rinv[i][i] = 1/R[i][i];  Rinv[i][j] = -(sum_{k=i+1..j} R[i][k] Rinv[k][j]) / R[i][i]   (j > i)
+  // Rinv is kept in global memory (one block; __ldcg/__stcg keep the traffic in L2, coherent after the barrier)
+  for (int idx = tid; idx < l * l; idx += blockDim.x) Rinv[idx] = 0.0;
+  __syncthreads();
+  for (int i = l - 1; i >= 0; --i) {
+    const double rii = A[i * ldA + i];
+    for (int j = i + tid; j < l; j += blockDim.x) {
+      double v;
+      if (j == i) {
+        v = dead[i] != 0.0 ? 0.0 : 1.0 / rii;
+      } else {
+        double a0 = 0.0, a1 = 0.0;
+        int k = i + 1;
+        for (; k + 1 <= j; k += 2) {
+          a0 = fma(A[i * ldA + k], __ldcg(&Rinv[k * l + j]), a0);
+          a1 = fma(A[i * ldA + k + 1], __ldcg(&Rinv[(k + 1) * l + j]), a1);
+        }
+        if (k <= j) a0 = fma(A[i * ldA + k], __ldcg(&Rinv[k * l + j]), a0);
+        v = -(a0 + a1) / rii;
+      }
+      __stcg(&Rinv[i * l + j], v);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Out(n, j') = sum_j In(n, j) Mat[j, j'] colscale[j'].  Block: 64 n x all j' (<= 128), 256 threads, thread
+// tile 4 n x TJ j'.  fp32 inputs, fp64 matrix rounded to fp32 for the space-side (S x l x k flops), fp64
+// accumulation on the (tiny) time side.
+constexpr int AP_BN = 64;
+
+template <int SIDE_IN, int SIDE_OUT, typename AccT>
+__global__ void __launch_bounds__(256)
+apply_kernel(const float* __restrict__ In, int64_t n, int l, int64_t ld_in, const double* __restrict__ Mat,
+             int64_t ldm, int k, const double* __restrict__ colscale, float* __restrict__ Out, int64_t ld_out,
+             int kp_out) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  // layout: Ms[l][KP] (AccT), Is[l][AP_BN + 4] (float)
+  const int KP = (k + 15) / 16 * 16;
+  AccT* Ms = reinterpret_cast<AccT*>(smraw);
+  float* Is = reinterpret_cast<float*>(smraw + (size_t)l * KP * sizeof(AccT));
+  constexpr int ISL = AP_BN + 4;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < l * KP; idx += 256) {
+    const int j = idx / KP, jp = idx % KP;
+    double v = 0.0;
+    if (jp < k) v = Mat[(int64_t)j * ldm + jp] * (colscale ? colscale[jp] : 1.0);
+    Ms[idx] = (AccT)v;
+  }
+  const int tn = tid & 15;   // 4 n each -> 64 n
+  const int tjg = tid >> 4;  // 16 groups over j'
+  const int n_jt = (KP + 15) / 16;  // j' per thread (KP/16), <= 8
+
+  for (int64_t blk = blockIdx.x; blk * AP_BN < n; blk += gridDim.x) {
+    const int64_t n0 = blk * AP_BN;
+    __syncthreads();
+    if (SIDE_IN == 1) {
+      const int lane = tid & 31, w = tid >> 5;
+      for (int j = w; j < l; j += 8) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int64_t nn = n0 + lane + 32 * h;
+          Is[j * ISL + lane + 32 * h] = (nn < n) ? In[(int64_t)j * ld_in + nn] : 0.f;
+        }
+      }
+    } else {
+      for (int idx = tid; idx < AP_BN * l; idx += 256) {
+        const int r = idx / l, j = idx % l;
+        Is[j * ISL + r] = (n0 + r < n) ? In[(n0 + r) * ld_in + j] : 0.f;
+      }
+    }
+    __syncthreads();
+    AccT acc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[a][b] = (AccT)0;
+    for (int j = 0; j < l; ++j) {
+      const float4 iv = *reinterpret_cast<const float4*>(&Is[j * ISL + 4 * tn]);
+      const AccT ia[4] = {(AccT)iv.x, (AccT)iv.y, (AccT)iv.z, (AccT)iv.w};
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        if (b < n_jt) {
+          const AccT m = Ms[j * KP + tjg + 16 * b];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) acc[a][b] = fma(ia[a], m, acc[a][b]);
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      if (b >= n_jt) continue;
+      const int jp = tjg + 16 * b;
+      if (jp >= kp_out) continue;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int64_t nn = n0 + 4 * tn + a;
+        if (nn >= n) continue;
+        const float v = (jp < k) ? (float)acc[a][b] : 0.f;
+        if (SIDE_OUT == 1) Out[(int64_t)jp * ld_out + nn] = v;
+        else Out[nn * ld_out + jp] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Symmetric eigen-decomposition by parallel cyclic Jacobi (round-robin pairing), one block, fp64.
+// A (l x l) lives in dynamic smem; the eigenvector matrix is accumulated TRANSPOSED in `work` (global,
+// row p = eigenvector p) and written out as columns at the end, sorted by descending eigenvalue.
+__global__ void __launch_bounds__(256)
+sym_eig_kernel(const double* __restrict__ G, int l, double* __restrict__ evals, double* __restrict__ evecs,
+               double* __restrict__ Vt, int32_t* __restrict__ info) {
+  extern __shared__ double sh[];
+  const int le = (l + 1) & ~1;  // even size for the tournament
+  const int ldA = le + 1;
+  double* A = sh;                      // le x ldA
+  double* cs = A + (size_t)le * ldA;   // le/2 cosines, le/2 sines
+  int* pairs = reinterpret_cast<int*>(cs + le);  // le ints: current seating
+  __shared__ double offnorm;
+  __shared__ double diagnorm;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int half = le / 2;
+
+  for (int idx = tid; idx < le * le; idx += nt) {
+    const int i = idx / le, j = idx % le;
+    double v = 0.0;
+    if (i < l && j < l) v = 0.5 * (G[(int64_t)i * l + j] + G[(int64_t)j * l + i]);
+    A[i * ldA + j] = v;
+    Vt[idx] = (i == j) ? 1.0 : 0.0;
+  }
+  for (int i = tid; i < le; i += nt) pairs[i] = i;
+  __syncthreads();
+
+  int sweeps_done = 0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    // convergence test: off-diagonal Frobenius norm vs diagonal
+    if (tid == 0) { offnorm = 0.0; diagnorm = 0.0; }
+    __syncthreads();
+    double off = 0.0, dg = 0.0;
+    for (int idx = tid; idx < le * le; idx += nt) {
+      const int i = idx / le, j = idx % le;
+      const double v = A[i * ldA + j];
+      if (i == j) dg += v * v; else off += v * v;
+    }
+    off = warp_sum(off); dg = warp_sum(dg);
+    if ((tid & 31) == 0) { atomicAdd(&offnorm, off); atomicAdd(&diagnorm, dg); }
+    __syncthreads();
+    const bool done = offnorm <= 1e-29 * diagnorm || diagnorm == 0.0;
+    __syncthreads();
+    if (done) break;
+    sweeps_done = sweep + 1;
+
+    for (int round = 0; round < le - 1; ++round) {
+      // pair q-th: (pairs[q], pairs[le-1-q])
+      for (int q = tid; q < half; q += nt) {
+        int p = pairs[q], r = pairs[le - 1 - q];
+        if (p > r) { int tmp = p; p = r; r = tmp; }
+        const double apq = A[p * ldA + r];
+        double c = 1.0, s = 0.0;
+        if (fabs(apq) > 1e-300) {
+          const double app = A[p * ldA + p], aqq = A[r * ldA + r];
+          const double tau = (aqq - app) / (2.0 * apq);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + t * t);
+          s = t * c;
+        }
+        cs[q] = c; cs[half + q] = s;
+      }
+      __syncthreads();
+      // rows: A <- J^T A   (row p, row r), and the eigenvector accumulator rows
+      for (int idx = tid; idx < half * le; idx += nt) {
+        const int q = idx / le, col = idx % le;
+        int p = pairs[q], r = pairs[le - 1 - q];
+        if (p > r) { int tmp = p; p = r; r = tmp; }
+        const double c = cs[q], s = cs[half + q];
+        const double ap = A[p * ldA + col], ar = A[r * ldA + col];
+        A[p * ldA + col] = c * ap - s * ar;
+        A[r * ldA + col] = s * ap + c * ar;
+        const double vp = __ldcg(&Vt[p * le + col]), vr = __ldcg(&Vt[r * le + col]);
+        __stcg(&Vt[p * le + col], c * vp - s * vr);
+        __stcg(&Vt[r * le + col], s * vp + c * vr);
+      }
+      __syncthreads();
+      // columns: A <- A J
+      for (int idx = tid; idx < half * le; idx += nt) {
+        const int q = idx % half, row = idx / half;
+        int p = pairs[q], r = pairs[le - 1 - q];
+        if (p > r) { int tmp = p; p = r; r = tmp; }
+        const double c = cs[q], s = cs[half + q];
+        const double ap = A[row * ldA + p], ar = A[row * ldA + r];
+        A[row * ldA + p] = c * ap - s * ar;
+        A[row * ldA + r] = s * ap + c * ar;
+      }
+      __syncthreads();
+      // rotate seating: position 0 fixed, others shift by one
+      int newv = -1;
+      if (tid < le && tid >= 1) newv = pairs[tid == 1 ? le - 1 : tid - 1];
+      __syncthreads();
+      if (tid < le && tid >= 1) pairs[tid] = newv;
+      __syncthreads();
+    }
+  }
+  // sort eigenvalues descending (l <= 128: rank by counting), write outputs
+  for (int i = tid; i < l; i += nt) {
+    const double vi = A[i * ldA + i];
+    int rank = 0;
+    for (int j = 0; j < l; ++j) {
+      const double vj = A[j * ldA + j];
+      rank += (vj > vi) || (vj == vi && j < i);
+    }
+    evals[rank] = vi;
+    pairs[i] = rank;  // reuse as destination column
+  }
+  __syncthreads();
+  for (int idx = tid; idx < l * l; idx += nt) {
+    const int i = idx / l, comp = idx % l;  // eigenvector i, component comp
+    evecs[(int64_t)comp * l + pairs[i]] = __ldcg(&Vt[i * le + comp]);
+  }
+  if (tid == 0) info[0] = sweeps_done;
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  // ordered-int trick, valid for any finite floats
+  if (v >= 0) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  if (v >= 0) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void minmax_init_kernel(float* vmax, float* vmin, int k) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k) { vmax[i] = -INFINITY; vmin[i] = INFINITY; }
+}
+
+__global__ void __launch_bounds__(256)
+row_minmax_kernel(const float* __restrict__ Vt, int64_t n, int64_t ld, float* __restrict__ vmax, float* __restrict__ vmin) {
+  const float* row = Vt + (int64_t)blockIdx.y * ld;
+  float mx = -INFINITY, mn = INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = row[i];
+    if (v == v) { mx = fmaxf(mx, v); mn = fminf(mn, v); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (mx > -INFINITY) atomic_max_float(&vmax[blockIdx.y], mx);
+    if (mn < INFINITY) atomic_min_float(&vmin[blockIdx.y], mn);
+  }
+}
+
+__global__ void finish_components_kernel(float* __restrict__ Vt, int64_t n, int64_t ld, const float* __restrict__ sign,
+                                         const uint8_t* __restrict__ valid) {
+  float* row = Vt + (int64_t)blockIdx.y * ld;
+  const float sg = sign ? sign[blockIdx.y] : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool ok = valid ? (valid[i] != 0) : true;
+    row[i] = ok ? sg * row[i] : nanf("");
+  }
+}
+
+}  // namespace xb
+
+using namespace xb;
+
+extern "C" int xeofs_b200_gram(const float* M, int64_t n, int64_t l, int64_t ld, int side, double* G, int accumulate,
+                               void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(M && G && n > 0 && l > 0 && l <= 128, "gram: bad arguments (l=%lld must be in 1..128)", (long long)l);
+  XB_CHECK_ARG(side == 0 || side == 1, "gram: side must be 0 (time-side) or 1 (space-side)");
+  if (!accumulate) XB_CUDA(cudaMemsetAsync(G, 0, (size_t)l * l * sizeof(double), stream));
+  const int64_t chunks = ceil_div(n, GR_CHUNK);
+  const int blocks = (int)imin(chunks, 2 * (int64_t)num_sms());
+  const int ti = l <= 16 ? 1 : l <= 32 ? 2 : l <= 64 ? 4 : 8;
+#define XB_GRAM(TI)                                                                        \
+  if (side == 0) gram_kernel<TI, 0><<<blocks, 256, 0, stream>>>(M, n, (int)l, ld, G);     \
+  else gram_kernel<TI, 1><<<blocks, 256, 0, stream>>>(M, n, (int)l, ld, G)
+  switch (ti) {
+    case 1: XB_GRAM(1); break;
+    case 2: XB_GRAM(2); break;
+    case 4: XB_GRAM(4); break;
+    default: XB_GRAM(8); break;
+  }
+#undef XB_GRAM
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
+extern "C" int xeofs_b200_chol_inv(const double* G, int64_t l, double* Rinv, int32_t* info, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(G && Rinv && info && l > 0 && l <= 128, "chol_inv: bad arguments (l=%lld must be in 1..128)", (long long)l);
+  const size_t smem = ((size_t)l * (l + 1) + 2 * (size_t)l) * sizeof(double);
+  XB_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  chol_inv_kernel<<<1, 256, smem, stream>>>(G, (int)l, Rinv, info);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
+extern "C" int xeofs_b200_apply(const float* In, int64_t n, int64_t l, int64_t ld_in, int side, const double* Mat,
+                                int64_t ldm, int64_t k, const double* colscale, float* Out, int64_t ld_out,
+                                void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(In && Mat && Out && n > 0, "apply: null pointer");
+  XB_CHECK_ARG(l > 0 && l <= 128 && k > 0 && k <= 128, "apply: l=%lld, k=%lld must be in 1..128", (long long)l, (long long)k);
+  XB_CHECK_ARG(side == 0 || side == 1, "apply: side must be 0 or 1");
+  const int KP = (int)lpad(k);
+  const int blocks = (int)imin(ceil_div(n, AP_BN), 4 * (int64_t)num_sms());
+  if (side == 1) {
+    // space-side: fp32 accumulation (S*l*k flops), output keeps lp rows (pad rows written as zero)
+    const size_t smem = (size_t)l * KP * sizeof(float) + (size_t)l * (AP_BN + 4) * sizeof(float);
+    XB_CUDA(cudaFuncSetAttribute(apply_kernel<1, 1, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    apply_kernel<1, 1, float><<<blocks, 256, smem, stream>>>(In, n, (int)l, ld_in, Mat, ldm, (int)k, colscale, Out,
+                                                            ld_out, KP);
+  } else {
+    const size_t smem = (size_t)l * KP * sizeof(double) + (size_t)l * (AP_BN + 4) * sizeof(float);
+    XB_CUDA(cudaFuncSetAttribute(apply_kernel<0, 0, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int kp_out = (int)imin(KP, ld_out);
+    apply_kernel<0, 0, double><<<blocks, 256, smem, stream>>>(In, n, (int)l, ld_in, Mat, ldm, (int)k, colscale, Out,
+                                                             ld_out, kp_out);
+  }
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
+extern "C" int xeofs_b200_sym_eig(const double* G, int64_t l, double* evals, double* evecs, double* work,
+                                  int32_t* info, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(G && evals && evecs && work && info && l > 0 && l <= 128, "sym_eig: bad arguments (l=%lld must be in 1..128)", (long long)l);
+  const int le = ((int)l + 1) & ~1;
+  const size_t smem = ((size_t)le * (le + 1) + le) * sizeof(double) + (size_t)le * sizeof(int);
+  XB_CUDA(cudaFuncSetAttribute(sym_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sym_eig_kernel<<<1, 256, smem, stream>>>(G, (int)l, evals, evecs, work, info);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
+extern "C" int xeofs_b200_row_minmax(const float* Vt, int64_t k, int64_t n, int64_t ld, float* vmax, float* vmin,
+                                     void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(Vt && vmax && vmin && k > 0 && k <= 65535 && n > 0, "row_minmax: bad arguments");
+  minmax_init_kernel<<<(unsigned)ceil_div(k, 128), 128, 0, stream>>>(vmax, vmin, (int)k);
+  XB_LAUNCH_CHECK();
+  const int bx = (int)imin(ceil_div(n, 256 * 8), 4 * (int64_t)num_sms());
+  row_minmax_kernel<<<dim3(bx > 0 ? bx : 1, (unsigned)k), 256, 0, stream>>>(Vt, n, ld, vmax, vmin);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
+extern "C" int xeofs_b200_finish_components(float* Vt, int64_t k, int64_t n, int64_t ld, const float* sign,
+                                            const uint8_t* valid, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(Vt && k > 0 && k <= 65535 && n > 0, "finish_components: bad arguments");
+  const int bx = (int)imin(ceil_div(n, 256 * 4), 4 * (int64_t)num_sms());
+  finish_components_kernel<<<dim3(bx > 0 ? bx : 1, (unsigned)k), 256, 0, stream>>>(Vt, n, ld, sign, valid);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}

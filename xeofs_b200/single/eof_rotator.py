@@ -1,0 +1,164 @@
+"""Varimax / Promax rotation of an EOF solution on B200 — drop-in for ``xeofs.single.EOFRotator``
+(single/eof_rotator.py:57-225; algorithm linalg/_numpy/_rotation.py:6-187).
+
+Each varimax iteration is ONE streaming pass over the (S x m) loadings: with Ln the Kaiser-normalised loadings,
+B = Ln R and W = colsum(B^2),
+    Ln^H (B o (B^2 - W/S)) = Ln^H B^3 - (1/S) (Ln^H Ln) R diag(W),
+so the kernel accumulates Ln^H B^3 and W in fp64 and the m x m remainder is done on the small matrices.
+The polar factor R = U V^T of svd(G) and delta = sum(svals) come from the eigen-decomposition of G^T G.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _engine as E
+from .. import _labels as L
+from .._lib import lpad
+
+
+class EOFRotator:
+    def __init__(self, n_modes=2, power=1, max_iter=None, rtol=1e-8, compute=True):
+        if max_iter is None:
+            max_iter = 1000 if compute else 100  # eof_rotator.py:65-66
+        self._params = dict(n_modes=n_modes, power=power, max_iter=max_iter, rtol=rtol, compute=compute)
+        self.attrs = {"model": "Rotated EOF analysis", "backend": "xeofs_b200"}
+        self.data = {}
+        self.n_iter_ = 0
+
+    # ------------------------------------------------------------------ rotation of a space-side loadings block
+    @staticmethod
+    def _polar(ops, G):
+        """U V^T and sum(svals) of svd(G) through eig(G^T G) (fp64, m x m)."""
+        ev, V = ops.sym_eig((G.t() @ G).contiguous())
+        sv = torch.sqrt(torch.clamp(ev, min=0.0))
+        inv = torch.where(sv > 0, 1.0 / sv, torch.zeros_like(sv))
+        return G @ (V * inv[None, :]) @ V.t(), sv.sum()
+
+    def _rotate(self, ops, comm, L0, S_local, n_rows, m):
+        """promax(loadings) of linalg/_numpy/_rotation.py:6-92.  Returns R_total (m x m fp64), phi, iterations."""
+        p = self._params
+        if m < 2:
+            raise ValueError(f"Cannot rotate {m} modes (columns), but must be 2 or more.")
+        _, _, Ln = ops.col_norms(L0, S_local, m, normalized_out=True)
+        XtX = ops.gram(Ln, S_local, m, 1)
+        comm.sum_(XtX)
+        R = torch.eye(m, dtype=torch.float64, device=ops.device)
+        alpha = 1.0 / n_rows  # gamma = 1 (varimax)
+        d, converged, it = 0.0, False, 0
+        for it in range(1, p["max_iter"] + 1):
+            G3, W, _ = ops.varimax_accumulate(Ln, S_local, m, R)
+            comm.sum_(G3)
+            comm.sum_(W)
+            G = G3 - alpha * (XtX @ R) * W[None, :]
+            R, dsum = self._polar(ops, G)
+            d_old, d = d, float(dsum.item())
+            if abs(d - d_old) / d < p["rtol"]:
+                converged = True
+                break
+        if not converged:
+            raise RuntimeError("Rotation process did not converge.")  # _rotation.py:179-180
+        self.n_iter_ = it
+        eye = torch.eye(m, dtype=torch.float64, device=ops.device)
+        power = p["power"]
+        if power == 1:  # Lr = I, phi = I up to round-off (_rotation.py:57-90)
+            return R, eye
+        _, _, amax = ops.varimax_accumulate(Ln, S_local, m, R, want_absmax=True)
+        comm.max_(amax)
+        Gp, _, _ = ops.varimax_accumulate(Ln, S_local, m, R, power=float(power), colscale=(1.0 / amax.double()))
+        comm.sum_(Gp)
+        ZtP = R.t() @ Gp
+        ZtZ = R.t() @ XtX @ R
+        Lr = torch.linalg.solve(ZtZ, ZtP)
+        sig = torch.diagonal(torch.linalg.inv(Lr.t() @ Lr))
+        Lr = Lr * torch.sqrt(sig)[None, :]
+        Li = torch.linalg.inv(Lr)
+        return R @ Lr, Li @ Li.t()
+
+    # ------------------------------------------------------------------ fit (eof_rotator.py:103-225)
+    def fit(self, model):
+        ops, comm = model.ops, model.comm
+        self.model, self.ops, self.comm = model, ops, comm
+        self.preprocessor = model.preprocessor
+        ff = model.preprocessor.fitted
+        p = self._params
+        m = int(p["n_modes"])
+        if m > model.k:
+            raise ValueError(f"n_modes={m} exceeds the {model.k} modes of the EOF model")
+        S, T = ff.S, ff.T
+        s = model._s[:m]
+        ev = (s**2 / (ff.n_samples - 1))
+        eye = torch.eye(m, dtype=torch.float64, device=ops.device)
+        # loadings = components * sqrt(expvar)   (eof_rotator.py:131-135)
+        L0 = ops.apply(model._Vt, S, m, 1, eye, m, colscale=torch.sqrt(ev))
+        Rt, phi = self._rotate(ops, comm, L0, S, ff.n_features, m)
+        # expvar = sum |L_rot|^2 = diag(Rt^T (L0^T L0) Rt)   (eof_rotator.py:155)
+        G0 = ops.gram(L0, S, m, 1)
+        comm.sum_(G0)
+        expvar = torch.diagonal(Rt.t() @ G0 @ Rt).clone()
+        idx = torch.argsort(expvar, descending=True)  # :156
+        expvar_s = expvar[idx]
+        norms = torch.sqrt(expvar_s * (ff.n_samples - 1))  # :163-164
+        # components = L_rot / sqrt(expvar), written already in sorted order (:160, 215-225)
+        Vt = ops.apply(L0, S, m, 1, Rt[:, idx].contiguous(), m, colscale=1.0 / torch.sqrt(expvar_s))
+        sign = E.sign_flip(ops, Vt, m, S, comm)  # :184-188
+        ops.finish_components(Vt, m, S, sign, None)
+        # scores = (scores / svals) R^-T * norms * sign   (:168-181)
+        RinvT = Rt if p["power"] == 1 else torch.linalg.inv(Rt).t()
+        Mat = (RinvT[:, idx] / s[:, None]).contiguous()
+        scores = ops.apply(model._scores, T, m, 0, Mat, m, colscale=norms * sign.double())
+        self.k = m
+        self._Vt, self._scores, self._s = Vt, scores, norms
+        self.data = {
+            "norms": norms, "explained_variance": expvar_s, "total_variance": model.data["total_variance"],
+            "idx_modes_sorted": idx, "rotation_matrix": Rt, "phi_matrix": phi, "modes_sign": sign,
+        }
+        return self
+
+    # ------------------------------------------------------------------ accessors
+    def components(self, normalized=True):
+        Vt = self._Vt
+        if not normalized:
+            Vt = Vt[: self.k] * self._s.to(torch.float32)[:, None]
+        return self.preprocessor.components_to_nd(Vt, self.k, "components")
+
+    def scores(self, normalized=False):
+        Sc = self._scores
+        if normalized:
+            Sc = Sc.clone()
+            Sc[:, : self.k] /= self._s.to(torch.float32)[None, :]
+        return self.preprocessor.scores_to_nd(Sc, self.k, "scores")
+
+    def _mode_array(self, t, name):
+        return L.wrap(t.cpu().numpy(), ("mode",), {"mode": np.arange(1, self.k + 1)}, name,
+                      self.preprocessor.as_xarray)
+
+    def singular_values(self):
+        return self._mode_array(self.data["norms"], "singular_values")
+
+    def explained_variance(self):
+        return self._mode_array(self.data["explained_variance"], "explained_variance")
+
+    def explained_variance_ratio(self):
+        return self._mode_array(self.data["explained_variance"] / self.data["total_variance"], "explained_variance_ratio")
+
+    def rotation_matrix(self):
+        return self.data["rotation_matrix"].cpu().numpy()
+
+    def phi_matrix(self):
+        return self.data["phi_matrix"].cpu().numpy()
+
+    def transform(self, data, normalized=False):
+        """eof_rotator.py:227-263: project on the un-rotated components, rotate, reorder, scale, sign."""
+        model, p = self.model, self._params
+        new, sample_shape, sample_coords, valid_sample = self.preprocessor.transform(data)
+        m = self.k
+        Z = self.ops.project_T(new, model._Vt, m, algo=self.ops.accurate_algo)
+        self.comm.sum_(Z)
+        Rt = self.data["rotation_matrix"]
+        RinvT = Rt if p["power"] == 1 else torch.linalg.inv(Rt).t()
+        idx = self.data["idx_modes_sorted"]
+        Mat = (RinvT[:, idx] / model._s[:m, None]).contiguous()
+        scale = self.data["modes_sign"].double() * (1.0 if normalized else self.data["norms"])
+        Zr = self.ops.apply(Z, int(Z.shape[0]), m, 0, Mat, m, colscale=scale * torch.ones_like(self.data["norms"]))
+        return self.preprocessor.scores_to_nd(Zr, m, "scores", sample_shape, sample_coords, valid_sample)
