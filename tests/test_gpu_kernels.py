@@ -78,7 +78,9 @@ def test_project_simt(ops, T, S, l, center):
     assert (Yt[l:] == 0).all()
     Y = np.zeros((lp, S), np.float32)
     Y[:l] = rng.standard_normal((l, S))
-    Z = ops.project_T(f, torch.from_numpy(Y).cuda(), l).cpu().numpy()
+    Yd = ops.space_side(lp, S, zero=True)
+    Yd.copy_(torch.from_numpy(Y))
+    Z = ops.project_T(f, Yd, l).cpu().numpy()
     ref = A @ Y[:l].astype(np.float64).T
     np.testing.assert_allclose(Z[:, :l], ref, atol=2e-5 * np.abs(ref).max())
 

@@ -45,6 +45,8 @@ class CudaOps:
             self.algo = self.accurate_algo = a
         self._ws = None
         self.launches = 0  # kernels enqueued through this object (bench.py reports it)
+        self.time_products = False  # bench.py: CUDA events around every streaming product on the launch stream
+        self._prod_events = []
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -55,6 +57,12 @@ class CudaOps:
 
     def zeros(self, shape, dtype=torch.float32):
         return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def space_side(self, rows, n, zero=False):
+        """(rows x n) fp32 view whose row stride is a multiple of 32 elements (128 B-aligned rows)."""
+        ld = (int(n) + 31) // 32 * 32
+        buf = (torch.zeros if zero else torch.empty)((rows, ld), dtype=torch.float32, device=self.device)
+        return buf[:, :n]
 
     def to_device(self, a, dtype=None):
         t = torch.as_tensor(a)
@@ -68,8 +76,26 @@ class CudaOps:
             self._ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=self.device)
         return self._ws
 
+    def _timed(self, name, l, fn):
+        if not self.time_products:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(self.device))
+        rc = fn()
+        e1.record(torch.cuda.current_stream(self.device))
+        self._prod_events.append((name, e0, e1, l))
+        return rc
+
+    def product_times(self):
+        """[(kernel name, milliseconds, l)] of the timed products (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        return [(n, e0.elapsed_time(e1), l) for n, e0, e1, l in self._prod_events]
+
     # ------------------------------------------------------------------ preprocessing
     def col_stats(self, X):
+        return self._timed("col_stats", 0, lambda: self._col_stats(X))
+
+    def _col_stats(self, X):
         T, S = int(X.shape[0]), int(X.shape[1])
         st = {
             "shift": self.empty(S), "sum": self.empty(S, torch.float64), "sumsq": self.empty(S, torch.float64),
@@ -102,11 +128,11 @@ class CudaOps:
         """Yt (lp x S) = A^T W,  W time-side (T x lp)."""
         algo = self.algo if algo is None else algo
         lp = lpad(l)
-        Yt = out if out is not None else self.empty((lp, f.S))
+        Yt = out if out is not None else self.space_side(lp, f.S)
         ws = self.workspace(f.T, f.S, l, algo)
-        check(self.lib.xeofs_b200_project_S(ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr),
-                                            ptr(W), int(W.stride(0)), l, ptr(Yt), int(Yt.stride(0)), ptr(ws),
-                                            ws.numel(), algo, self._stream()), "project_S")
+        check(self._timed("project_S", l, lambda: self.lib.xeofs_b200_project_S(
+            ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr), ptr(W), int(W.stride(0)), l,
+            ptr(Yt), int(Yt.stride(0)), ptr(ws), ws.numel(), algo, self._stream())), "project_S")
         self.launches += 2
         return Yt
 
@@ -116,9 +142,9 @@ class CudaOps:
         lp = lpad(l)
         Z = out if out is not None else self.empty((f.T, lp))
         ws = self.workspace(f.T, f.S, l, algo)
-        check(self.lib.xeofs_b200_project_T(ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr),
-                                            ptr(Yt), int(Yt.stride(0)), l, ptr(Z), int(Z.stride(0)), ptr(ws),
-                                            ws.numel(), algo, self._stream()), "project_T")
+        check(self._timed("project_T", l, lambda: self.lib.xeofs_b200_project_T(
+            ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr), ptr(Yt), int(Yt.stride(0)), l,
+            ptr(Z), int(Z.stride(0)), ptr(ws), ws.numel(), algo, self._stream())), "project_T")
         self.launches += 2 + (2 if f.ccorr is not None else 0)
         return Z
 
@@ -133,7 +159,7 @@ class CudaOps:
     def chol_inv(self, G, info=None):
         l = int(G.shape[0])
         Rinv = self.empty((l, l), torch.float64)
-        info = info if info is not None else self.empty(1, torch.int32)
+        info = info if info is not None else self.empty(2, torch.int32)
         check(self.lib.xeofs_b200_chol_inv(ptr(G), l, ptr(Rinv), ptr(info), self._stream()), "chol_inv")
         self.launches += 1
         return Rinv, info
@@ -142,7 +168,7 @@ class CudaOps:
         """Out(n, j') = sum_j In(n, j) Mat[j, j'] colscale[j'];  same side/layout as In, kp = lpad(k) columns."""
         kp = lpad(k)
         if out is None:
-            out = self.empty((kp, n)) if side == 1 else self.zeros((n, kp))
+            out = self.space_side(kp, n) if side == 1 else self.zeros((n, kp))
         check(self.lib.xeofs_b200_apply(ptr(In), n, l, int(In.stride(0)), side, ptr(Mat), int(Mat.stride(0)), k,
                                         ptr(colscale), ptr(out), int(out.stride(0)), self._stream()), "apply")
         self.launches += 1
@@ -186,7 +212,7 @@ class CudaOps:
     # ------------------------------------------------------------------ rotation
     def col_norms(self, L, S, m, normalized_out=False):
         h, rn = self.empty(S), self.empty(S)
-        Ln = self.zeros((lpad(m), S)) if normalized_out else None
+        Ln = self.space_side(lpad(m), S, zero=True) if normalized_out else None
         check(self.lib.xeofs_b200_col_norms(ptr(L), S, m, int(L.stride(0)), ptr(h), ptr(rn), ptr(Ln),
                                             S if Ln is None else int(Ln.stride(0)), self._stream()), "col_norms")
         self.launches += 1

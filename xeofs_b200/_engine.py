@@ -220,12 +220,13 @@ def sketch_matrix(ops, n_global, n_local, offset, side, l, random_state):
     rng = random_state if isinstance(random_state, np.random.RandomState) else np.random.RandomState(random_state)
     Om = rng.normal(size=(n_global, l))[offset:offset + n_local].astype(np.float32)
     lp = lpad(l)
-    buf = np.zeros((n_local, lp) if side == 0 else (lp, n_local), dtype=np.float32)
     if side == 0:
+        buf = np.zeros((n_local, lp), dtype=np.float32)
         buf[:, :l] = Om
-    else:
-        buf[:l, :] = Om.T
-    return ops.to_device(buf)
+        return ops.to_device(buf)
+    buf = ops.space_side(lp, n_local, zero=True)
+    buf[:l].copy_(ops.to_device(np.ascontiguousarray(Om.T)))
+    return buf
 
 
 def randomized_svd(ops, op, k, n_oversamples=10, n_iter="auto", random_state=None, comm=NO_COMM,
