@@ -20,7 +20,9 @@
  *      lp = l rounded up to a multiple of 16; pad rows/columns are zero and stay zero;
  *  - per-feature vectors (length S): pivot (subtracted before tensor-core rounding), dscale
  *    (= valid * coslat * weight / std), ccorr (rank-1 correction (pivot - mean_eff) * dscale, may be NULL = 0).
- *    Effective matrix:  A[t,s] = (X[t,s] - pivot[s]) * dscale[s] + ccorr[s],  NaN entries count as 0.
+ *    Effective matrix:  A[t,s] = (X[t,s] - pivot[s]) * dscale[s] + ccorr[s];  a NaN entry counts as 0 in the
+ *    first term.  Samples that are NaN throughout (dropped by the Sanitizer, sanitizer.py:49-50,124) are named by
+ *    row_valid[T] (uint8, NULL = every sample valid): such a row of A is zero altogether.
  */
 #ifndef XEOFS_B200_H
 #define XEOFS_B200_H
@@ -85,11 +87,13 @@ int xeofs_b200_scaling_finalize(int64_t S, const float* shift, const double* sum
  * l is the live column count, lp = round_up(l,16) the stored one.                                    */
 int64_t xeofs_b200_project_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo);
 int xeofs_b200_project_S(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
-                         const float* dscale, const float* ccorr, const float* W, int64_t ldw, int64_t l,
+                         const float* dscale, const float* ccorr, const uint8_t* row_valid, const float* W,
+                         int64_t ldw, int64_t l,
                          float* Yt, int64_t ldy, void* workspace, int64_t workspace_bytes, int algo,
                          void* stream);
 int xeofs_b200_project_T(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
-                         const float* dscale, const float* ccorr, const float* Yt, int64_t ldy, int64_t l,
+                         const float* dscale, const float* ccorr, const uint8_t* row_valid, const float* Yt,
+                         int64_t ldy, int64_t l,
                          float* Z, int64_t ldz, void* workspace, int64_t workspace_bytes, int algo,
                          void* stream);
 

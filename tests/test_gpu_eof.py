@@ -102,6 +102,6 @@ def test_transform_and_inverse_transform():
     np.testing.assert_allclose(m.transform(da).values, sc.values, rtol=1e-3, atol=1e-4)
     rec = m.inverse_transform(sc)
     assert rec.dims == DIMS
-    np.testing.assert_allclose(rec.values, X, rtol=1e-4)
+    np.testing.assert_allclose(rec.values, X, rtol=1e-4, atol=2e-5)
     o = oeof.eof_fit(X, DIMS, "time", coords=coords, n_modes=20, standardize=True, use_coslat=True, solver="full")
     np.testing.assert_allclose(m.singular_values().values[:19], o["singular_values"][:19], rtol=RTOL_S)

@@ -161,3 +161,58 @@ def test_minmax_finish_reconstruct(ops):
     assert np.isnan(rec[:, 10]).all()
     ok = np.arange(S) != 10
     np.testing.assert_allclose(rec[:, ok], ref[:, ok], rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- tcgen05 products
+TC_SHAPES = [(25, 20, 12), (300, 1000, 20), (1000, 4096, 60), (520, 776, 110), (64, 132, 5), (8760, 2500, 60),
+             (200, 70000, 40)]
+
+
+def _tc_case(T, S, l, center, seed):
+    from xeofs_b200._lib import lpad
+    rng = np.random.default_rng(seed)
+    X = (280 + 3 * rng.standard_normal((T, S))).astype(np.float32)
+    X[:, 1] = np.nan
+    if T > 30:
+        X[7] = np.nan       # an all-NaN sample contributes zeros
+    featw = rng.uniform(0.5, 1.5, S)
+    lp = lpad(l)
+    W = np.zeros((T, lp), np.float32)
+    W[:, :l] = rng.standard_normal((T, l))
+    Y = np.zeros((lp, S), np.float32)
+    Y[:l] = rng.standard_normal((l, S))
+    return X, featw, W, Y, lp
+
+
+@pytest.mark.parametrize("T,S,l", TC_SHAPES)
+@pytest.mark.parametrize("center", [True, False])
+@pytest.mark.parametrize("algo,tol", [("tf32x3", 2e-5), ("tf32x1", 3e-3), ("simt", 2e-5)])
+def test_project_tcgen05(T, S, l, center, algo, tol):
+    """tcgen05 kind::tf32 kernels (A operand in TMEM, B by TMA) against the fp64 statement of A^T W and A Y.
+    3xTF32 must be as accurate as the fp32 SIMT kernel; single TF32 carries 2^-11 operand rounding."""
+    from xeofs_b200 import _lib
+    from xeofs_b200._cuda_ops import CudaOps
+    ops = CudaOps(algo="simt")
+    a = _lib.ALGO_NAMES[algo]
+    X, featw, W, Y, lp = _tc_case(T, S, l, center, seed=T + S + l)
+    Xd = ops.space_side(T, S)
+    Xd.copy_(torch.from_numpy(X))
+    from xeofs_b200._cuda_ops import Field
+    st = ops.col_stats(Xd)
+    fin = ops.scaling_finalize(st, torch.as_tensor(featw, dtype=torch.float64).cuda(), center, True)
+    row_valid = (st["row_nan"] < S).to(torch.uint8)
+    f = Field(Xd, fin["pivot"], fin["dscale"], fin["ccorr"], fin["valid"], fin["mean"], fin["std"], row_valid)
+    A = np.nan_to_num(_A_ref(X, featw, center, True), nan=0.0)
+    Yt = ops.project_S(f, torch.from_numpy(W).cuda(), l, algo=a).cpu().numpy()
+    ref = (A.T @ W[:, :l].astype(np.float64)).T
+    np.testing.assert_allclose(Yt[:l], ref, atol=tol * np.abs(ref).max())
+    assert (Yt[l:] == 0).all()
+    Yd = ops.space_side(lp, S, zero=True)
+    Yd.copy_(torch.from_numpy(Y))
+    Z = ops.project_T(f, Yd, l, algo=a).cpu().numpy()
+    ref = A @ Y[:l].astype(np.float64).T
+    np.testing.assert_allclose(Z[:, :l], ref, atol=tol * np.abs(ref).max())
+    # the deterministic split reduction: a second call is bit-identical
+    if algo != "simt":  # the SIMT validation kernels combine their split sums with atomics
+        Z2 = ops.project_T(f, Yd, l, algo=a).cpu().numpy()
+        np.testing.assert_array_equal(Z, Z2)

@@ -17,13 +17,14 @@ class Field:
     vectors that fold Scaler.transform (preprocessing/scaler.py:146-153) into the operand load:
     A[t,s] = (X[t,s] - pivot[s]) * dscale[s] + ccorr[s]."""
 
-    def __init__(self, X, pivot, dscale, ccorr, valid, mean=None, std=None):
+    def __init__(self, X, pivot, dscale, ccorr, valid, mean=None, std=None, row_valid=None):
         self.X = X
         self.T, self.S = int(X.shape[0]), int(X.shape[1])
         self.ldx = int(X.stride(0))
         self.pivot, self.dscale, self.ccorr = pivot, dscale, ccorr
         self.valid = valid
         self.mean, self.std = mean, std
+        self.row_valid = row_valid  # (T,) uint8, None = every sample valid (sanitizer.py:49-50)
 
 
 class CudaOps:
@@ -131,7 +132,8 @@ class CudaOps:
         Yt = out if out is not None else self.space_side(lp, f.S)
         ws = self.workspace(f.T, f.S, l, algo)
         check(self._timed("project_S", l, lambda: self.lib.xeofs_b200_project_S(
-            ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr), ptr(W), int(W.stride(0)), l,
+            ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr), ptr(f.row_valid), ptr(W),
+            int(W.stride(0)), l,
             ptr(Yt), int(Yt.stride(0)), ptr(ws), ws.numel(), algo, self._stream())), "project_S")
         self.launches += 2
         return Yt
@@ -143,7 +145,8 @@ class CudaOps:
         Z = out if out is not None else self.empty((f.T, lp))
         ws = self.workspace(f.T, f.S, l, algo)
         check(self._timed("project_T", l, lambda: self.lib.xeofs_b200_project_T(
-            ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr), ptr(Yt), int(Yt.stride(0)), l,
+            ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr), ptr(f.row_valid), ptr(Yt),
+            int(Yt.stride(0)), l,
             ptr(Z), int(Z.stride(0)), ptr(ws), ws.numel(), algo, self._stream())), "project_T")
         self.launches += 2 + (2 if f.ccorr is not None else 0)
         return Z

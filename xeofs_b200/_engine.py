@@ -117,7 +117,10 @@ def fit_field(ops, X, featw=None, center=True, standardize=False, check_nans=Tru
             )
     n_samples = int(valid_sample.sum().item())
     ff = FittedField()
-    ff.field = Field(X, fin["pivot"], fin["dscale"], fin["ccorr"], fin["valid"], fin["mean"], fin["std"])
+    # centred: pivot == mean, the rank-1 term vanishes;  all-NaN samples are named to the kernels only when present
+    ccorr = None if center else fin["ccorr"]
+    row_valid = valid_sample.to(torch.uint8) if n_samples < T else None
+    ff.field = Field(X, fin["pivot"], fin["dscale"], ccorr, fin["valid"], fin["mean"], fin["std"], row_valid)
     ff.mean, ff.std, ff.valid, ff.featw = fin["mean"], fin["std"], fin["valid"], featw
     ff.valid_sample, ff.n_samples, ff.n_features = valid_sample, n_samples, n_valid
     ff.total_variance = total_variance
@@ -138,6 +141,10 @@ class FieldOperator:
         t_dim, s_dim = (ff.T, ff.T, 0), (ff.S_global, ff.S, 1)
         self.r, self.c = (s_dim, t_dim) if self.transposed else (t_dim, s_dim)
         self.shape = (ff.n_features, ff.n_samples) if self.transposed else (ff.n_samples, ff.n_features)
+        # which entries of M's column space exist in the reference's (compacted) matrix
+        t_mask = ff.valid_sample if ff.n_samples < ff.T else None
+        s_mask = ff.valid.bool() if ff.n_features < ff.S_global else None
+        self.c_mask = t_mask if self.transposed else s_mask
 
     def _proj_S(self, W, l, algo):
         return self.ops.project_S(self.ff.field, W, l, algo=algo)
@@ -175,8 +182,9 @@ class CrossOperator:
         self.transposed = fx.n_features < fy.n_features
         x_dim, y_dim = (fx.S_global, fx.S, 1), (fy.S_global, fy.S, 1)
         self.r, self.c = (y_dim, x_dim) if self.transposed else (x_dim, y_dim)
-        self.shape = (self.r[0], self.c[0]) if False else (
-            (fy.n_features, fx.n_features) if self.transposed else (fx.n_features, fy.n_features))
+        self.shape = (fy.n_features, fx.n_features) if self.transposed else (fx.n_features, fy.n_features)
+        cf = fx if self.transposed else fy
+        self.c_mask = cf.valid.bool() if cf.n_features < cf.S_global else None
 
     def _through(self, f_in, f_out, Q, l, algo):
         Z = self.ops.project_T(f_in.field, Q, l, algo=algo)
@@ -214,23 +222,39 @@ def orthonormalize(ops, M, dim, l, comm, passes, infos):
     return M
 
 
-def sketch_matrix(ops, n_global, n_local, offset, side, l, random_state):
-    """sklearn.utils.extmath.randomized_range_finder: Q = rng.normal(size=(M.shape[1], l)), generated on
-    the host with numpy's RandomState so that the oracle and the device path share the sketch."""
+def sketch_matrix(ops, op, l, random_state, comm=NO_COMM):
+    """sklearn.utils.extmath.randomized_range_finder: Q = rng.normal(size=(M.shape[1], l)) with M the reference's
+    compacted matrix (all-NaN samples / features dropped), generated on the host with numpy's RandomState so that
+    the oracle and the device path share the sketch; rows are scattered to the entries that survive the Sanitizer."""
     rng = random_state if isinstance(random_state, np.random.RandomState) else np.random.RandomState(random_state)
-    Om = rng.normal(size=(n_global, l))[offset:offset + n_local].astype(np.float32)
+    n_valid_global = op.shape[1]
+    n_local, side, mask = op.c[1], op.c[2], op.c_mask
+    Om = rng.normal(size=(n_valid_global, l))
+    n_loc_valid = n_local if mask is None else int(mask.sum().item())
+    offset = 0
+    if side == 1 and comm.active:  # features are sharded: this rank's first valid feature in the global order
+        counts = torch.zeros(comm.world, dtype=torch.int64, device=ops.device)
+        counts[comm.rank] = n_loc_valid
+        comm.sum_(counts)
+        offset = int(counts[: comm.rank].sum().item())
+    Om = ops.to_device(np.ascontiguousarray(Om[offset:offset + n_loc_valid], dtype=np.float32))
     lp = lpad(l)
     if side == 0:
-        buf = np.zeros((n_local, lp), dtype=np.float32)
-        buf[:, :l] = Om
-        return ops.to_device(buf)
+        buf = ops.zeros((n_local, lp))
+        if mask is None:
+            buf[:, :l] = Om
+        else:
+            buf[mask, :l] = Om
+        return buf
     buf = ops.space_side(lp, n_local, zero=True)
-    buf[:l].copy_(ops.to_device(np.ascontiguousarray(Om.T)))
+    if mask is None:
+        buf[:l] = Om.t()
+    else:
+        buf[:l, mask] = Om.t()
     return buf
 
 
-def randomized_svd(ops, op, k, n_oversamples=10, n_iter="auto", random_state=None, comm=NO_COMM,
-                   shard_offset=0, Omega=None):
+def randomized_svd(ops, op, k, n_oversamples=10, n_iter="auto", random_state=None, comm=NO_COMM, Omega=None):
     """Halko et al. range finder + small SVD, the arithmetic of sklearn.utils.extmath.randomized_svd
     (power_iteration_normalizer='auto', transpose='auto') with CholeskyQR as the normalizer.
 
@@ -247,8 +271,7 @@ def randomized_svd(ops, op, k, n_oversamples=10, n_iter="auto", random_state=Non
         n_iter = 7 if k < 0.1 * min(n_r, n_c) else 4
     infos = []
     if Omega is None:
-        off = shard_offset if op.c[2] == 1 else 0
-        Q = sketch_matrix(ops, op.sketch_rows(), op.c[1], off, op.c[2], l, random_state)
+        Q = sketch_matrix(ops, op, l, random_state, comm)
     else:
         Q = Omega
     for _ in range(int(n_iter)):

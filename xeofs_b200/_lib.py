@@ -30,8 +30,8 @@ SIGNATURES = {
     "xeofs_b200_col_stats": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "xeofs_b200_scaling_finalize": (_int, [_i64, _p, _p, _p, _p, _p, _int, _p, _p, _p, _p, _p, _p, _p, _p]),
     "xeofs_b200_project_workspace_bytes": (_i64, [_i64, _i64, _i64, _int]),
-    "xeofs_b200_project_S": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _int, _p]),
-    "xeofs_b200_project_T": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _int, _p]),
+    "xeofs_b200_project_S": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _int, _p]),
+    "xeofs_b200_project_T": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _int, _p]),
     "xeofs_b200_gram": (_int, [_p, _i64, _i64, _i64, _int, _p, _int, _p]),
     "xeofs_b200_chol_inv": (_int, [_p, _i64, _p, _p, _p]),
     "xeofs_b200_apply": (_int, [_p, _i64, _i64, _i64, _int, _p, _i64, _i64, _p, _p, _i64, _p]),

@@ -93,7 +93,7 @@ class Preprocessor:
             raise ValueError(f"Feature shape {feature_shape} differs from the fitted one {self.feature_shape}.")
         ff = self.fitted
         f = ff.field
-        new = Field(X2, f.pivot, f.dscale, f.ccorr, f.valid, f.mean, f.std)
+        new = Field(X2, f.pivot, f.dscale, f.ccorr, f.valid, f.mean, f.std, None)
         valid_sample = None
         if self.check_nans:
             st = self.ops.col_stats(X2)
@@ -111,6 +111,8 @@ class Preprocessor:
             if not bool(ok.all().item()):
                 raise ValueError("Input data contains partial NaN entries, which will cause the the SVD to fail.")
             valid_sample = row_nan < ff.S_global
+            if not bool(valid_sample.all().item()):
+                new.row_valid = valid_sample.to(torch.uint8)
         sample_coords = {d: coords[d] for d in self.sample_dims if d in coords}
         return new, sample_shape, sample_coords, valid_sample
 

@@ -85,8 +85,7 @@ class MCA:
             n_over, n_iter = kw.get("n_oversamples", 10), kw.get("n_iter", "auto")
         c_field = f1 if op.transposed else f2
         Ur, s, Vc, infos = E.randomized_svd(ops, op, k, n_oversamples=n_over, n_iter=n_iter,
-                                            random_state=p["random_state"], comm=comm,
-                                            shard_offset=self._shard_offset(c_field.S))
+                                            random_state=p["random_state"], comm=comm)
         E.check_infos(infos)
         # C = Q1 s Q2^T;  M = C^T when transposed
         Q1t, Q2t = (Vc, Ur) if op.transposed else (Ur, Vc)

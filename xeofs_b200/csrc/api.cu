@@ -29,17 +29,17 @@ int num_sms() {
 }
 
 // project_simt.cu
-int project_S_simt(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const float*,
-                   int64_t, int64_t, float*, int64_t, float*, cudaStream_t);
-int project_T_simt(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const float*,
-                   int64_t, int64_t, float*, int64_t, float*, cudaStream_t);
+int project_S_simt(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const uint8_t*,
+                   const float*, int64_t, int64_t, float*, int64_t, float*, cudaStream_t);
+int project_T_simt(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const uint8_t*,
+                   const float*, int64_t, int64_t, float*, int64_t, float*, cudaStream_t);
 // project_tc.cu
 bool tc_supported(int64_t T, int64_t S, int64_t ldx, const float* X, int64_t l);
 int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo);
-int project_S_tc(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const float*,
-                 int64_t, int64_t, float*, int64_t, void*, int64_t, int, cudaStream_t);
-int project_T_tc(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const float*,
-                 int64_t, int64_t, float*, int64_t, void*, int64_t, int, cudaStream_t);
+int project_S_tc(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const uint8_t*,
+                 const float*, int64_t, int64_t, float*, int64_t, void*, int64_t, int, cudaStream_t);
+int project_T_tc(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const uint8_t*,
+                 const float*, int64_t, int64_t, float*, int64_t, void*, int64_t, int, cudaStream_t);
 
 }  // namespace xb
 
@@ -88,8 +88,8 @@ static int check_project_args(const char* who, const float* X, int64_t T, int64_
 }
 
 extern "C" int xeofs_b200_project_S(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
-                                    const float* dscale, const float* ccorr, const float* W, int64_t ldw, int64_t l,
-                                    float* Yt, int64_t ldy, void* workspace, int64_t workspace_bytes, int algo,
+                                    const float* dscale, const float* ccorr, const uint8_t* row_valid, const float* W,
+                                    int64_t ldw, int64_t l, float* Yt, int64_t ldy, void* workspace, int64_t workspace_bytes, int algo,
                                     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = check_project_args("project_S", X, T, S, ldx, pivot, dscale, W, Yt, ldw, ldy, l, workspace, workspace_bytes, algo);
@@ -97,17 +97,17 @@ extern "C" int xeofs_b200_project_S(const float* X, int64_t T, int64_t S, int64_
   XB_CHECK_ARG(ldw >= lpad(l) && ldy >= S, "project_S: ldw=%lld must be >= lp and ldy=%lld >= S", (long long)ldw, (long long)ldy);
   algo = resolve_algo(algo, T, S, ldx, X, l);
   if (algo == XEOFS_ALGO_SIMT)
-    return project_S_simt(X, T, S, ldx, pivot, dscale, ccorr, W, ldw, l, Yt, ldy, (float*)workspace, stream);
+    return project_S_simt(X, T, S, ldx, pivot, dscale, ccorr, row_valid, W, ldw, l, Yt, ldy, (float*)workspace, stream);
   if (!xeofs_b200_has_tcgen05() || !tc_supported(T, S, ldx, X, l)) {
     set_error("project_S: tcgen05 path unavailable for this device/shape (need sm_100, ldx %% 4 == 0, 16-byte aligned X)");
     return XEOFS_E_UNSUPPORTED;
   }
-  return project_S_tc(X, T, S, ldx, pivot, dscale, ccorr, W, ldw, l, Yt, ldy, workspace, workspace_bytes, algo, stream);
+  return project_S_tc(X, T, S, ldx, pivot, dscale, ccorr, row_valid, W, ldw, l, Yt, ldy, workspace, workspace_bytes, algo, stream);
 }
 
 extern "C" int xeofs_b200_project_T(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
-                                    const float* dscale, const float* ccorr, const float* Yt, int64_t ldy, int64_t l,
-                                    float* Z, int64_t ldz, void* workspace, int64_t workspace_bytes, int algo,
+                                    const float* dscale, const float* ccorr, const uint8_t* row_valid, const float* Yt,
+                                    int64_t ldy, int64_t l, float* Z, int64_t ldz, void* workspace, int64_t workspace_bytes, int algo,
                                     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = check_project_args("project_T", X, T, S, ldx, pivot, dscale, Yt, Z, ldy, ldz, l, workspace, workspace_bytes, algo);
@@ -115,10 +115,10 @@ extern "C" int xeofs_b200_project_T(const float* X, int64_t T, int64_t S, int64_
   XB_CHECK_ARG(ldz >= lpad(l) && ldy >= S, "project_T: ldz=%lld must be >= lp and ldy=%lld >= S", (long long)ldz, (long long)ldy);
   algo = resolve_algo(algo, T, S, ldx, X, l);
   if (algo == XEOFS_ALGO_SIMT)
-    return project_T_simt(X, T, S, ldx, pivot, dscale, ccorr, Yt, ldy, l, Z, ldz, (float*)workspace + lpad(l), stream);
+    return project_T_simt(X, T, S, ldx, pivot, dscale, ccorr, row_valid, Yt, ldy, l, Z, ldz, (float*)workspace + lpad(l), stream);
   if (!xeofs_b200_has_tcgen05() || !tc_supported(T, S, ldx, X, l)) {
     set_error("project_T: tcgen05 path unavailable for this device/shape (need sm_100, ldx %% 4 == 0, 16-byte aligned X)");
     return XEOFS_E_UNSUPPORTED;
   }
-  return project_T_tc(X, T, S, ldx, pivot, dscale, ccorr, Yt, ldy, l, Z, ldz, workspace, workspace_bytes, algo, stream);
+  return project_T_tc(X, T, S, ldx, pivot, dscale, ccorr, row_valid, Yt, ldy, l, Z, ldz, workspace, workspace_bytes, algo, stream);
 }

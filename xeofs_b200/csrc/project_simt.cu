@@ -8,13 +8,15 @@ namespace xb {
 
 // ------------------------------------------------------------------------------------------------
 // column sums of W (T x lp) -> out[lp]   (needed for the rank-1 correction of project_S)
-__global__ void colsum_kernel(const float* __restrict__ W, int64_t T, int64_t ldw, int lp, float* __restrict__ out) {
+__global__ void colsum_kernel(const float* __restrict__ W, int64_t T, int64_t ldw, int lp,
+                              const uint8_t* __restrict__ row_valid, float* __restrict__ out) {
   // one block per 32 columns, 8 warps stride over rows
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   const int w = threadIdx.x >> 5;
   double acc = 0;
   if (j < lp)
-    for (int64_t t = w; t < T; t += 8) acc += (double)W[t * ldw + j];
+    for (int64_t t = w; t < T; t += 8)
+      if (!row_valid || row_valid[t]) acc += (double)W[t * ldw + j];
   __shared__ double sh[8][32];
   sh[w][threadIdx.x & 31] = acc;
   __syncthreads();
@@ -43,13 +45,14 @@ __global__ void ccorr_dot_kernel(const float* __restrict__ Yt, int64_t S, int64_
   }
 }
 
-// Z[t, j] += r[j]
-__global__ void add_rowvec_kernel(float* __restrict__ Z, int64_t T, int64_t ldz, int l, const float* __restrict__ r) {
+// Z[t, j] += r[j] on the valid samples
+__global__ void add_rowvec_kernel(float* __restrict__ Z, int64_t T, int64_t ldz, int l, const float* __restrict__ r,
+                                  const uint8_t* __restrict__ row_valid) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < T * l) {
     int64_t t = i / l;
     int j = (int)(i % l);
-    Z[t * ldz + j] += r[j];
+    if (!row_valid || row_valid[t]) Z[t * ldz + j] += r[j];
   }
 }
 
@@ -228,11 +231,24 @@ project_T_simt_kernel(const float* __restrict__ X, int64_t T, int64_t S, int64_t
   }
 }
 
+int launch_colsum(const float* W, int64_t T, int64_t ldw, int lp, const uint8_t* row_valid, float* out,
+                  cudaStream_t stream) {
+  colsum_kernel<<<(lp + 31) / 32, 256, 0, stream>>>(W, T, ldw, lp, row_valid, out);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
+int launch_ccorr_dot(const float* Yt, int64_t S, int64_t ldy, const float* ccorr, int lp, float* out, cudaStream_t stream) {
+  ccorr_dot_kernel<<<(unsigned)lp, 256, 0, stream>>>(Yt, S, ldy, ccorr, out);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
 int project_S_simt(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot, const float* dscale,
-                   const float* ccorr, const float* W, int64_t ldw, int64_t l, float* Yt, int64_t ldy,
+                   const float* ccorr, const uint8_t* row_valid, const float* W, int64_t ldw, int64_t l, float* Yt, int64_t ldy,
                    float* wsum /* lp floats of workspace */, cudaStream_t stream) {
   const int lp = (int)lpad(l);
-  colsum_kernel<<<(lp + 31) / 32, 256, 0, stream>>>(W, T, ldw, lp, wsum);
+  colsum_kernel<<<(lp + 31) / 32, 256, 0, stream>>>(W, T, ldw, lp, row_valid, wsum);
   XB_LAUNCH_CHECK();
   const bool vec = (ldx % 4 == 0) && ((uintptr_t)X % 16 == 0);
   dim3 grid((unsigned)ceil_div(S, PS_BS), (unsigned)ceil_div(lp, PS_BJ));
@@ -244,18 +260,18 @@ int project_S_simt(const float* X, int64_t T, int64_t S, int64_t ldx, const floa
   return XEOFS_OK;
 }
 
-int project_T_finish(const float* Yt, int64_t T, int64_t S, int64_t ldy, const float* ccorr, int64_t l, float* Z,
-                     int64_t ldz, float* rvec /* lp floats */, cudaStream_t stream) {
+int project_T_finish(const float* Yt, int64_t T, int64_t S, int64_t ldy, const float* ccorr, const uint8_t* row_valid,
+                     int64_t l, float* Z, int64_t ldz, float* rvec /* lp floats */, cudaStream_t stream) {
   if (!ccorr) return XEOFS_OK;
   ccorr_dot_kernel<<<(unsigned)l, 256, 0, stream>>>(Yt, S, ldy, ccorr, rvec);
   XB_LAUNCH_CHECK();
-  add_rowvec_kernel<<<(unsigned)ceil_div(T * l, 256), 256, 0, stream>>>(Z, T, ldz, (int)l, rvec);
+  add_rowvec_kernel<<<(unsigned)ceil_div(T * l, 256), 256, 0, stream>>>(Z, T, ldz, (int)l, rvec, row_valid);
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
 }
 
 int project_T_simt(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot, const float* dscale,
-                   const float* ccorr, const float* Yt, int64_t ldy, int64_t l, float* Z, int64_t ldz,
+                   const float* ccorr, const uint8_t* row_valid, const float* Yt, int64_t ldy, int64_t l, float* Z, int64_t ldz,
                    float* rvec, cudaStream_t stream) {
   const int lp = (int)lpad(l);
   XB_CUDA(cudaMemsetAsync(Z, 0, (size_t)T * ldz * sizeof(float), stream));
@@ -272,7 +288,7 @@ int project_T_simt(const float* X, int64_t T, int64_t S, int64_t ldx, const floa
   else
     project_T_simt_kernel<false><<<grid, 256, 0, stream>>>(X, T, S, ldx, pivot, dscale, Yt, ldy, lp, Z, ldz, spb);
   XB_LAUNCH_CHECK();
-  return project_T_finish(Yt, T, S, ldy, ccorr, l, Z, ldz, rvec, stream);
+  return project_T_finish(Yt, T, S, ldy, ccorr, row_valid, l, Z, ldz, rvec, stream);
 }
 
 }  // namespace xb

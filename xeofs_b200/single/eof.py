@@ -87,8 +87,7 @@ class EOF:
         else:
             n_over, n_iter = kw.get("n_oversamples", 10), kw.get("n_iter", "auto")
         Ur, s, Vc, infos = E.randomized_svd(ops, op, k, n_oversamples=n_over, n_iter=n_iter,
-                                            random_state=p["random_state"], comm=comm,
-                                            shard_offset=self._shard_offset(ff))
+                                            random_state=p["random_state"], comm=comm)
         E.check_infos(infos)
         # un-transpose: A = U s V^T with V on the space side
         Vt, Ut = (Ur, Vc) if op.transposed else (Vc, Ur)
