@@ -23,6 +23,8 @@
 // 2.2e-5 after 8760 rows).  The 3xTF32 kernels therefore alternate between two TMEM accumulators and move each
 // finished group of TC_FLUSH stages (64 K=8 steps) into fp32 registers of the epilogue warps (round-to-nearest adds).
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -122,6 +124,23 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+
 __device__ __forceinline__ uint32_t to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -138,36 +157,60 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
 }
 
+
 struct TcParams {
   int64_t T, S;
   int lp;             // N of the MMA (multiple of 16, <= 128)
   int stages;
-  int nchunks_total;  // K-chunks over the whole K extent
+  int nchunks_total;  // stages' worth of K (32*KB values each) over the whole K extent
   int chunks_per_cta; // project_T: K-chunks per split (project_S: = nchunks_total)
-  const float* pivot;   // project_S: [S];  project_T: zero-padded copy, multiple of 32 long
+  int dcols;          // TMEM columns per accumulator buffer (lp rounded up to 32)
+  const float* pivot;   // project_S: [S];  project_T: zero-padded copy (multiple of 128 long)
   const float* dscale;  // same
   const float* ccorr;   // project_S epilogue (may be null)
   const float* wsum;    // project_S epilogue: column sums of W [lp]
   float* out;           // project_S: Yt (ldo = ldy);  project_T: partial sums [split][tiles*128][lp]
   int64_t ldo;
   uint32_t tmem_cols;
+  const float* X;       // project_T: rows are fetched with one bulk copy each
+  int64_t ldx;
+  const float* bimg_hi; // small operand as a sequence of shared-memory images, one per 32-wide K slab:
+  const float* bimg_lo; //   [slab][lp rows][32 k], 16-byte chunks XOR-swizzled by (row & 7)  (lo: 3xTF32 only)
+};
+
+struct Pipe {
+  int st = 0;
+  uint32_t ph = 0;
+  __device__ __forceinline__ void advance(int stages) {
+    if (++st == stages) { st = 0; ph ^= 1; }
+  }
 };
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int NS, bool SIDE_T>
-__global__ void __launch_bounds__(TC_THREADS, NS == 1 ? 2 : 1)
+// NS: 1 = single TF32 product, 3 = 3xTF32.  SIDE_T: false = project_S, true = project_T.
+// KB: 32-wide K slabs per pipeline stage (project_T reads KB*128 contiguous bytes of every row per TMA box).
+template <int NS, bool SIDE_T, int KB>
+__global__ void __launch_bounds__(TC_THREADS, (NS == 1 && KB == 1) ? 2 : 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBhi,
                   const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
+  static_assert(SIDE_T || KB == 1, "project_S stages are 32 rows of t");
+  constexpr int NPART = NS == 3 ? 2 : 1;            // operand parts kept per value (hi | lo)
+  // project_T: a stage holds 128 rows of KB*32 (+4) floats, KB*128 + 16 bytes apart: TMA fetches them as 128 long
+  // pieces (the engine's cost is per piece, about 7 cycles, whatever its length), one thread then reads one row, and
+  // the odd multiple of 16 bytes spreads the rows of a quarter-warp over all banks without a swizzle
+  constexpr int XPITCH = SIDE_T ? KB * 128 + 16 : TC_TILE * 4;
+  constexpr int XB = SIDE_T ? TC_TILE * XPITCH : TC_XBYTES;  // bytes of X per stage
+  constexpr int ACOLS = TC_KC * KB * NPART;         // TMEM columns of one A-operand slot
+  constexpr int FLUSH_STAGES = TC_FLUSH / KB;       // stages per accumulator flush group (NS == 3)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stages = p.stages, lp = p.lp;
-  const int bbytes = lp * TC_KC * 4;
-  uint8_t* xs = smem;                                   // [stages][16 KB]
-  uint8_t* bhi = xs + (size_t)stages * TC_XBYTES;       // [stages][lp*128 B]
-  uint8_t* blo = bhi + (size_t)stages * bbytes;         // [stages][lp*128 B]   (NS == 3)
-  uint8_t* pd = blo + (NS == 3 ? (size_t)stages * bbytes : 0);  // [stages][256 B] pivot | dscale (SIDE_T)
-  uint64_t* bars = (uint64_t*)(pd + (size_t)stages * 256);
+  const int bbytes = lp * TC_KC * 4;                    // one K-major slab of the small operand
+  uint8_t* xs = smem;                                   // [stages][XB]
+  uint8_t* bs = xs + (size_t)stages * XB;               // [stages][NPART][KB][bbytes]
+  uint8_t* pd = bs + (size_t)stages * NPART * KB * bbytes;  // [stages][pivot KB*128 B | dscale KB*128 B] (SIDE_T)
+  uint64_t* bars = (uint64_t*)(pd + (SIDE_T ? (size_t)stages * KB * 256 : 0));
   uint64_t* full = bars;                       // TMA bytes landed
   uint64_t* empty = bars + TC_MAX_STAGES;      // MMAs of the stage retired
   uint64_t* aready = bars + 2 * TC_MAX_STAGES; // A operand of the stage is in TMEM
@@ -196,72 +239,93 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t a_cols_per_stage = TC_KC * (NS == 3 ? 2 : 1);
-  const uint32_t a_col0 = NS == 3 ? 2 * TC_D_COLS : TC_D_COLS;  // first TMEM column of the A-operand ring
+  const uint32_t a_col0 = (NS == 3 ? 2 : 1) * p.dcols;  // first TMEM column of the A-operand ring
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      const uint32_t tx = TC_XBYTES + bbytes * (NS == 3 ? 2 : 1) + (SIDE_T ? 256 : 0);
-      for (int c = 0; c < nchunks; ++c) {
-        const int st = c % stages;
-        const uint32_t ph = (c / stages) & 1;
-        mbar_wait(&empty[st], ph ^ 1);
-        mbar_expect_tx(&full[st], tx);
-        const int k0 = (chunk0 + c) * TC_KC;
-        if (!SIDE_T) {
-          tma_load_2d(xs + (size_t)st * TC_XBYTES, &mapX, (int)tile0, k0, &full[st], HINT_EVICT_FIRST);
-        } else {
-          tma_load_2d(xs + (size_t)st * TC_XBYTES, &mapX, k0, (int)tile0, &full[st], HINT_EVICT_FIRST);
-          bulk_load_1d(pd + st * 256, p.pivot + k0, 128, &full[st]);
-          bulk_load_1d(pd + st * 256 + 128, p.dscale + k0, 128, &full[st]);
+    if (!SIDE_T) {
+      if (lane == 0) {
+        const uint32_t tx = XB + bbytes * NPART;
+        Pipe pp;
+        for (int c = 0; c < nchunks; ++c, pp.advance(stages)) {
+          const int st = pp.st;
+          mbar_wait(&empty[st], pp.ph ^ 1);
+          mbar_expect_tx(&full[st], tx);
+          tma_load_2d(xs + (size_t)st * XB, &mapX, (int)tile0, c * TC_KC, &full[st], HINT_EVICT_FIRST);
+          uint8_t* b = bs + (size_t)st * NPART * bbytes;
+          tma_load_2d(b, &mapBhi, 0, c * (lp >> 3), &full[st], HINT_EVICT_LAST);
+          if (NS == 3) tma_load_2d(b + bbytes, &mapBlo, 0, c * (lp >> 3), &full[st], HINT_EVICT_LAST);
         }
-        tma_load_2d(bhi + (size_t)st * bbytes, &mapBhi, k0, 0, &full[st], HINT_EVICT_LAST);
-        if (NS == 3) tma_load_2d(blo + (size_t)st * bbytes, &mapBlo, k0, 0, &full[st], HINT_EVICT_LAST);
+      }
+    } else if (lane == 0) {
+      const uint32_t tx = XB + bbytes * NPART * KB + KB * 256;
+      Pipe pp;
+      for (int c = 0; c < nchunks; ++c, pp.advance(stages)) {
+        const int st = pp.st;
+        const int k0 = (chunk0 + c) * TC_KC * KB;
+        mbar_wait(&empty[st], pp.ph ^ 1);
+        mbar_expect_tx(&full[st], tx);
+        tma_load_2d(xs + (size_t)st * XB, &mapX, k0, (int)tile0, &full[st], HINT_EVICT_FIRST);
+        bulk_load_1d(pd + st * KB * 256, p.pivot + 2 * k0, KB * 256, &full[st]);
+        uint8_t* b = bs + (size_t)st * NPART * KB * bbytes;
+        tma_load_2d(b, &mapBhi, 0, (chunk0 + c) * KB * (lp >> 3), &full[st], HINT_EVICT_LAST);
+        if (NS == 3) tma_load_2d(b + (size_t)KB * bbytes, &mapBlo, 0, (chunk0 + c) * KB * (lp >> 3), &full[st], HINT_EVICT_LAST);
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc(lp);
-      for (int c = 0; c < nchunks; ++c) {
-        const int st = c % stages;
-        const uint32_t ph = (c / stages) & 1;
+      Pipe pp;
+      int g = 0, cg = 0;  // flush group and stage within it (NS == 3)
+      for (int c = 0; c < nchunks; ++c, pp.advance(stages)) {
+        const int st = pp.st;
         uint32_t d_tmem = tmem_base;
         bool first = c == 0;
         if (NS == 3) {
-          const int g = c / TC_FLUSH, buf = g & 1;
-          first = (c % TC_FLUSH) == 0;
+          const int buf = g & 1;
+          first = cg == 0;
           if (first) {
             mbar_wait(&dempty[buf], (((uint32_t)g >> 1) & 1) ^ 1);  // registers hold what this buffer had
             tc_fence_after();
           }
-          d_tmem = tmem_base + buf * TC_D_COLS;
+          d_tmem = tmem_base + buf * p.dcols;
         }
-        mbar_wait(&full[st], ph);
-        mbar_wait(&aready[st], ph);
+        mbar_wait(&full[st], pp.ph);
+        mbar_wait(&aready[st], pp.ph);
         tc_fence_after();
-        const uint32_t a_hi = tmem_base + a_col0 + st * a_cols_per_stage;
-        const uint64_t dh = make_b_desc(smem_u32(bhi + (size_t)st * bbytes));
-        const uint64_t dl = NS == 3 ? make_b_desc(smem_u32(blo + (size_t)st * bbytes)) : 0;
+        const uint32_t a_hi = tmem_base + a_col0 + st * ACOLS;
+        const uint32_t b0 = smem_u32(bs + (size_t)st * NPART * KB * bbytes);
 #pragma unroll
-        for (int k = 0; k < TC_KC / 8; ++k) {
-          // +32 bytes (8 tf32) along K inside the swizzle atom = +2 in the (address >> 4) field
-          mma_tf32_ts(d_tmem, a_hi + k * 8, dh + 2 * k, idesc, !(first && k == 0));
-          if (NS == 3) {
-            mma_tf32_ts(d_tmem, a_hi + k * 8, dl + 2 * k, idesc, 1);
-            mma_tf32_ts(d_tmem, a_hi + TC_KC + k * 8, dh + 2 * k, idesc, 1);
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t dh = make_b_desc(b0 + kb * bbytes);
+          const uint64_t dl = NS == 3 ? make_b_desc(b0 + (KB + kb) * bbytes) : 0;
+#pragma unroll
+          for (int k = 0; k < TC_KC / 8; ++k) {
+            // +32 bytes (8 tf32) along K inside the swizzle atom = +2 in the (address >> 4) field
+            const uint32_t a = a_hi + kb * TC_KC + k * 8;
+            mma_tf32_ts(d_tmem, a, dh + 2 * k, idesc, !(first && kb == 0 && k == 0));
+            if (NS == 3) {
+              mma_tf32_ts(d_tmem, a, dl + 2 * k, idesc, 1);
+              mma_tf32_ts(d_tmem, a + TC_KC * KB, dh + 2 * k, idesc, 1);
+            }
           }
         }
         mma_commit(&empty[st]);
-        if (NS == 3 && ((c % TC_FLUSH) == TC_FLUSH - 1 || c == nchunks - 1)) mma_commit(&dfull[(c / TC_FLUSH) & 1]);
+        if (NS == 3) {
+          if (++cg == FLUSH_STAGES || c == nchunks - 1) {
+            mma_commit(&dfull[g & 1]);
+            ++g;
+            cg = 0;
+          }
+        }
       }
       if (NS == 1) mma_commit(&dfull[0]);
     }
   } else {
     // ===================================================================== operand stage + epilogue
     const int q = warp & 3;             // TMEM lane quarter this warp may touch
-    const int half = (warp - 2) >> 2;   // which 16 of the 32 K values of a stage
+    const int half = (warp - 2) >> 2;   // which 16 of the 32 K values of a slab
     const int row = q * 32 + lane;      // row of D / TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float piv = 0.f;
@@ -271,7 +335,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     float acc[NS == 3 ? 64 : 1];
 #pragma unroll
     for (int i = 0; i < (NS == 3 ? 64 : 1); ++i) acc[i] = 0.f;
-    const int nflush = (nchunks + TC_FLUSH - 1) / TC_FLUSH;
+    const int nflush = (nchunks + FLUSH_STAGES - 1) / FLUSH_STAGES;
     int next_flush = 0;
     // registers += accumulator buffer of flush group g (after the MMA warp committed it), then hand the buffer back
     auto flush = [&](int g) {
@@ -282,7 +346,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       for (int gi = 0; gi < 8; ++gi) {
         if (gi < groups) {
           float v[8];
-          tmem_ld8(tmem_base + lane_addr + buf * TC_D_COLS + half * (lp >> 1) + gi * 8, v);
+          tmem_ld8(tmem_base + lane_addr + buf * p.dcols + half * (lp >> 1) + gi * 8, v);
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[(NS == 3 ? gi * 8 + e : 0)] += v[e];
         }
@@ -292,47 +356,60 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       if (lane == 0) mbar_arrive(&dempty[buf]);
     };
 
-    for (int c = 0; c < nchunks; ++c) {
-      const int st = c % stages;
-      const uint32_t ph = (c / stages) & 1;
-      if (NS == 3 && next_flush < nflush && c >= (next_flush + 1) * TC_FLUSH + 1) flush(next_flush++);
-      mbar_wait(&full[st], ph);
+    const uint32_t xs_u32 = smem_u32(xs), pd_u32 = smem_u32(pd);
+    Pipe pp;
+    for (int c = 0; c < nchunks; ++c, pp.advance(stages)) {
+      const int st = pp.st;
+      if (NS == 3 && next_flush < nflush && c >= (next_flush + 1) * FLUSH_STAGES + 1) flush(next_flush++);
+      mbar_wait(&full[st], pp.ph);
       tc_fence_after();
-      uint32_t hi[16], lo[16];
-      if (!SIDE_T) {
-        // X stage = [32 t][128 s] fp32; this thread owns column `row`, rows half*16 .. +15
-        const float* src = (const float*)(xs + (size_t)st * TC_XBYTES) + (half * 16) * TC_TILE + row;
+      const uint32_t a_slot = tmem_base + lane_addr + a_col0 + st * ACOLS + half * 16;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          float v = src[r * TC_TILE] - piv;
-          v = (v == v) ? v : 0.f;
-          hi[r] = to_tf32(v);
-          if (NS == 3) lo[r] = __float_as_uint(v - __uint_as_float(hi[r]));
-        }
-      } else {
-        // X stage = [128 t][32 s] fp32, 16-byte chunks XOR-swizzled by (row & 7); this thread owns row `row`,
-        // chunks half*4 .. +3
-        const float* src = (const float*)(xs + (size_t)st * TC_XBYTES) + row * TC_KC;
-        const float* pv = (const float*)(pd + st * 256);
+      for (int kb = 0; kb < KB; ++kb) {
+        uint32_t hi[16], lo[16];
+        if (!SIDE_T) {
+          // X stage = [32 t][128 s] fp32; this thread owns column `row`, rows half*16 .. +15
+          const uint32_t src = xs_u32 + st * XB + ((half * 16) * TC_TILE + row) * 4;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int ch = half * 4 + cc;
-          const float4 x = *reinterpret_cast<const float4*>(src + ((ch ^ (row & 7)) << 2));
-          const float4 pq = *reinterpret_cast<const float4*>(pv + ch * 4);
-          const float4 dq = *reinterpret_cast<const float4*>(pv + 32 + ch * 4);
-          const float xa[4] = {x.x, x.y, x.z, x.w}, pa[4] = {pq.x, pq.y, pq.z, pq.w}, da[4] = {dq.x, dq.y, dq.z, dq.w};
+          for (int r = 0; r < 16; ++r) {
+            float v = lds32(src + r * TC_TILE * 4) - piv;
+            v = (v == v) ? v : 0.f;
+            if (NS == 3) {
+              hi[r] = __float_as_uint(v) & 0xffffe000u;
+              lo[r] = __float_as_uint(v - __uint_as_float(hi[r]));
+            } else {
+              hi[r] = __float_as_uint(v);  // the tensor core reads the upper 19 bits
+            }
+          }
+        } else {
+          // X stage = 128 rows (t) of KB*32 (+4 unused) fp32, XPITCH bytes apart; this thread owns row `row`, 16-byte
+          // chunks half*4 .. +3 of slab kb.  Anything that is not a finite number counts
+          // as 0 (NaN samples / features; beyond the last feature dscale is 0 and the small operand too)
+          const uint32_t src = xs_u32 + st * XB + row * XPITCH + kb * 128;
+          const uint32_t pv = pd_u32 + st * KB * 256 + kb * 256;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float v = xa[e] - pa[e];
-            v = (v == v) ? v * da[e] : 0.f;
-            hi[cc * 4 + e] = to_tf32(v);
-            if (NS == 3) lo[cc * 4 + e] = __float_as_uint(v - __uint_as_float(hi[cc * 4 + e]));
+          for (int cc = 0; cc < 4; ++cc) {
+            const int ch = half * 4 + cc;
+            const float4 x = lds128(src + ch * 16);
+            const float4 pq = lds128(pv + ch * 16);
+            const float4 dq = lds128(pv + 128 + ch * 16);
+            const float xa[4] = {x.x, x.y, x.z, x.w}, pa[4] = {pq.x, pq.y, pq.z, pq.w}, da[4] = {dq.x, dq.y, dq.z, dq.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float v = xa[e] - pa[e];
+              v = (fabsf(v) <= 3.4028234e38f) ? v * da[e] : 0.f;
+              if (NS == 3) {
+                hi[cc * 4 + e] = __float_as_uint(v) & 0xffffe000u;
+                lo[cc * 4 + e] = __float_as_uint(v - __uint_as_float(hi[cc * 4 + e]));
+              } else {
+                hi[cc * 4 + e] = __float_as_uint(v);
+              }
+            }
           }
         }
+        tmem_st16(a_slot + kb * TC_KC, hi);
+        if (NS == 3) tmem_st16(a_slot + kb * TC_KC + TC_KC * KB, lo);
       }
-      const uint32_t a_hi = tmem_base + lane_addr + a_col0 + st * a_cols_per_stage + half * 16;
-      tmem_st16(a_hi, hi);
-      if (NS == 3) tmem_st16(a_hi + TC_KC, lo);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -383,58 +460,63 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------ small helpers
-// W (T x ldw, time-side) -> Wt_hi / Wt_lo (lp x Tpad, K-major for the MMA: t contiguous), TF32-rounded value and
-// fp32 remainder; pad columns (t >= T) and pad rows (j >= l... already zero in W) are zero.  wsum[j] = sum_t W[t,j].
+// Offset (in floats) of element (row j, k) inside the image of one 32-wide K slab: [lp rows][32 k], 16-byte chunks
+// XOR-swizzled by (row & 7) — the K-major SWIZZLE_128B layout the UMMA descriptor names.
+__device__ __forceinline__ int img_offset(int j, int kk) { return j * 32 + ((((kk >> 2) ^ (j & 7)) << 2) | (kk & 3)); }
+
+// W (T x ldw, time-side) -> images of the K slabs of W^T (K = t): hi = value with the TF32 bits only, lo = fp32
+// remainder (3xTF32 only, else the value goes in unsplit).  Zero beyond T.
 __global__ void __launch_bounds__(256)
-prep_W_kernel(const float* __restrict__ W, int64_t T, int64_t ldw, int lp, int64_t Tpad, float* __restrict__ Whi,
-              float* __restrict__ Wlo) {
-  __shared__ float tile[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+prep_W_kernel(const float* __restrict__ W, int64_t T, int64_t ldw, int lp, float* __restrict__ Whi, float* __restrict__ Wlo) {
+  // one block per slab of 32 t: thread (j, 4 k's)
   const int64_t t0 = (int64_t)blockIdx.x * 32;
-  const int j0 = blockIdx.y * 32;
-  for (int r = ty; r < 32; r += 8) {
-    const int64_t t = t0 + r;
-    const int j = j0 + tx;
-    tile[r][tx] = (t < T && j < lp) ? W[t * ldw + j] : 0.f;
-  }
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int j = j0 + r;
-    const int64_t t = t0 + tx;
-    if (j < lp && t < Tpad) {
-      const float v = tile[tx][r];
-      const float h = __uint_as_float(to_tf32(v));
-      Whi[(int64_t)j * Tpad + t] = h;
-      if (Wlo) Wlo[(int64_t)j * Tpad + t] = v - h;
+  float* hi = Whi + (size_t)blockIdx.x * lp * 32;
+  float* lo = Wlo ? Wlo + (size_t)blockIdx.x * lp * 32 : nullptr;
+  for (int idx = threadIdx.x; idx < lp * 32; idx += 256) {
+    const int kk = idx / lp, j = idx % lp;  // consecutive threads walk a row of W
+    const int64_t t = t0 + kk;
+    const float v = t < T ? W[t * ldw + j] : 0.f;
+    if (lo) {
+      const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      hi[img_offset(j, kk)] = h;
+      lo[img_offset(j, kk)] = v - h;
+    } else {
+      hi[img_offset(j, kk)] = v;
     }
   }
 }
 
-// zero-padded copies of pivot / dscale (length Spad, multiple of 32) for the 128-byte bulk copies of project_T
+// pivot / dscale zero-padded to Spad and interleaved per 32-wide slab ([slab][pivot 32 | dscale 32]) so that one bulk
+// copy brings both for a stage of project_T
 __global__ void pad_vectors_kernel(const float* __restrict__ pivot, const float* __restrict__ dscale, int64_t S,
-                                   int64_t Spad, float* __restrict__ ppad, float* __restrict__ dpad) {
+                                   int64_t Spad, float* __restrict__ pdpad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Spad) {
-    ppad[i] = i < S ? pivot[i] : 0.f;
-    dpad[i] = i < S ? dscale[i] : 0.f;
+    const int64_t o = (i >> 5) * 64 + (i & 31);
+    pdpad[o] = i < S ? pivot[i] : 0.f;
+    pdpad[o + 32] = i < S ? dscale[i] : 0.f;
   }
 }
 
-// Yt (lp x ldy) -> TF32-rounded copy and fp32 remainder (lp x Spad), zero beyond S
-__global__ void split_Y_kernel(const float* __restrict__ Yt, int64_t S, int64_t ldy, int64_t Spad, float* __restrict__ Yhi,
-                               float* __restrict__ Ylo) {
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int64_t j = blockIdx.y;
-  if (i >= Spad) return;
-  float v[4], h[4], l[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    v[e] = (i + e < S) ? Yt[j * ldy + i + e] : 0.f;
-    h[e] = __uint_as_float(to_tf32(v[e]));
-    l[e] = v[e] - h[e];
+// Yt (lp x ldy, space-side) -> images of its K slabs (K = s), zero beyond S.  One block per slab.
+__global__ void __launch_bounds__(256)
+tile_Y_kernel(const float* __restrict__ Yt, int64_t S, int64_t ldy, int lp, float* __restrict__ Yhi, float* __restrict__ Ylo) {
+  const int64_t s0 = (int64_t)blockIdx.x * 32;
+  float* hi = Yhi + (size_t)blockIdx.x * lp * 32;
+  float* lo = Ylo ? Ylo + (size_t)blockIdx.x * lp * 32 : nullptr;
+  const int kk = threadIdx.x & 31;
+  const float scale = 1.f;
+  (void)scale;
+  for (int j = threadIdx.x >> 5; j < lp; j += 8) {
+    const float v = (s0 + kk < S) ? Yt[(int64_t)j * ldy + s0 + kk] : 0.f;
+    if (lo) {
+      const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      hi[img_offset(j, kk)] = h;
+      lo[img_offset(j, kk)] = v - h;
+    } else {
+      hi[img_offset(j, kk)] = v;
+    }
   }
-  *reinterpret_cast<float4*>(Yhi + j * Spad + i) = make_float4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<float4*>(Ylo + j * Spad + i) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
 // Z[t, j] = sum_split P[split][t][j] + r[j]   (r only on the valid samples)
@@ -473,27 +555,40 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp32 tensor map: inner (contiguous) extent `inner`, `outer` rows `ld` elements apart
-static int make_map(CUtensorMap* m, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
-                    int box_outer, bool swizzle128) {
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+// fp32 tensor map of rank 2 (inner, outer) or rank 3 (inner, mid, outer); strides in elements
+static int make_map(CUtensorMap* m, const float* base, int rank, const int64_t* dims, const int64_t* strides,
+                    const int* box, bool swizzle128) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
     return XEOFS_E_UNSUPPORTED;
   }
-  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t bx[3], estr[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gdim[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = (cuuint64_t)strides[i] * sizeof(float);
+  static const CUtensorMapL2promotion promo[4] = {CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
+                                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, gdim, gstr, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   promo[env_int("XEOFS_TC_PROMO", 3) & 3], CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) for extent %lld x %lld ld %lld box %d x %d", (int)r, (long long)inner,
-              (long long)outer, (long long)ld, box_inner, box_outer);
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d extent %lld x %lld box %d x %d", (int)r, rank, (long long)dims[0],
+              (long long)dims[1], box[0], box[1]);
     return XEOFS_E_CUDA;
   }
   return XEOFS_OK;
+}
+static int make_map2(CUtensorMap* m, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                     int box_outer, bool swizzle128) {
+  const int64_t dims[2] = {inner, outer}, str[1] = {ld};
+  const int box[2] = {box_inner, box_outer};
+  return make_map(m, base, 2, dims, str, box, swizzle128);
 }
 
 bool tc_supported(int64_t T, int64_t S, int64_t ldx, const float* X, int64_t l) {
@@ -502,67 +597,97 @@ bool tc_supported(int64_t T, int64_t S, int64_t ldx, const float* X, int64_t l) 
 }
 
 static inline int64_t align256(int64_t b) { return round_up(b, 256); }
+static inline bool is_x3(int algo) { return algo == XEOFS_ALGO_TF32X3 || algo == XEOFS_ALGO_AUTO; }
+
+// project_T: 32-wide K slabs per stage = bytes of a row fetched per bulk copy / 128.  The largest that leaves
+// at least two stages of shared memory and TMEM.
+struct Shape {
+  int stages, dcols, kb;
+  uint32_t tmem_cols;
+  size_t smem;
+};
+static Shape pick_shape(int lp, int ns, bool side_t, int kb) {
+  Shape sh;
+  const int npart = ns == 3 ? 2 : 1;
+  const bool two_ctas = !side_t && ns == 1;  // project_S x1: two CTAs per SM share the 512 TMEM columns
+  const int xb = side_t ? TC_TILE * (kb * 128 + 16) : TC_XBYTES;
+  const int per_stage = xb + lp * TC_KC * 4 * npart * kb + (side_t ? kb * 256 : 0);
+  sh.kb = kb;
+  sh.dcols = (int)round_up(lp, 32);
+  sh.tmem_cols = two_ctas ? 256 : 512;
+  const int ring = (int)sh.tmem_cols - (ns == 3 ? 2 : 1) * sh.dcols;
+  const int by_tmem = ring / (TC_KC * kb * npart);
+  const int budget = (two_ctas ? 110 : 222) * 1024 - 2048;
+  int st = budget / per_stage;
+  if (st > by_tmem) st = by_tmem;
+  if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
+  sh.stages = st;
+  sh.smem = (size_t)(st > 0 ? st : 1) * per_stage + 1024 /*alignment*/ + 256 /*barriers*/;
+  return sh;
+}
+static Shape pick_shape_T(int lp, int ns, int64_t S, int64_t ldx) {
+  int kb = env_int("XEOFS_TC_KB", 2);
+  if (kb != 1 && kb != 2 && kb != 4) kb = 2;
+  (void)S; (void)ldx;
+  Shape sh = pick_shape(lp, ns, true, kb);
+  while (sh.stages < 2 && kb > 1) {
+    kb >>= 1;
+    sh = pick_shape(lp, ns, true, kb);
+  }
+  return sh;
+}
 
 struct TGeom {
   int64_t t_tiles, rows_pad, Spad;
   int chunks_total, chunks_per_cta, splits;
 };
-static TGeom t_geometry(int64_t T, int64_t S, bool x3) {
+static TGeom t_geometry(int64_t T, int64_t S, bool x3, int kb) {
   TGeom g;
   g.t_tiles = ceil_div(T, TC_TILE);
   g.rows_pad = g.t_tiles * TC_TILE;
-  g.Spad = round_up(S, TC_KC);
-  g.chunks_total = (int)(g.Spad / TC_KC);
-  int64_t want = ceil_div(4 * (int64_t)num_sms(), g.t_tiles);
+  g.Spad = round_up(S, 128);  // covers every KB
+  g.chunks_total = (int)ceil_div(S, TC_KC * kb);
+  int64_t want = ceil_div(2 * (int64_t)num_sms(), g.t_tiles);
   if (want < 1) want = 1;
   if (want > g.chunks_total) want = g.chunks_total;
   g.chunks_per_cta = (int)ceil_div(g.chunks_total, want);
   // single-TF32 kernels keep one TMEM accumulator for the whole K range of a CTA: bound its truncation bias
-  if (!x3 && g.chunks_per_cta > 1024) g.chunks_per_cta = 1024;
+  if (!x3 && g.chunks_per_cta > 1024 / kb) g.chunks_per_cta = 1024 / kb;
   g.splits = (int)ceil_div(g.chunks_total, g.chunks_per_cta);
   return g;
 }
 
 int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo) {
   const int64_t lp = lpad(l);
-  const bool x3 = (algo == XEOFS_ALGO_TF32X3 || algo == XEOFS_ALGO_AUTO);
+  const bool x3 = is_x3(algo);
   const int64_t Tpad = round_up(T, TC_KC);
-  // project_S: wsum | Wt_hi | Wt_lo
+  // project_S: wsum | W image hi | W image lo
   const int64_t bs = align256(lp * 4) + (x3 ? 2 : 1) * align256(lp * Tpad * 4);
-  // project_T: rvec | pivot_pad | dscale_pad | partials | Yhi | Ylo
-  const TGeom g = t_geometry(T, S, false);  // the finer split needs the larger partial-sum buffer
-  int64_t bt = align256(lp * 4) + 2 * align256(g.Spad * 4) + align256((int64_t)g.splits * g.rows_pad * lp * 4);
-  if (x3) bt += 2 * align256(lp * g.Spad * 4);
+  // project_T: rvec | pivot_pad | dscale_pad | partials | Y image hi | Y image lo
+  // (the finest split has the largest partial buffer)
+  int64_t part = 0;
+  for (int kb = 1; kb <= 4; kb *= 2) {
+    const TGeom g = t_geometry(T, S, false, kb);
+    const int64_t b = (int64_t)g.splits * g.rows_pad * lp * 4;
+    if (b > part) part = b;
+  }
+  const int64_t Spad = round_up(S, 128);
+  const int64_t bt = align256(lp * 4) + 2 * align256(Spad * 4) + align256(part) + (x3 ? 2 : 1) * align256(lp * Spad * 4);
   return (bs > bt ? bs : bt) + 256;
 }
 
-static int pick_stages(int lp, int ns, bool side_t, size_t* smem_bytes) {
-  const int per_stage = TC_XBYTES + lp * TC_KC * 4 * (ns == 3 ? 2 : 1) + 256;
-  // x1: two CTAs per SM (TMEM 2 x 256 columns) -> about 110 KB each; x3: one CTA per SM
-  const int budget = ns == 1 ? 110 * 1024 : 200 * 1024;
-  const int max_by_tmem = 4;  // x1: (256 - 128) / 32;  x3: (512 - 2 * 128) / 64
-  int st = (budget - 2048) / per_stage;
-  if (st > max_by_tmem) st = max_by_tmem;
-  if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
-  if (st < 2) st = 2;
-  (void)side_t;
-  *smem_bytes = (size_t)st * per_stage + 1024 /*alignment*/ + 256 /*barriers*/;
-  return st;
-}
-
-template <int NS, bool SIDE_T>
+template <int NS, bool SIDE_T, int KB>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p, dim3 grid,
                      size_t smem, cudaStream_t stream) {
-  XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<NS, SIDE_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  project_tc_kernel<NS, SIDE_T><<<grid, TC_THREADS, smem, stream>>>(mx, mh, ml, p);
+  XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<NS, SIDE_T, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  project_tc_kernel<NS, SIDE_T, KB><<<grid, TC_THREADS, smem, stream>>>(mx, mh, ml, p);
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
 }
 
 int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot, const float* dscale,
                  const float* ccorr, const uint8_t* row_valid, const float* W, int64_t ldw, int64_t l, float* Yt,
-                 int64_t ldy, void* workspace,
-                 int64_t workspace_bytes, int algo, cudaStream_t stream) {
+                 int64_t ldy, void* workspace, int64_t workspace_bytes, int algo, cudaStream_t stream) {
   (void)workspace_bytes;
   const int lp = (int)lpad(l);
   const int ns = algo == XEOFS_ALGO_TF32X3 ? 3 : 1;
@@ -573,81 +698,83 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   float* Wlo = ns == 3 ? (float*)((uint8_t*)Whi + align256(lp * Tpad * 4)) : nullptr;
   int rc = launch_colsum(W, T, ldw, lp, row_valid, wsum, stream);
   if (rc) return rc;
-  prep_W_kernel<<<dim3((unsigned)(Tpad / 32), (unsigned)ceil_div(lp, 32)), 256, 0, stream>>>(W, T, ldw, lp, Tpad, Whi, Wlo);
+  prep_W_kernel<<<(unsigned)(Tpad / TC_KC), 256, 0, stream>>>(W, T, ldw, lp, Whi, Wlo);
   XB_LAUNCH_CHECK();
   CUtensorMap mx, mh, ml;
-  rc = make_map(&mx, X, S, T, ldx, TC_TILE, TC_KC, false);
+  rc = make_map2(&mx, X, S, T, ldx, TC_TILE, TC_KC, false);
   if (rc) return rc;
-  rc = make_map(&mh, Whi, Tpad, lp, Tpad, TC_KC, lp, true);
+  // the operand images as rows of 1 KB: a stage's image arrives as lp/8 long pieces
+  rc = make_map2(&mh, Whi, 256, (Tpad / TC_KC) * (lp / 8), 256, 256, lp / 8, false);
   if (rc) return rc;
   ml = mh;
   if (ns == 3) {
-    rc = make_map(&ml, Wlo, Tpad, lp, Tpad, TC_KC, lp, true);
+    rc = make_map2(&ml, Wlo, 256, (Tpad / TC_KC) * (lp / 8), 256, 256, lp / 8, false);
     if (rc) return rc;
   }
+  const Shape sh = pick_shape(lp, ns, false, 1);
   TcParams p{};
   p.T = T; p.S = S; p.lp = lp;
-  size_t smem;
-  p.stages = pick_stages(lp, ns, false, &smem);
+  p.stages = sh.stages; p.dcols = sh.dcols; p.tmem_cols = sh.tmem_cols;
   p.nchunks_total = (int)(Tpad / TC_KC);
   p.chunks_per_cta = p.nchunks_total;
   p.pivot = pivot; p.dscale = dscale; p.ccorr = ccorr; p.wsum = wsum;
   p.out = Yt; p.ldo = ldy;
-  p.tmem_cols = ns == 1 ? 256 : 512;
+  p.X = X; p.ldx = ldx; p.bimg_hi = Whi; p.bimg_lo = Wlo;
   dim3 grid((unsigned)ceil_div(S, TC_TILE));
-  return ns == 3 ? launch_tc<3, false>(mx, mh, ml, p, grid, smem, stream) : launch_tc<1, false>(mx, mh, ml, p, grid, smem, stream);
+  return ns == 3 ? launch_tc<3, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
+                 : launch_tc<1, false, 1>(mx, mh, ml, p, grid, sh.smem, stream);
 }
 
 int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot, const float* dscale,
                  const float* ccorr, const uint8_t* row_valid, const float* Yt, int64_t ldy, int64_t l, float* Z,
-                 int64_t ldz, void* workspace,
-                 int64_t workspace_bytes, int algo, cudaStream_t stream) {
+                 int64_t ldz, void* workspace, int64_t workspace_bytes, int algo, cudaStream_t stream) {
   (void)workspace_bytes;
   const int lp = (int)lpad(l);
-  int ns = algo == XEOFS_ALGO_TF32X3 ? 3 : 1;
-  const TGeom g = t_geometry(T, S, ns == 3);
+  const int ns = algo == XEOFS_ALGO_TF32X3 ? 3 : 1;
+  const Shape sh = pick_shape_T(lp, ns, S, ldx);
+  XB_CHECK_ARG(sh.stages >= 1, "project_T: no pipeline shape fits lp=%d", lp);
+  const int kb = sh.kb;
+  const TGeom g = t_geometry(T, S, ns == 3, kb);
   XB_CHECK_ARG(g.splits <= 65535, "project_T: too many splits");
   uint8_t* ws = (uint8_t*)workspace;
   float* rvec = (float*)ws; ws += align256(lp * 4);
-  float* ppad = (float*)ws; ws += align256(g.Spad * 4);
-  float* dpad = (float*)ws; ws += align256(g.Spad * 4);
+  float* pdpad = (float*)ws; ws += 2 * align256(g.Spad * 4);
   float* part = (float*)ws; ws += align256((int64_t)g.splits * g.rows_pad * lp * 4);
   float* Yhi = (float*)ws; ws += align256(lp * g.Spad * 4);
-  float* Ylo = (float*)ws;
-  pad_vectors_kernel<<<(unsigned)ceil_div(g.Spad, 256), 256, 0, stream>>>(pivot, dscale, S, g.Spad, ppad, dpad);
+  float* Ylo = ns == 3 ? (float*)ws : nullptr;
+  pad_vectors_kernel<<<(unsigned)ceil_div(g.Spad, 256), 256, 0, stream>>>(pivot, dscale, S, g.Spad, pdpad);
   XB_LAUNCH_CHECK();
-  // the small operand straight from the caller's buffer when it can be a TMA source and one product is enough
-  const bool direct = ns == 1 && ldy % 4 == 0 && ((uintptr_t)Yt % 16 == 0);
-  CUtensorMap mx, mh, ml;
-  int rc = make_map(&mx, X, S, T, ldx, TC_KC, TC_TILE, true);
-  if (rc) return rc;
-  if (direct) {
-    rc = make_map(&mh, Yt, S, lp, ldy, TC_KC, lp, true);
-    if (rc) return rc;
-    ml = mh;
-  } else {
-    split_Y_kernel<<<dim3((unsigned)ceil_div(g.Spad / 4, 256), (unsigned)lp), 256, 0, stream>>>(Yt, S, ldy, g.Spad, Yhi, Ylo);
-    XB_LAUNCH_CHECK();
-    rc = make_map(&mh, Yhi, g.Spad, lp, g.Spad, TC_KC, lp, true);
-    if (rc) return rc;
-    rc = make_map(&ml, Ylo, g.Spad, lp, g.Spad, TC_KC, lp, true);
-    if (rc) return rc;
-  }
+  tile_Y_kernel<<<(unsigned)(g.Spad / TC_KC), 256, 0, stream>>>(Yt, S, ldy, lp, Yhi, Ylo);
+  XB_LAUNCH_CHECK();
+  int rc;
   if (ccorr) {
     rc = launch_ccorr_dot(Yt, S, ldy, ccorr, lp, rvec, stream);
     if (rc) return rc;
   }
   TcParams p{};
   p.T = T; p.S = S; p.lp = lp;
-  size_t smem;
-  p.stages = pick_stages(lp, ns, true, &smem);
+  p.stages = sh.stages; p.dcols = sh.dcols; p.tmem_cols = sh.tmem_cols;
   p.nchunks_total = g.chunks_total;
   p.chunks_per_cta = g.chunks_per_cta;
-  p.pivot = ppad; p.dscale = dpad; p.ccorr = nullptr; p.wsum = nullptr;
+  p.pivot = pdpad; p.dscale = nullptr; p.ccorr = nullptr; p.wsum = nullptr;
   p.out = part; p.ldo = lp;
-  p.tmem_cols = ns == 1 ? 256 : 512;
+  p.X = X; p.ldx = ldx; p.bimg_hi = Yhi; p.bimg_lo = Ylo;
   dim3 grid((unsigned)g.t_tiles, (unsigned)g.splits);
-  rc = ns == 3 ? launch_tc<3, true>(mx, mh, ml, p, grid, smem, stream) : launch_tc<1, true>(mx, mh, ml, p, grid, smem, stream);
+  CUtensorMap mx, mh, ml;
+  // rows of X in pieces of KB*32 + 4 floats (the 4 extra only give the shared-memory rows their odd pitch)
+  rc = make_map2(&mx, X, S, T, ldx, kb * TC_KC + 4, TC_TILE, false);
+  if (rc) return rc;
+  rc = make_map2(&mh, Yhi, 256, (g.Spad / TC_KC) * (lp / 8), 256, 256, kb * lp / 8, false);
+  if (rc) return rc;
+  ml = mh;
+  if (ns == 3) {
+    rc = make_map2(&ml, Ylo, 256, (g.Spad / TC_KC) * (lp / 8), 256, 256, kb * lp / 8, false);
+    if (rc) return rc;
+  }
+#define XB_T_LAUNCH(NSV, KBV) launch_tc<NSV, true, KBV>(mx, mh, ml, p, grid, sh.smem, stream)
+  if (ns == 3) rc = kb == 1 ? XB_T_LAUNCH(3, 1) : kb == 2 ? XB_T_LAUNCH(3, 2) : XB_T_LAUNCH(3, 4);
+  else rc = kb == 1 ? XB_T_LAUNCH(1, 1) : kb == 2 ? XB_T_LAUNCH(1, 2) : XB_T_LAUNCH(1, 4);
+#undef XB_T_LAUNCH
   if (rc) return rc;
   reduce_partials_kernel<<<(unsigned)ceil_div(T * lp, 256), 256, 0, stream>>>(part, g.splits, g.rows_pad, lp, T,
                                                                               ccorr ? rvec : nullptr, row_valid, Z, ldz);
