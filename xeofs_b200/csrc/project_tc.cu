@@ -30,7 +30,10 @@
 
 namespace xb {
 
-constexpr int TC_THREADS = 320;
+// warps per TMEM lane quarter in the operand stage: the 3xTF32 kernels run one CTA per SM and need the extra warps to
+// hide the latencies of their longer conversion chain
+__host__ __device__ constexpr int tc_nw(int ns) { return ns == 3 ? 4 : 2; }
+__host__ __device__ constexpr int tc_threads(int ns) { return 64 + 128 * tc_nw(ns); }
 constexpr int TC_KC = 32;        // K elements per stage (= one 128-byte swizzle atom of fp32)
 constexpr int TC_TILE = 128;     // rows of D per CTA (TMEM lanes)
 constexpr int TC_XBYTES = TC_TILE * TC_KC * 4;  // 16 KB of X per stage
@@ -62,6 +65,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+// one lane of the (converged) warp: the compiler keeps what the elected lane computes in uniform registers, which the
+// TMA / tcgen05 instructions take, instead of moving per-thread values over one by one
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 %%rx;\n\t"
+      ".reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %1;\n\t"
+      "@%%px mov.s32 %0, 1;\n\t"
+      "}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -111,6 +129,27 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&v)[N]) {
+  static_assert(N == 8 || N == 16, "8 or 16 columns per store");
+  if constexpr (N == 16) tmem_st16(taddr, v);
+  else tmem_st8(taddr, v);
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
@@ -169,6 +208,8 @@ struct TcParams {
   const float* dscale;  // same
   const float* ccorr;   // project_S epilogue (may be null)
   const float* wsum;    // project_S epilogue: column sums of W [lp]
+  uint32_t exp_xor;     // timing experiments only (0 in production)
+  const uint8_t* chunk_flags;  // project_S: [K-chunk] 1 if the 32 samples hold one that is NaN throughout (null: none)
   float* out;           // project_S: Yt (ldo = ldy);  project_T: partial sums [split][tiles*128][lp]
   int64_t ldo;
   uint32_t tmem_cols;
@@ -190,11 +231,13 @@ struct Pipe {
 // NS: 1 = single TF32 product, 3 = 3xTF32.  SIDE_T: false = project_S, true = project_T.
 // KB: 32-wide K slabs per pipeline stage (project_T reads KB*128 contiguous bytes of every row per TMA box).
 template <int NS, bool SIDE_T, int KB>
-__global__ void __launch_bounds__(TC_THREADS, (NS == 1 && KB == 1) ? 2 : 1)
+__global__ void __launch_bounds__(tc_threads(NS), (NS == 1 && !SIDE_T) ? 2 : 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBhi,
                   const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
   static_assert(SIDE_T || KB == 1, "project_S stages are 32 rows of t");
   constexpr int NPART = NS == 3 ? 2 : 1;            // operand parts kept per value (hi | lo)
+  constexpr int NW = tc_nw(NS);                     // operand-stage warps per TMEM lane quarter
+  constexpr int KW = TC_KC / NW;                    // K values of a slab converted by one warp
   // project_T: a stage holds 128 rows of KB*32 (+4) floats, KB*128 + 16 bytes apart: TMA fetches them as 128 long
   // pieces (the engine's cost is per piece, about 7 cycles, whatever its length), one thread then reads one row, and
   // the odd multiple of 16 bytes spreads the rows of a quarter-warp over all banks without a swizzle
@@ -226,12 +269,12 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
-      mbar_init(&aready[i], 8);
+      mbar_init(&aready[i], 4 * NW);
     }
     mbar_init(&dfull[0], 1);
     mbar_init(&dfull[1], 1);
-    mbar_init(&dempty[0], 8);
-    mbar_init(&dempty[1], 8);
+    mbar_init(&dempty[0], 4 * NW);
+    mbar_init(&dempty[1], 4 * NW);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -243,38 +286,32 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (!SIDE_T) {
-      if (lane == 0) {
-        const uint32_t tx = XB + bbytes * NPART;
-        Pipe pp;
-        for (int c = 0; c < nchunks; ++c, pp.advance(stages)) {
-          const int st = pp.st;
-          mbar_wait(&empty[st], pp.ph ^ 1);
-          mbar_expect_tx(&full[st], tx);
-          tma_load_2d(xs + (size_t)st * XB, &mapX, (int)tile0, c * TC_KC, &full[st], HINT_EVICT_FIRST);
-          uint8_t* b = bs + (size_t)st * NPART * bbytes;
-          tma_load_2d(b, &mapBhi, 0, c * (lp >> 3), &full[st], HINT_EVICT_LAST);
-          if (NS == 3) tma_load_2d(b + bbytes, &mapBlo, 0, c * (lp >> 3), &full[st], HINT_EVICT_LAST);
-        }
-      }
-    } else if (lane == 0) {
-      const uint32_t tx = XB + bbytes * NPART * KB + KB * 256;
-      Pipe pp;
-      for (int c = 0; c < nchunks; ++c, pp.advance(stages)) {
-        const int st = pp.st;
-        const int k0 = (chunk0 + c) * TC_KC * KB;
-        mbar_wait(&empty[st], pp.ph ^ 1);
+    // the whole warp walks the ring; one elected lane issues
+    const uint32_t tx = XB + bbytes * NPART * KB + (SIDE_T ? KB * 256 : 0);
+    const int tile0i = (int)tile0;
+    Pipe pp;
+    for (int c = 0; c < nchunks; ++c, pp.advance(stages)) {
+      const int st = pp.st;
+      mbar_wait(&empty[st], pp.ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&full[st], tx);
-        tma_load_2d(xs + (size_t)st * XB, &mapX, k0, (int)tile0, &full[st], HINT_EVICT_FIRST);
-        bulk_load_1d(pd + st * KB * 256, p.pivot + 2 * k0, KB * 256, &full[st]);
         uint8_t* b = bs + (size_t)st * NPART * KB * bbytes;
-        tma_load_2d(b, &mapBhi, 0, (chunk0 + c) * KB * (lp >> 3), &full[st], HINT_EVICT_LAST);
-        if (NS == 3) tma_load_2d(b + (size_t)KB * bbytes, &mapBlo, 0, (chunk0 + c) * KB * (lp >> 3), &full[st], HINT_EVICT_LAST);
+        const int brow = (chunk0 + c) * KB * (lp >> 3);
+        if (!SIDE_T) {
+          tma_load_2d(xs + (size_t)st * XB, &mapX, tile0i, c * TC_KC, &full[st], HINT_EVICT_FIRST);
+        } else {
+          const int k0 = (chunk0 + c) * TC_KC * KB;
+          tma_load_2d(xs + (size_t)st * XB, &mapX, k0, tile0i, &full[st], HINT_EVICT_FIRST);
+          bulk_load_1d(pd + st * KB * 256, p.pivot + 2 * k0, KB * 256, &full[st]);
+        }
+        tma_load_2d(b, &mapBhi, 0, brow, &full[st], HINT_EVICT_LAST);
+        if (NS == 3) tma_load_2d(b + (size_t)KB * bbytes, &mapBlo, 0, brow, &full[st], HINT_EVICT_LAST);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc(lp);
       Pipe pp;
       int g = 0, cg = 0;  // flush group and stage within it (NS == 3)
@@ -285,56 +322,58 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         if (NS == 3) {
           const int buf = g & 1;
           first = cg == 0;
-          if (first) {
-            mbar_wait(&dempty[buf], (((uint32_t)g >> 1) & 1) ^ 1);  // registers hold what this buffer had
-            tc_fence_after();
-          }
+          if (first) mbar_wait(&dempty[buf], (((uint32_t)g >> 1) & 1) ^ 1);  // registers hold what this buffer had
           d_tmem = tmem_base + buf * p.dcols;
         }
         mbar_wait(&full[st], pp.ph);
         mbar_wait(&aready[st], pp.ph);
         tc_fence_after();
-        const uint32_t a_hi = tmem_base + a_col0 + st * ACOLS;
-        const uint32_t b0 = smem_u32(bs + (size_t)st * NPART * KB * bbytes);
+        const bool group_end = NS == 3 && (cg + 1 == FLUSH_STAGES || c == nchunks - 1);
+        if (elect_one()) {
+          const uint32_t a_hi = tmem_base + a_col0 + st * ACOLS;
+          const uint32_t b0 = smem_u32(bs + (size_t)st * NPART * KB * bbytes);
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-          const uint64_t dh = make_b_desc(b0 + kb * bbytes);
-          const uint64_t dl = NS == 3 ? make_b_desc(b0 + (KB + kb) * bbytes) : 0;
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint64_t dh = make_b_desc(b0 + kb * bbytes);
+            const uint64_t dl = NS == 3 ? make_b_desc(b0 + (KB + kb) * bbytes) : 0;
 #pragma unroll
-          for (int k = 0; k < TC_KC / 8; ++k) {
-            // +32 bytes (8 tf32) along K inside the swizzle atom = +2 in the (address >> 4) field
-            const uint32_t a = a_hi + kb * TC_KC + k * 8;
-            mma_tf32_ts(d_tmem, a, dh + 2 * k, idesc, !(first && kb == 0 && k == 0));
-            if (NS == 3) {
-              mma_tf32_ts(d_tmem, a, dl + 2 * k, idesc, 1);
-              mma_tf32_ts(d_tmem, a + TC_KC * KB, dh + 2 * k, idesc, 1);
+            for (int k = 0; k < TC_KC / 8; ++k) {
+              // +32 bytes (8 tf32) along K inside the swizzle atom = +2 in the (address >> 4) field
+              const uint32_t a = a_hi + kb * TC_KC + k * 8;
+              mma_tf32_ts(d_tmem, a, dh + 2 * k, idesc, !(first && kb == 0 && k == 0));
+              if (NS == 3) {
+                mma_tf32_ts(d_tmem ^ p.exp_xor, a, dl + 2 * k, idesc, 1);
+                mma_tf32_ts(d_tmem, a + TC_KC * KB, dh + 2 * k, idesc, 1);
+              }
             }
           }
+          mma_commit(&empty[st]);
+          if (group_end) mma_commit(&dfull[g & 1]);
+          if (NS == 1 && c == nchunks - 1) mma_commit(&dfull[0]);
         }
-        mma_commit(&empty[st]);
+        __syncwarp();
         if (NS == 3) {
-          if (++cg == FLUSH_STAGES || c == nchunks - 1) {
-            mma_commit(&dfull[g & 1]);
-            ++g;
-            cg = 0;
-          }
+          if (group_end) { ++g; cg = 0; } else { ++cg; }
         }
       }
-      if (NS == 1) mma_commit(&dfull[0]);
     }
   } else {
     // ===================================================================== operand stage + epilogue
+    // NW warps share each TMEM lane quarter: warp `part` of a quarter converts KW = 32/NW of the 32 K values of a
+    // slab and owns lp/NW columns of the accumulator
     const int q = warp & 3;             // TMEM lane quarter this warp may touch
-    const int half = (warp - 2) >> 2;   // which 16 of the 32 K values of a slab
+    const int part = (warp - 2) >> 2;
     const int row = q * 32 + lane;      // row of D / TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float piv = 0.f;
     if (!SIDE_T) piv = (tile0 + row < p.S) ? p.pivot[tile0 + row] : 0.f;
 
-    const int groups = lp >> 4;  // groups of 8 accumulator columns owned by this warp (its half of lp)
-    float acc[NS == 3 ? 64 : 1];
+    constexpr int ACCN = NS == 3 ? 128 / NW : 1;
+    const int cw = lp / NW;      // accumulator columns of this warp: [part*cw, +cw)
+    const int groups = cw >> 2;  // in groups of 4
+    float acc[ACCN];
 #pragma unroll
-    for (int i = 0; i < (NS == 3 ? 64 : 1); ++i) acc[i] = 0.f;
+    for (int i = 0; i < ACCN; ++i) acc[i] = 0.f;
     const int nflush = (nchunks + FLUSH_STAGES - 1) / FLUSH_STAGES;
     int next_flush = 0;
     // registers += accumulator buffer of flush group g (after the MMA warp committed it), then hand the buffer back
@@ -343,12 +382,12 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       mbar_wait(&dfull[buf], ((uint32_t)g >> 1) & 1);
       tc_fence_after();
 #pragma unroll
-      for (int gi = 0; gi < 8; ++gi) {
+      for (int gi = 0; gi < ACCN / 4; ++gi) {
         if (gi < groups) {
-          float v[8];
-          tmem_ld8(tmem_base + lane_addr + buf * p.dcols + half * (lp >> 1) + gi * 8, v);
+          float v[4];
+          tmem_ld4(tmem_base + lane_addr + buf * p.dcols + part * cw + gi * 4, v);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[(NS == 3 ? gi * 8 + e : 0)] += v[e];
+          for (int e = 0; e < 4; ++e) acc[(NS == 3 ? gi * 4 + e : 0)] += v[e];
         }
       }
       tc_fence_before();
@@ -361,35 +400,43 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     for (int c = 0; c < nchunks; ++c, pp.advance(stages)) {
       const int st = pp.st;
       if (NS == 3 && next_flush < nflush && c >= (next_flush + 1) * FLUSH_STAGES + 1) flush(next_flush++);
+      // project_S: a NaN only spoils the row of D of its own feature (dropped in the epilogue if the feature is
+      // invalid), except in samples that are NaN throughout: only stages holding such a sample test every value
+      const bool check = SIDE_T || (p.chunk_flags != nullptr && p.chunk_flags[c] != 0);
       mbar_wait(&full[st], pp.ph);
       tc_fence_after();
-      const uint32_t a_slot = tmem_base + lane_addr + a_col0 + st * ACOLS + half * 16;
+      const uint32_t a_slot = tmem_base + lane_addr + a_col0 + st * ACOLS + part * KW;
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
-        uint32_t hi[16], lo[16];
+        uint32_t hi[KW], lo[KW];
         if (!SIDE_T) {
-          // X stage = [32 t][128 s] fp32; this thread owns column `row`, rows half*16 .. +15
-          const uint32_t src = xs_u32 + st * XB + ((half * 16) * TC_TILE + row) * 4;
+          // X stage = [32 t][128 s] fp32; this thread owns column `row`, rows part*KW .. +KW-1
+          const uint32_t src = xs_u32 + st * XB + ((part * KW) * TC_TILE + row) * 4;
+          float v[KW];
 #pragma unroll
-          for (int r = 0; r < 16; ++r) {
-            float v = lds32(src + r * TC_TILE * 4) - piv;
-            v = (v == v) ? v : 0.f;
+          for (int r = 0; r < KW; ++r) v[r] = lds32(src + r * TC_TILE * 4) - piv;
+          if (check) {
+#pragma unroll
+            for (int r = 0; r < KW; ++r) v[r] = (v[r] == v[r]) ? v[r] : 0.f;
+          }
+#pragma unroll
+          for (int r = 0; r < KW; ++r) {
             if (NS == 3) {
-              hi[r] = __float_as_uint(v) & 0xffffe000u;
-              lo[r] = __float_as_uint(v - __uint_as_float(hi[r]));
+              hi[r] = __float_as_uint(v[r]) & 0xffffe000u;
+              lo[r] = __float_as_uint(v[r] - __uint_as_float(hi[r]));
             } else {
-              hi[r] = __float_as_uint(v);  // the tensor core reads the upper 19 bits
+              hi[r] = __float_as_uint(v[r]);  // the tensor core reads the upper 19 bits
             }
           }
         } else {
           // X stage = 128 rows (t) of KB*32 (+4 unused) fp32, XPITCH bytes apart; this thread owns row `row`, 16-byte
-          // chunks half*4 .. +3 of slab kb.  Anything that is not a finite number counts
-          // as 0 (NaN samples / features; beyond the last feature dscale is 0 and the small operand too)
+          // chunks part*KW/4 .. of slab kb.  Anything that is not a finite number counts as 0 (NaN samples /
+          // features; beyond the last feature dscale is 0 and the small operand too)
           const uint32_t src = xs_u32 + st * XB + row * XPITCH + kb * 128;
           const uint32_t pv = pd_u32 + st * KB * 256 + kb * 256;
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const int ch = half * 4 + cc;
+          for (int cc = 0; cc < KW / 4; ++cc) {
+            const int ch = part * (KW / 4) + cc;
             const float4 x = lds128(src + ch * 16);
             const float4 pq = lds128(pv + ch * 16);
             const float4 dq = lds128(pv + 128 + ch * 16);
@@ -407,8 +454,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             }
           }
         }
-        tmem_st16(a_slot + kb * TC_KC, hi);
-        if (NS == 3) tmem_st16(a_slot + kb * TC_KC + TC_KC * KB, lo);
+        tmem_st<KW>(a_slot + kb * TC_KC, hi);
+        if (NS == 3) tmem_st<KW>(a_slot + kb * TC_KC + TC_KC * KB, lo);
       }
       tmem_wait_st();
       tc_fence_before();
@@ -432,24 +479,25 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
     float* dstT = SIDE_T ? p.out + ((int64_t)blockIdx.y * gridDim.x * TC_TILE + rrow) * lp : nullptr;
 #pragma unroll
-    for (int gi = 0; gi < 8; ++gi) {
+    for (int gi = 0; gi < 128 / NW / 4; ++gi) {
       if (gi < groups) {
-        const int j0 = half * (lp >> 1) + gi * 8;
-        float v[8];
+        const int j0 = part * cw + gi * 4;
+        float v[4];
         if (NS == 3) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = acc[(NS == 3 ? gi * 8 + e : 0)];
+          for (int e = 0; e < 4; ++e) v[e] = acc[(NS == 3 ? gi * 4 + e : 0)];
         } else {
-          tmem_ld8(tmem_base + lane_addr + j0, v);
+          tmem_ld4(tmem_base + lane_addr + j0, v);
         }
         if (!SIDE_T) {
           if (ok) {
+            // an invalid feature (dscale 0) gives a zero row even if its accumulator holds NaN
 #pragma unroll
-            for (int e = 0; e < 8; ++e) p.out[(int64_t)(j0 + e) * p.ldo + rrow] = fmaf(ds, v[e], cs * p.wsum[j0 + e]);
+            for (int e = 0; e < 4; ++e)
+              p.out[(int64_t)(j0 + e) * p.ldo + rrow] = ds != 0.f ? fmaf(ds, v[e], cs * p.wsum[j0 + e]) : 0.f;
           }
         } else {
           *reinterpret_cast<float4*>(dstT + j0) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(dstT + j0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
       }
     }
@@ -496,6 +544,18 @@ __global__ void pad_vectors_kernel(const float* __restrict__ pivot, const float*
     pdpad[o] = i < S ? pivot[i] : 0.f;
     pdpad[o + 32] = i < S ? dscale[i] : 0.f;
   }
+}
+
+// flags[c] = 1 if one of the 32 samples of K-chunk c is NaN throughout (row_valid == 0)
+__global__ void chunk_flags_kernel(const uint8_t* __restrict__ row_valid, int64_t T, int nchunks, uint8_t* __restrict__ flags) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  uint8_t f = 0;
+  for (int r = 0; r < 32; ++r) {
+    const int64_t t = (int64_t)c * 32 + r;
+    if (t < T && !row_valid[t]) f = 1;
+  }
+  flags[c] = f;
 }
 
 // Yt (lp x ldy, space-side) -> images of its K slabs (K = s), zero beyond S.  One block per slab.
@@ -661,8 +721,8 @@ int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo) {
   const int64_t lp = lpad(l);
   const bool x3 = is_x3(algo);
   const int64_t Tpad = round_up(T, TC_KC);
-  // project_S: wsum | W image hi | W image lo
-  const int64_t bs = align256(lp * 4) + (x3 ? 2 : 1) * align256(lp * Tpad * 4);
+  // project_S: wsum | chunk flags | W image hi | W image lo
+  const int64_t bs = align256(lp * 4) + align256(Tpad / TC_KC) + (x3 ? 2 : 1) * align256(lp * Tpad * 4);
   // project_T: rvec | pivot_pad | dscale_pad | partials | Y image hi | Y image lo
   // (the finest split has the largest partial buffer)
   int64_t part = 0;
@@ -680,7 +740,7 @@ template <int NS, bool SIDE_T, int KB>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p, dim3 grid,
                      size_t smem, cudaStream_t stream) {
   XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<NS, SIDE_T, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  project_tc_kernel<NS, SIDE_T, KB><<<grid, TC_THREADS, smem, stream>>>(mx, mh, ml, p);
+  project_tc_kernel<NS, SIDE_T, KB><<<grid, tc_threads(NS), smem, stream>>>(mx, mh, ml, p);
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
 }
@@ -694,10 +754,15 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   const int64_t Tpad = round_up(T, TC_KC);
   uint8_t* ws = (uint8_t*)workspace;
   float* wsum = (float*)ws;
-  float* Whi = (float*)(ws + align256(lp * 4));
+  uint8_t* flags = ws + align256(lp * 4);
+  float* Whi = (float*)(flags + align256(Tpad / TC_KC));
   float* Wlo = ns == 3 ? (float*)((uint8_t*)Whi + align256(lp * Tpad * 4)) : nullptr;
   int rc = launch_colsum(W, T, ldw, lp, row_valid, wsum, stream);
   if (rc) return rc;
+  if (row_valid) {
+    chunk_flags_kernel<<<(unsigned)ceil_div(Tpad / TC_KC, 128), 128, 0, stream>>>(row_valid, T, (int)(Tpad / TC_KC), flags);
+    XB_LAUNCH_CHECK();
+  }
   prep_W_kernel<<<(unsigned)(Tpad / TC_KC), 256, 0, stream>>>(W, T, ldw, lp, Whi, Wlo);
   XB_LAUNCH_CHECK();
   CUtensorMap mx, mh, ml;
@@ -720,6 +785,8 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   p.pivot = pivot; p.dscale = dscale; p.ccorr = ccorr; p.wsum = wsum;
   p.out = Yt; p.ldo = ldy;
   p.X = X; p.ldx = ldx; p.bimg_hi = Whi; p.bimg_lo = Wlo;
+  p.chunk_flags = row_valid ? flags : nullptr;
+  p.exp_xor = env_int("XEOFS_TC_EXP", 0) == 2 ? 64 : 0;
   dim3 grid((unsigned)ceil_div(S, TC_TILE));
   return ns == 3 ? launch_tc<3, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
                  : launch_tc<1, false, 1>(mx, mh, ml, p, grid, sh.smem, stream);
