@@ -148,6 +148,13 @@ int xeofs_b200_reconstruct(const float* scores, int64_t T, int64_t lds, const fl
                            const int32_t* modes, int64_t m, const float* pivot, const float* dscale,
                            const float* ccorr, const uint8_t* valid, float* out, int64_t ldo, void* stream);
 
+/* ---- M3: a block of preprocessed samples as a space-side matrix (cross/cpcca.py:991-1000) ------------------------
+ * out[j, s] = A[t0 + j, s] for j < nrows, zero for nrows <= j < rows_out.  With project_T this yields 128 columns of
+ * the T x T Gram matrices X X^T and Y Y^T at a time, from which sum |C|^2 = <X X^T, Y Y^T>_F / (n-1)^2.            */
+int xeofs_b200_scaled_rows(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
+                           const float* dscale, const float* ccorr, const uint8_t* row_valid, int64_t t0,
+                           int64_t nrows, int64_t rows_out, float* out, int64_t ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,124 @@
+"""GPU parity through the C-ABI for the other two classes on the path: xeofs_b200.cross.MCA (implicit cross-covariance
+operator) and xeofs_b200.single.EOFRotator (varimax / promax, rows R1-R2), against the oracle on
+identical seeded inputs; plus size-independent a-posteriori properties of EOF.fit at sizes the oracle cannot reach."""
+import numpy as np
+import pytest
+import torch
+
+from _inputs import planted
+from oracle import eof as oeof
+from oracle import mca as omca
+from oracle import rotation as orot
+
+pytestmark = pytest.mark.gpu
+DIMS = ("time", "lat", "lon")
+
+
+def _coupled_fields(T, S1, S2, r, seed):
+    rng = np.random.default_rng(seed)
+    U = np.linalg.qr(rng.standard_normal((T, r)))[0]
+    sig = 500 * 0.75 ** np.arange(r)
+    X = 280 + (U * sig) @ np.linalg.qr(rng.standard_normal((S1, r)))[0].T + 0.05 * rng.standard_normal((T, S1))
+    Y = 1000 + (U * sig) @ np.linalg.qr(rng.standard_normal((S2, r)))[0].T + 0.05 * rng.standard_normal((T, S2))
+    return X.astype(np.float32), Y.astype(np.float32)
+
+
+@pytest.mark.parametrize("shape", [(300, 40 * 30, 20 * 36, 6), (400, 10 * 12, 60 * 50, 8)])
+@pytest.mark.parametrize("kw", [dict(), dict(standardize=True, use_coslat=True)])
+def test_mca_matches_explicit_cross_covariance_oracle(shape, kw):
+    """C = X^T Y/(n-1) is formed explicitly by the oracle (cross/cpcca.py:1008-1015) and applied implicitly on the
+    device; singular values rtol 1e-4, components up to the reference's sign rule, total squared covariance."""
+    import xeofs_b200 as xb
+    T, S1, S2, k = shape
+    X, Y = _coupled_fields(T, S1, S2, 2 * k, seed=S1)
+    n1 = 40 if S1 == 1200 else 10
+    n2 = 20 if S2 == 720 else 60
+    X = X.reshape(T, n1, S1 // n1)
+    Y = Y.reshape(T, n2, S2 // n2)
+    X[:, 3, 5] = np.nan
+    Y[:, 7, 1] = np.nan
+    cx = {"lat": np.linspace(80, -80, n1), "lon": np.arange(S1 // n1) * 1.0}
+    cy = {"lat": np.linspace(60, -60, n2), "lon": np.arange(S2 // n2) * 1.0}
+    o = omca.mca_fit(X, Y, DIMS, DIMS, "time", coords_x=cx, coords_y=cy, n_modes=k, random_state=3, **kw)
+    m = xb.cross.MCA(n_modes=k, random_state=3, **kw)
+    m.fit(xb.DataArray(X, DIMS, cx), xb.DataArray(Y, DIMS, cy), dim="time")
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    np.testing.assert_allclose(m.total_squared_covariance(), o["total_squared_covariance"], rtol=1e-4)
+    c1, c2 = m.components()
+    for c, oc, f in ((c1, o["components1_2d"], o["fitted1"]), (c2, o["components2_2d"], o["fitted2"])):
+        V = c.values.reshape(-1, k)
+        np.testing.assert_array_equal(np.isnan(V).any(axis=1), ~f["is_valid_feature"])
+        dots = (V[f["is_valid_feature"]] * oc).sum(axis=0)
+        assert (dots >= 1 - 1e-4).all(), dots
+    s1, s2 = m.scores()
+    for sc, osc in ((s1, o["scores1"]), (s2, o["scores2"])):
+        scale = np.abs(osc).max(axis=0)
+        np.testing.assert_allclose(sc.values / scale, osc / scale, atol=2e-3)
+
+
+@pytest.mark.parametrize("power", [1, 2])
+@pytest.mark.parametrize("m_rot", [2, 10])
+def test_rotator_matches_oracle(power, m_rot):
+    """Varimax (power=1) / promax rotation of the leading modes: one streaming pass per iteration on the device vs
+    linalg/_numpy/_rotation.py restated in the oracle (pinned by golden vectors from the reference's own source)."""
+    import xeofs_b200 as xb
+    T, nlat, nlon, k = 500, 30, 60, 12
+    X = planted(T, nlat * nlon, 2 * k, seed=21).reshape(T, nlat, nlon)
+    X[:, 4, 4] = np.nan
+    coords = {"lat": np.linspace(85, -85, nlat), "lon": np.arange(nlon) * 6.0}
+    kw = dict(n_modes=k, use_coslat=True, random_state=2, solver_kwargs={"n_iter": 4})
+    o = oeof.eof_fit(X, DIMS, "time", coords=coords, **kw)
+    model = xb.single.EOF(**kw).fit(xb.DataArray(X, DIMS, coords), dim="time")
+    r = xb.single.EOFRotator(n_modes=m_rot, power=power).fit(model)
+    ro = orot.eof_rotator_fit(o["components_2d"], o["explained_variance"], o["scores"], o["norms"], o["A"].shape[0],
+                              n_modes=m_rot, power=power)
+    np.testing.assert_allclose(r.explained_variance().values, ro["explained_variance"], rtol=1e-4)
+    np.testing.assert_allclose(r.singular_values().values, ro["norms"], rtol=1e-4)
+    V = r.components().values.reshape(-1, m_rot)[o["fitted"]["is_valid_feature"]]
+    dots = (V * ro["components_2d"]).sum(axis=0)
+    assert (dots >= 1 - 1e-4).all(), dots
+    sc = r.scores().values.reshape(-1, m_rot)
+    scale = np.abs(ro["scores"]).max(axis=0)
+    np.testing.assert_allclose(sc / scale, ro["scores"] / scale, atol=2e-3)
+    if power == 1:  # tests/models/single/test_eof_rotator.py:98-137
+        np.testing.assert_allclose(r.explained_variance().values.sum(), model.explained_variance().values[:m_rot].sum(),
+                                   rtol=1e-5)
+    assert r.n_iter_ < 1000
+
+
+def test_rotator_not_converged_raises():
+    import xeofs_b200 as xb
+    X = planted(200, 600, 12, seed=5).reshape(200, 20, 30)
+    model = xb.single.EOF(n_modes=6, random_state=1).fit(xb.DataArray(X, DIMS), dim="time")
+    with pytest.raises(RuntimeError, match="did not converge"):
+        xb.single.EOFRotator(n_modes=6, max_iter=1, rtol=1e-14).fit(model)
+
+
+def test_eof_large_a_posteriori_properties():
+    """At a size the fp64 oracle takes minutes for (8760 x 65 536, 2.3 GB): (s_i, v_i) are singular pairs of the
+    preprocessed matrix — ||A v_i|| = s_i through the fp32 SIMT kernels (a different code path from the tcgen05 one
+    the fit used), V orthonormal, scores = A V, explained variance below total variance."""
+    import xeofs_b200 as xb
+    from xeofs_b200 import _lib
+    T, nlat, nlon, k = 8760, 64, 1024, 20
+    g = torch.Generator(device="cuda").manual_seed(3)
+    U = torch.linalg.qr(torch.randn((T, 2 * k), generator=g, device="cuda"))[0]
+    V = torch.linalg.qr(torch.randn((nlat * nlon, 2 * k), generator=g, device="cuda"))[0]
+    sig = 1e5 * 0.85 ** torch.arange(2 * k, device="cuda")
+    X = 280 + (U * sig) @ V.t() + 0.05 * torch.randn((T, nlat * nlon), generator=g, device="cuda")
+    coords = {"lat": np.linspace(89, -89, nlat), "lon": np.arange(nlon) * (360.0 / nlon)}
+    m = xb.single.EOF(n_modes=k, use_coslat=True, random_state=5, solver_kwargs={"n_iter": 4})
+    m.fit(xb.DataArray(X.reshape(T, nlat, nlon), DIMS, coords), dim="time")
+    s = m.data["norms"]
+    ops, f = m.ops, m.preprocessor.fitted.field
+    Z = ops.project_T(f, m._Vt, k, algo=_lib.ALGO_SIMT)[:, :k].double()
+    np.testing.assert_allclose(Z.norm(dim=0).cpu().numpy(), s.cpu().numpy(), rtol=1e-4)
+    G = ops.gram(m._Vt, f.S, k, 1).cpu().numpy()
+    np.testing.assert_allclose(G, np.eye(k), atol=1e-4)
+    sc = m._scores[:, :k].double()
+    scale = sc.abs().max(dim=0).values
+    assert float(((Z - sc) / scale).abs().max()) < 2e-3
+    evr = m.explained_variance_ratio().values
+    assert evr.sum() <= 1.0 + 1e-6 and (np.diff(evr) <= 1e-9).all()
+    # the planted spectrum, seen through the coslat weights, bounds the leading value
+    assert 0.3 * 1e5 < float(s[0]) < 1.01 * 1e5

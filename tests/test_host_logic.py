@@ -1,0 +1,220 @@
+"""CPU: the host side of the drop-in (preprocessor, range-finder driver, EOF / MCA / EOFRotator classes) driven through
+a torch-CPU test double of the kernel interface (tests/cpu_ops.py) against the oracle, the C-ABI library's symbol
+table, and the feature-sharded path over torch.distributed (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from _inputs import MOCK_LAT, MOCK_LON, mock_data_array, planted
+from cpu_ops import TorchCpuOps
+from oracle import eof as oeof
+from oracle import mca as omca
+from oracle import rotation as orot
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DIMS = ("time", "lat", "lon")
+
+
+# ---------------------------------------------------------------- the C-ABI library
+def test_library_exports_every_declared_symbol():
+    """include/xeofs_b200.h is the contract: every function it declares is exported by the built library and
+    bound (with a signature) by xeofs_b200/_lib.py.  No compute call is made (no GPU here)."""
+    from xeofs_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "xeofs_b200.h")).read()
+    declared = set(re.findall(r"\b(xeofs_b200_\w+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().xeofs_b200_version() >= 100
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+    from xeofs_b200._cuda_ops import CudaOps
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        CudaOps()
+
+
+def test_product_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "xeofs_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+
+
+# ---------------------------------------------------------------- EOF host logic vs oracle
+def _compare_eof(o, m, k, tol=1e-6):
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-5)
+    np.testing.assert_allclose(m.explained_variance_ratio().values, o["explained_variance_ratio"], rtol=1e-5)
+    comps = m.components().values
+    np.testing.assert_array_equal(np.isnan(comps), np.isnan(o["components"]))
+    vf = o["fitted"]["is_valid_feature"]
+    dots = (comps.reshape(-1, k)[vf] * o["components_2d"]).sum(axis=0)
+    assert (dots > 1 - 1e-5).all(), dots
+    sc = m.scores().values.reshape(-1, k)
+    vs = o["fitted"]["is_valid_sample"]
+    scale = np.abs(o["scores"]).max(axis=0)
+    np.testing.assert_allclose(sc[vs] / scale, o["scores"] / scale, atol=2e-4)
+    assert np.isnan(sc[~vs]).all()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(standardize=True, use_coslat=True), dict(center=False)])
+def test_eof_host_logic_wide_with_nans(kw):
+    import xeofs_b200 as xb
+    T, nlat, nlon, k = 120, 12, 30, 6
+    X = planted(T, nlat * nlon, 2 * k, seed=1).reshape(T, nlat, nlon)
+    X[:, np.random.default_rng(9).random((nlat, nlon)) < 0.1] = np.nan
+    X[17] = np.nan
+    coords = {"lat": np.linspace(80, -80, nlat), "lon": np.arange(nlon) * 12.0}
+    o = oeof.eof_fit(X, DIMS, "time", coords=coords, n_modes=k, random_state=5, solver_kwargs={"n_iter": 4}, **kw)
+    m = xb.single.EOF(n_modes=k, random_state=5, solver_kwargs={"n_iter": 4}, ops=TorchCpuOps(), **kw)
+    m.fit(xb.DataArray(X, DIMS, coords), dim="time")
+    _compare_eof(o, m, k)
+
+
+def test_eof_host_logic_tall_and_exact_policy():
+    import xeofs_b200 as xb
+    X = mock_data_array().astype(np.float32)
+    coords = {"lat": MOCK_LAT, "lon": MOCK_LON}
+    for k in (3, 18):  # 18 > 0.8 * rank: exact policy (decomposer.py:112-131)
+        o = oeof.eof_fit(X, DIMS, "time", coords=coords, n_modes=k, random_state=5)
+        m = xb.single.EOF(n_modes=k, random_state=5, ops=TorchCpuOps()).fit(xb.DataArray(X, DIMS, coords), dim="time")
+        np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+
+
+def test_error_conventions():
+    import xeofs_b200 as xb
+    X = mock_data_array().astype(np.float32)
+    da = xb.DataArray(X, DIMS, {"lat": MOCK_LAT, "lon": MOCK_LON})
+    with pytest.raises(ValueError, match="rank"):
+        xb.single.EOF(n_modes=21, ops=TorchCpuOps()).fit(da, dim="time")
+    with pytest.raises(TypeError):
+        xb.single.EOF(n_modes=2, ops=TorchCpuOps()).fit(X, dim="time")
+    Xn = X.copy()
+    Xn[3, 2, 1] = np.nan
+    with pytest.raises(ValueError, match="partial NaN"):
+        xb.single.EOF(n_modes=2, ops=TorchCpuOps()).fit(xb.DataArray(Xn, DIMS), dim="time")
+    with pytest.raises(ValueError, match="latitude"):
+        xb.single.EOF(n_modes=2, use_coslat=True, ops=TorchCpuOps()).fit(xb.DataArray(X, ("time", "y", "x")), dim="time")
+    with pytest.raises(NotImplementedError):
+        xb.cross.MCA(n_modes=2, use_pca=True, ops=TorchCpuOps())
+
+
+def test_transform_inverse_transform_host_logic():
+    import xeofs_b200 as xb
+    X = mock_data_array().astype(np.float32)
+    da = xb.DataArray(X, DIMS, {"lat": MOCK_LAT, "lon": MOCK_LON})
+    m = xb.single.EOF(n_modes=20, standardize=True, use_coslat=True, solver="full", ops=TorchCpuOps()).fit(da, dim="time")
+    np.testing.assert_allclose(m.transform(da).values, m.scores().values, rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(m.inverse_transform(m.scores()).values, X, rtol=1e-4, atol=2e-5)
+
+
+# ---------------------------------------------------------------- MCA / rotator host logic vs oracle
+def test_mca_host_logic():
+    import xeofs_b200 as xb
+    T, k = 150, 5
+    rng = np.random.default_rng(0)
+    U = np.linalg.qr(rng.standard_normal((T, 2 * k)))[0]
+    sig = 100 * 0.7 ** np.arange(2 * k)
+    X = ((U * sig) @ np.linalg.qr(rng.standard_normal((80, 2 * k)))[0].T + 0.01 * rng.standard_normal((T, 80))).astype(np.float32)
+    Y = ((U * sig) @ np.linalg.qr(rng.standard_normal((60, 2 * k)))[0].T + 0.01 * rng.standard_normal((T, 60))).astype(np.float32)
+    X[:, 5] = np.nan
+    o = omca.mca_fit(X, Y, ("time", "x"), ("time", "y"), "time", n_modes=k, random_state=3)
+    m = xb.cross.MCA(n_modes=k, random_state=3, ops=TorchCpuOps())
+    m.fit(xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-5)
+    np.testing.assert_allclose(m.total_squared_covariance(), o["total_squared_covariance"], rtol=1e-5)
+    c1, c2 = m.components()
+    v1 = c1.values[~np.isnan(c1.values).any(axis=1)]
+    dots = np.abs((v1 * o["components1_2d"]).sum(axis=0))
+    assert (dots > 1 - 1e-5).all(), dots
+    assert ((c2.values * o["components2_2d"]).sum(axis=0) > 1 - 1e-5).all()
+
+
+def test_rotator_host_logic():
+    import xeofs_b200 as xb
+    X = planted(200, 300, 12, seed=4).reshape(200, 10, 30)
+    coords = {"lat": np.linspace(60, -60, 10), "lon": np.arange(30) * 12.0}
+    ops = TorchCpuOps()
+    m = xb.single.EOF(n_modes=8, random_state=1, ops=ops).fit(xb.DataArray(X, DIMS, coords), dim="time")
+    o = oeof.eof_fit(X, DIMS, "time", coords=coords, n_modes=8, random_state=1)
+    for power in (1, 2):
+        r = xb.single.EOFRotator(n_modes=5, power=power).fit(m)
+        ro = orot.eof_rotator_fit(o["components_2d"], o["explained_variance"], o["scores"], o["norms"],
+                                  o["A"].shape[0], n_modes=5, power=power)
+        np.testing.assert_allclose(r.explained_variance().values, ro["explained_variance"], rtol=1e-5)
+        V = r.components().values.reshape(-1, 5)
+        dots = (V * ro["components_2d"]).sum(axis=0)
+        assert (dots > 1 - 1e-5).all(), dots
+        if power == 1:  # rotation conserves the variance (tests/models/single/test_eof_rotator.py:98-137)
+            np.testing.assert_allclose(r.explained_variance().values.sum(), m.explained_variance().values[:5].sum(),
+                                       rtol=1e-5)
+
+
+# ---------------------------------------------------------------- feature sharding over gloo, world size 2
+_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests")); sys.path.insert(0, os.path.join(sys.argv[1], "tests", "golden"))
+from _inputs import planted
+from cpu_ops import TorchCpuOps
+import xeofs_b200 as xb
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+T, nlat, nlon, k = 90, 8, 20, 5
+X = planted(T, nlat * nlon, 2 * k, seed=2).reshape(T, nlat, nlon)
+X[:, 1, 3] = np.nan; X[:, 6, 7] = np.nan; X[11] = np.nan
+lat = np.linspace(70, -70, nlat)
+rows = slice(rank * nlat // world, (rank + 1) * nlat // world)
+coords = {"lat": lat[rows], "lon": np.arange(nlon) * 18.0}
+m = xb.single.EOF(n_modes=k, use_coslat=True, standardize=True, random_state=7, solver_kwargs={"n_iter": 3},
+                  distributed=True, ops=TorchCpuOps())
+m.fit(xb.DataArray(X[:, rows], ("time", "lat", "lon"), coords), dim="time")
+r = xb.single.EOFRotator(n_modes=4).fit(m)
+np.savez(os.path.join(sys.argv[2], f"rank{rank}.npz"), s=m.singular_values().values, comps=m.components().values,
+         scores=m.scores().values, evr=m.explained_variance_ratio().values, collectives=m.comm.collectives,
+         rot_ev=r.explained_variance().values, rot_comps=r.components().values)
+dist.destroy_process_group()
+'''
+
+
+def test_feature_sharded_fit_over_gloo(tmp_path):
+    """One process per shard, feature axis split by latitude rows; the result must equal the single-process fit."""
+    import xeofs_b200 as xb
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", str(script), ROOT, str(tmp_path)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-3000:]
+    T, nlat, nlon, k = 90, 8, 20, 5
+    X = planted(T, nlat * nlon, 2 * k, seed=2).reshape(T, nlat, nlon)
+    X[:, 1, 3] = np.nan
+    X[:, 6, 7] = np.nan
+    X[11] = np.nan
+    coords = {"lat": np.linspace(70, -70, nlat), "lon": np.arange(nlon) * 18.0}
+    ref = xb.single.EOF(n_modes=k, use_coslat=True, standardize=True, random_state=7, solver_kwargs={"n_iter": 3},
+                        ops=TorchCpuOps()).fit(xb.DataArray(X, DIMS, coords), dim="time")
+    rref = xb.single.EOFRotator(n_modes=4).fit(ref)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    assert int(r0["collectives"]) > 0
+    for r in (r0, r1):
+        np.testing.assert_allclose(r["s"], ref.singular_values().values, rtol=1e-6)
+        np.testing.assert_allclose(r["evr"], ref.explained_variance_ratio().values, rtol=1e-6)
+        np.testing.assert_allclose(r["scores"], ref.scores().values, rtol=1e-4, atol=1e-4, equal_nan=True)
+        np.testing.assert_allclose(r["rot_ev"], rref.explained_variance().values, rtol=1e-5)
+    comps = np.concatenate([r0["comps"], r1["comps"]], axis=0)
+    np.testing.assert_allclose(comps, ref.components().values, atol=2e-5, equal_nan=True)
+    rot = np.concatenate([r0["rot_comps"], r1["rot_comps"]], axis=0)
+    np.testing.assert_allclose(rot, rref.components().values, atol=5e-5, equal_nan=True)

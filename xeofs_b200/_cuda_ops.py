@@ -212,6 +212,16 @@ class CudaOps:
         self.launches += 1
         return out
 
+    def scaled_rows(self, f: Field, t0, t1):
+        """Rows t0:t1 of the preprocessed matrix as a space-side block (pad rows zero)."""
+        w = int(t1 - t0)
+        out = self.space_side(lpad(w), f.S)
+        check(self.lib.xeofs_b200_scaled_rows(ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr),
+                                              ptr(f.row_valid), int(t0), w, lpad(w), ptr(out), int(out.stride(0)),
+                                              self._stream()), "scaled_rows")
+        self.launches += 1
+        return out
+
     # ------------------------------------------------------------------ rotation
     def col_norms(self, L, S, m, normalized_out=False):
         h, rn = self.empty(S), self.empty(S)

@@ -110,16 +110,6 @@ class MCA:
             self.data["total_squared_covariance"] = self._total_squared_covariance()
         return self
 
-    def _scaled_rows(self, ff, t0, t1):
-        """Rows t0:t1 of the preprocessed matrix as a space-side block (scaler.py:146-153 on 128 samples)."""
-        f = ff.field
-        blk = (f.X[t0:t1] - f.pivot[None, :]) * f.dscale[None, :] + f.ccorr[None, :]
-        blk = torch.nan_to_num(blk, nan=0.0)
-        blk[:, ~ff.valid.bool()] = 0.0
-        out = torch.zeros((lpad(t1 - t0), ff.S), dtype=torch.float32, device=f.X.device)
-        out[: t1 - t0] = blk
-        return out
-
     def _total_squared_covariance(self):
         """cpcca.py:991-1000: sum |C|^2 = <X X^T, Y Y^T>_F / (n-1)^2, from the two T x T Gram matrices built
         128 columns at a time with the streaming product."""
@@ -130,8 +120,8 @@ class MCA:
         for t0 in range(0, T, 128):
             t1 = min(T, t0 + 128)
             w = t1 - t0
-            g1 = ops.project_T(f1.field, self._scaled_rows(f1, t0, t1), w, algo=ops.accurate_algo)
-            g2 = ops.project_T(f2.field, self._scaled_rows(f2, t0, t1), w, algo=ops.accurate_algo)
+            g1 = ops.project_T(f1.field, ops.scaled_rows(f1.field, t0, t1), w, algo=ops.accurate_algo)
+            g2 = ops.project_T(f2.field, ops.scaled_rows(f2.field, t0, t1), w, algo=ops.accurate_algo)
             comm.sum_(g1)
             comm.sum_(g2)
             acc += (g1[:, :w].double() * g2[:, :w].double()).sum()

@@ -91,3 +91,35 @@ extern "C" int xeofs_b200_reconstruct(const float* scores, int64_t T, int64_t ld
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
 }
+
+namespace xb {
+// out[j, s] = A[t0 + j, s] for j < nrows (the preprocessed samples as a space-side block), zero for the pad rows
+__global__ void scaled_rows_kernel(const float* __restrict__ X, int64_t S, int64_t ldx, const float* __restrict__ pivot,
+                                   const float* __restrict__ dscale, const float* __restrict__ ccorr,
+                                   const uint8_t* __restrict__ row_valid, int64_t t0, int nrows, float* __restrict__ out,
+                                   int64_t ldo) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (s >= S) return;
+  float v = 0.f;
+  if (j < nrows && (!row_valid || row_valid[t0 + j])) {
+    const float d = X[(t0 + j) * ldx + s] - pivot[s];
+    v = ((d == d) ? d * dscale[s] : 0.f) + (ccorr ? ccorr[s] : 0.f);
+  }
+  out[(int64_t)j * ldo + s] = v;
+}
+}  // namespace xb
+
+extern "C" int xeofs_b200_scaled_rows(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
+                                      const float* dscale, const float* ccorr, const uint8_t* row_valid, int64_t t0,
+                                      int64_t nrows, int64_t rows_out, float* out, int64_t ldo, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(X && pivot && dscale && out, "scaled_rows: null pointer");
+  XB_CHECK_ARG(S > 0 && ldx >= S && ldo >= S && t0 >= 0 && nrows > 0 && t0 + nrows <= T && rows_out >= nrows &&
+                   rows_out <= 65535,
+               "scaled_rows: bad shape");
+  scaled_rows_kernel<<<dim3((unsigned)ceil_div(S, 256), (unsigned)rows_out), 256, 0, stream>>>(
+      X, S, ldx, pivot, dscale, ccorr, row_valid, t0, (int)nrows, out, ldo);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}

@@ -24,8 +24,10 @@ __global__ void col_norms_kernel(const float* __restrict__ L, int64_t S, int m, 
   }
 }
 
-// One pass over the loadings: B = Ln R (chunk of 32 features at a time, fp32 products, fp64 reduction),
-// Gout += Ln^T B^3, Wout += colsum(B^2).  16x16 threads, register tile TI x TI of Gout per thread.
+// One pass over the loadings: B = Ln R (chunk of 32 features at a time), Gout += Ln^T B^3, Wout += colsum(B^2), all
+// arithmetic in fp64 on the fp32 loadings: the reference's stopping rule (relative change of sum(svals) below 1e-8,
+// _rotation.py:176) sits below fp32 noise — with B in fp32 the iteration stops ~15 % early and the rotated variances
+// are off by 1e-3.  16x16 threads, register tile TI x TI of Gout per thread.
 constexpr int VM_CHUNK = 32;
 
 template <int TI>
@@ -35,14 +37,14 @@ varimax_accumulate_kernel(const float* __restrict__ L, int64_t S, int m, int64_t
                           double* __restrict__ Gout, double* __restrict__ Wout, float* __restrict__ absmax) {
   constexpr int MP = 16 * TI;
   extern __shared__ __align__(16) unsigned char smraw[];
-  float* Rs = reinterpret_cast<float*>(smraw);            // [MP][MP+1]  R (fp32)
-  float* Ls = Rs + MP * (MP + 1);                          // [VM_CHUNK][MP+4]   normalised loadings chunk
-  float* Bs = Ls + VM_CHUNK * (MP + 4);                    // [VM_CHUNK][MP+4]   B^3 chunk
+  double* Rs = reinterpret_cast<double*>(smraw);          // [MP][MP+1]  R
+  double* Bs = Rs + MP * (MP + 1);                         // [VM_CHUNK][MP+4]   B, then f(B)
+  float* Ls = reinterpret_cast<float*>(Bs + VM_CHUNK * (MP + 4));  // [VM_CHUNK][MP+4]   normalised loadings chunk
   const int tid = threadIdx.x;
   const int ti = tid >> 4, tj = tid & 15;
   for (int idx = tid; idx < MP * MP; idx += 256) {
     const int i = idx / MP, j = idx % MP;
-    Rs[i * (MP + 1) + j] = (i < m && j < m) ? (float)R[(int64_t)i * m + j] : 0.f;
+    Rs[i * (MP + 1) + j] = (i < m && j < m) ? R[(int64_t)i * m + j] : 0.0;
   }
   double acc[TI][TI];
 #pragma unroll
@@ -52,7 +54,7 @@ varimax_accumulate_kernel(const float* __restrict__ L, int64_t S, int m, int64_t
   double wacc[(MP + 255) / 256 > 0 ? (MP + 255) / 256 : 1];
   wacc[0] = 0.0;
   float amax = 0.f;
-  const float cs = (colscale && tid < m) ? (float)colscale[tid] : 1.f;
+  const double cs = (colscale && tid < m) ? colscale[tid] : 1.0;
   (void)cs;
 
   const int64_t n_chunks = (S + VM_CHUNK - 1) / VM_CHUNK;
@@ -74,8 +76,8 @@ varimax_accumulate_kernel(const float* __restrict__ L, int64_t S, int m, int64_t
     {
       const int r = tid >> 3, c0 = tid & 7;
       for (int j = c0; j < MP; j += 8) {
-        float b = 0.f;
-        for (int i = 0; i < m; ++i) b = fmaf(Ls[r * (MP + 4) + i], Rs[i * (MP + 1) + j], b);
+        double b = 0.0;
+        for (int i = 0; i < m; ++i) b = fma((double)Ls[r * (MP + 4) + i], Rs[i * (MP + 1) + j], b);
         Bs[r * (MP + 4) + j] = b;
       }
     }
@@ -85,14 +87,13 @@ varimax_accumulate_kernel(const float* __restrict__ L, int64_t S, int m, int64_t
       double w2 = 0.0;
 #pragma unroll 4
       for (int r = 0; r < VM_CHUNK; ++r) {
-        const float bf = Bs[r * (MP + 4) + tid];
-        const double b = (double)bf;
+        const double b = Bs[r * (MP + 4) + tid];
         w2 = fma(b, b, w2);
-        amax = fmaxf(amax, fabsf(bf));
+        amax = fmaxf(amax, fabsf((float)b));
         // f(b): varimax b^3; promax target (b c)|b c|^(power-1)   (_rotation.py:57-62, 166-170)
-        float fb;
-        if (power == 3.f && !colscale) fb = bf * bf * bf;
-        else { const float u = bf * cs; fb = (power == 1.f) ? u : u * powf(fabsf(u), power - 1.f); }
+        double fb;
+        if (power == 3.f && !colscale) fb = b * b * b;
+        else { const double u = b * cs; fb = (power == 1.f) ? u : u * pow(fabs(u), (double)power - 1.0); }
         Bs[r * (MP + 4) + tid] = fb;
       }
       wacc[0] += w2;
@@ -104,7 +105,7 @@ varimax_accumulate_kernel(const float* __restrict__ L, int64_t S, int m, int64_t
 #pragma unroll
       for (int x = 0; x < TI; ++x) {
         a[x] = (double)Ls[r * (MP + 4) + ti * TI + x];
-        b[x] = (double)Bs[r * (MP + 4) + tj * TI + x];
+        b[x] = Bs[r * (MP + 4) + tj * TI + x];
       }
 #pragma unroll
       for (int x = 0; x < TI; ++x)
@@ -154,7 +155,8 @@ extern "C" int xeofs_b200_varimax_accumulate(const float* L, int64_t S, int64_t 
   XB_CHECK_ARG(power >= 1.0, "varimax_accumulate: power must be >= 1");
   const int ti = m <= 16 ? 1 : m <= 32 ? 2 : m <= 64 ? 4 : 8;
   const int MP = 16 * ti;
-  const size_t smem = ((size_t)MP * (MP + 1) + 2 * (size_t)VM_CHUNK * (MP + 4)) * sizeof(float);
+  const size_t smem = ((size_t)MP * (MP + 1) + (size_t)VM_CHUNK * (MP + 4)) * sizeof(double) +
+                      (size_t)VM_CHUNK * (MP + 4) * sizeof(float);
   const int blocks = (int)imin(ceil_div(S, VM_CHUNK), 2 * (int64_t)num_sms());
 #define XB_VM(TI)                                                                                                  \
   XB_CUDA(cudaFuncSetAttribute(varimax_accumulate_kernel<TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
