@@ -45,6 +45,9 @@ extern "C" {
 #define XEOFS_ALGO_TF32X1 2 /* tcgen05 kind::tf32, one product (power iterations)               */
 #define XEOFS_ALGO_TF32X3 3 /* tcgen05 kind::tf32, hi/lo split, 3 products (~fp32 accuracy)     */
 #define XEOFS_ALGO_AUTO_FAST 4 /* TF32X1 where the tcgen05 path applies, else SIMT (power iterations) */
+#define XEOFS_ALGO_TF32X2 5 /* tcgen05 kind::tf32, field split hi/lo, the small operand (W / Yt) must hold TF32-exact
+                               values (xeofs_b200_round_tf32): 2 products, ~fp32 accuracy; SIMT where tcgen05 does
+                               not apply                                                                        */
 
 /* flags for xeofs_b200_scaling_finalize */
 #define XEOFS_F_CENTER 1
@@ -96,6 +99,10 @@ int xeofs_b200_project_T(const float* X, int64_t T, int64_t S, int64_t ldx, cons
                          int64_t ldy, int64_t l,
                          float* Z, int64_t ldz, void* workspace, int64_t workspace_bytes, int algo,
                          void* stream);
+
+/* In place: every value of the (rows x cols, leading dimension ld) matrix keeps only the bits a TF32 operand has
+ * (the low 13 mantissa bits are cleared), so that TF32X2 products with it as the small operand are exact.        */
+int xeofs_b200_round_tf32(float* M, int64_t rows, int64_t cols, int64_t ld, void* stream);
 
 /* ---- D2: the k-column orthonormalisation (sklearn's LU / QR normalizers) as CholeskyQR -----------
  * gram:      G[i,j] (+)= sum_n M(n,i) M(n,j), fp64, l x l row-major.  side 0: M is time-side (n x ld),

@@ -16,7 +16,7 @@ class TorchCpuOps:
 
     def __init__(self):
         self.device = torch.device("cpu")
-        self.algo = self.accurate_algo = 1
+        self.algo = self.accurate_algo = self.exact_algo = 1
         self.launches = 0
         self.time_products = False
 
@@ -90,6 +90,11 @@ class TorchCpuOps:
         Z = out if out is not None else self.zeros((f.T, lp))
         Z[:, :lp] = (self._A(f) @ Yt[:lp].double().t()).float()
         return Z
+
+    def round_tf32_(self, M, rows, cols):
+        v = M[:rows, :cols].contiguous().view(torch.int32) & -8192  # 0xffffe000
+        M[:rows, :cols] = v.view(torch.float32)
+        return M
 
     # ------------------------------------------------------------------ k-column linear algebra
     @staticmethod

@@ -152,7 +152,7 @@ def test_rotator_host_logic():
         r = xb.single.EOFRotator(n_modes=5, power=power).fit(m)
         ro = orot.eof_rotator_fit(o["components_2d"], o["explained_variance"], o["scores"], o["norms"],
                                   o["A"].shape[0], n_modes=5, power=power)
-        np.testing.assert_allclose(r.explained_variance().values, ro["explained_variance"], rtol=1e-5)
+        np.testing.assert_allclose(r.explained_variance().values, ro["explained_variance"], rtol=5e-5)
         V = r.components().values.reshape(-1, 5)
         dots = (V * ro["components_2d"]).sum(axis=0)
         assert (dots > 1 - 1e-5).all(), dots

@@ -38,13 +38,15 @@ class CudaOps:
         a = _lib.ALGO_NAMES[algo] if isinstance(algo, str) else int(algo)
         # algo: arithmetic of the power-iteration products; accurate_algo: of the two products the singular
         # values are read from (the final range basis and B = Q^T M)
+        # exact_algo: the same two products when the caller has made the small operand TF32-exact (round_tf32_)
         if a == _lib.ALGO_AUTO:
-            self.algo, self.accurate_algo = _lib.ALGO_AUTO_FAST, _lib.ALGO_AUTO
+            self.algo, self.accurate_algo, self.exact_algo = _lib.ALGO_AUTO_FAST, _lib.ALGO_AUTO, _lib.ALGO_TF32X2
         elif a == _lib.ALGO_TF32X1:
-            self.algo, self.accurate_algo = _lib.ALGO_TF32X1, _lib.ALGO_TF32X3
+            self.algo, self.accurate_algo, self.exact_algo = _lib.ALGO_TF32X1, _lib.ALGO_TF32X3, _lib.ALGO_TF32X2
         else:
-            self.algo = self.accurate_algo = a
+            self.algo = self.accurate_algo = self.exact_algo = a
         self._ws = None
+        self._unit = None
         self.launches = 0  # kernels enqueued through this object (bench.py reports it)
         self.time_products = False  # bench.py: CUDA events around every streaming product on the launch stream
         self._prod_events = []
@@ -151,6 +153,12 @@ class CudaOps:
         self.launches += 2 + (2 if f.ccorr is not None else 0)
         return Z
 
+    def round_tf32_(self, M, rows, cols):
+        """In place: keep the TF32 bits of every value (so that ALGO_TF32X2 products with M are exact)."""
+        check(self.lib.xeofs_b200_round_tf32(ptr(M), int(rows), int(cols), int(M.stride(0)), self._stream()), "round_tf32")
+        self.launches += 1
+        return M
+
     # ------------------------------------------------------------------ k-column linear algebra
     def gram(self, M, n, l, side, out=None, accumulate=False):
         G = out if out is not None else self.empty((l, l), torch.float64)
@@ -167,9 +175,26 @@ class CudaOps:
         self.launches += 1
         return Rinv, info
 
+    def _unit_vectors(self, S):
+        if self._unit is None or self._unit[0].numel() < S:
+            self._unit = (self.zeros(S), torch.ones(S, dtype=torch.float32, device=self.device))
+        return self._unit[0][:S], self._unit[1][:S]
+
     def apply(self, In, n, l, side, Mat, k, colscale=None, out=None):
         """Out(n, j') = sum_j In(n, j) Mat[j, j'] colscale[j'];  same side/layout as In, kp = lpad(k) columns."""
         kp = lpad(k)
+        if (side == 1 and self.accurate_algo != _lib.ALGO_SIMT and In.stride(0) % 4 == 0 and In.data_ptr() % 16 == 0
+                and bool(self.lib.xeofs_b200_has_tcgen05())):
+            # space-side: (kp x n) = Mat^T (k x l) . In (l x n) is the streaming product A^T W of the (l x n) "field" In
+            # with W = Mat: the tensor-core kernel in 3xTF32 (fp32-level accuracy), in place if out is In
+            W = self.zeros((l, kp))
+            M = Mat[:l, :k] if colscale is None else Mat[:l, :k] * colscale[None, :k]
+            W[:, :k] = M.to(torch.float32)
+            zero, one = self._unit_vectors(n)
+            f = Field(In[:l, :n], zero, one, None, None)
+            if out is None:
+                out = self.space_side(kp, n)
+            return self.project_S(f, W, k, algo=_lib.ALGO_TF32X3, out=out)
         if out is None:
             out = self.space_side(kp, n) if side == 1 else self.zeros((n, kp))
         check(self.lib.xeofs_b200_apply(ptr(In), n, l, int(In.stride(0)), side, ptr(Mat), int(Mat.stride(0)), k,

@@ -74,11 +74,12 @@ class FittedField:
         self.center = self.standardize = False
 
 
-def fit_field(ops, X, featw=None, center=True, standardize=False, check_nans=True, comm=NO_COMM):
+def fit_field(ops, X, featw=None, center=True, standardize=False, check_nans=True, comm=NO_COMM, overlap=None):
     """One streaming pass of column statistics + the Scaler vectors (scaler.py:100-153), the Sanitizer
     masks and its isolated-NaN check (sanitizer.py:46-56, 108-122), total variance (utils/xarray_utils.py:236-253).
 
     X: (T, S_local) fp32 CUDA tensor (row stride arbitrary), featw: (S_local,) fp64 CUDA tensor or None.
+    ``overlap``: host work to run while the statistics pass is in flight (before the one host sync).
     """
     from ._cuda_ops import Field
 
@@ -87,35 +88,38 @@ def fit_field(ops, X, featw=None, center=True, standardize=False, check_nans=Tru
     fin = ops.scaling_finalize(st, featw, center, standardize)
     # scalars: total variance, number of valid features, max / min non-NaN count over valid features
     sc = fin["scalars"].clone()
+    row_nan = st["row_nan"].to(torch.int64)
+    S_global = S
     if comm.active:
-        head = sc[:2].clone()
+        head = torch.cat([sc[:2], torch.tensor([float(S)], dtype=torch.float64, device=sc.device)])
         comm.sum_(head)
         mx = sc[2:3].clone()
         comm.max_(mx)
         mn = sc[3:4].clone()
         comm.min_(mn)
-        sc = torch.cat([head, mx, mn])
-    row_nan = st["row_nan"].to(torch.int64)
-    n_feat_local = torch.tensor([S], dtype=torch.int64, device=row_nan.device)
-    if comm.active:
         comm.sum_(row_nan)
-        comm.sum_(n_feat_local)
-    S_global = int(n_feat_local.item())
-    sc_h = sc.cpu().numpy()  # the one host sync of the preprocessing
-    total_variance, n_valid = float(sc_h[0]), int(round(sc_h[1]))
-    n_invalid = S_global - n_valid
+        sc = torch.cat([head[:2], mx, mn, head[2:3]])
+    else:
+        sc = torch.cat([sc, torch.tensor([float(S)], dtype=torch.float64, device=sc.device)])
+    # a sample is valid when it holds at least one non-NaN value (sanitizer.py:49-50); every sample must have either
+    # none or all of the valid features (sanitizer.py:115-122).  Evaluated on the device, fetched with ONE copy.
+    s_glob = sc[4]
+    n_invalid = s_glob - sc[1]
+    rn = row_nan.double()
+    valid_sample = rn < s_glob
+    pattern_ok = ((rn == n_invalid) | (rn == s_glob)).all()
+    packed = torch.cat([sc, valid_sample.sum().double()[None], pattern_ok.double()[None]])
+    if overlap is not None:
+        overlap()
+    h = packed.cpu().numpy()  # the one host sync of the preprocessing
+    total_variance, n_valid, S_global = float(h[0]), int(round(h[1])), int(round(h[4]))
+    n_samples = int(round(h[5]))
     if n_valid == 0:
         raise ValueError("Input data contains no valid (non-NaN) feature.")
-    # a sample is valid when it holds at least one non-NaN value (sanitizer.py:49-50)
-    valid_sample = row_nan < S_global
-    if check_nans:
-        # sanitizer.py:115-122: every sample has either 0 or all-valid-features non-NaN entries
-        ok = (row_nan == n_invalid) | (row_nan == S_global)
-        if not bool(ok.all().item()):
-            raise ValueError(
-                "Input data contains partial NaN entries, which will cause the the SVD to fail."
-            )
-    n_samples = int(valid_sample.sum().item())
+    if check_nans and h[6] == 0.0:
+        raise ValueError(
+            "Input data contains partial NaN entries, which will cause the the SVD to fail."
+        )
     ff = FittedField()
     # centred: pivot == mean, the rank-1 term vanishes;  all-NaN samples are named to the kernels only when present
     ccorr = None if center else fin["ccorr"]
@@ -154,12 +158,18 @@ class FieldOperator:
         self.comm.sum_(Z)
         return Z
 
-    def mul(self, Q, l, accurate=False):
-        algo = self.ops.accurate_algo if accurate else self.algo
+    # products with a TF32-exact small operand need two tensor-core products instead of three for fp32 accuracy
+    supports_exact = True
+
+    def _algo(self, accurate, exact):
+        return self.ops.exact_algo if exact else (self.ops.accurate_algo if accurate else self.algo)
+
+    def mul(self, Q, l, accurate=False, exact=False):
+        algo = self._algo(accurate, exact)
         return self._proj_S(Q, l, algo) if self.transposed else self._proj_T(Q, l, algo)
 
-    def mul_t(self, Q, l, accurate=False):
-        algo = self.ops.accurate_algo if accurate else self.algo
+    def mul_t(self, Q, l, accurate=False, exact=False):
+        algo = self._algo(accurate, exact)
         return self._proj_T(Q, l, algo) if self.transposed else self._proj_S(Q, l, algo)
 
     def sketch_rows(self):
@@ -170,6 +180,8 @@ class FieldOperator:
 class CrossOperator:
     """Implicit cross-covariance C = X^T Y / (n - 1) (cross/cpcca.py:1008-1015) — never materialised:
     C Q = X^T (Y Q) / (n-1), C^T Q = Y^T (X Q) / (n-1).  M = C^T when S1 < S2 (sklearn's transpose rule)."""
+
+    supports_exact = False  # the intermediate time-side block of C Q = X^T (Y Q) is not TF32-exact
 
     def __init__(self, ops, fx, fy, comm=NO_COMM, algo=None):
         self.ops, self.fx, self.fy, self.comm, self.algo = ops, fx, fy, comm, algo
@@ -222,14 +234,38 @@ def orthonormalize(ops, M, dim, l, comm, passes, infos):
     return M
 
 
-def sketch_matrix(ops, op, l, random_state, comm=NO_COMM):
+_SKETCH_CACHE = {}
+
+
+def draw_sketch(random_state, rows, l):
+    """The host draw of sklearn's range finder, rng.normal(size=(rows, l)) with numpy's legacy RandomState (the
+    stream the reference uses, so both sides project on the same sketch).  The generator fills row-major, so the
+    first n rows of a larger draw are the draw for n rows.  The draw is a pure function of an integer seed and the
+    shape (about 30 ns per number, single-threaded): the last few are memoised."""
+    if isinstance(random_state, np.random.RandomState):
+        return random_state.normal(size=(rows, l))
+    if random_state is None:
+        return np.random.RandomState(None).normal(size=(rows, l))
+    key = (int(random_state), int(rows), int(l))
+    hit = _SKETCH_CACHE.get(key)
+    if hit is None:
+        hit = np.random.RandomState(key[0]).normal(size=(rows, l))
+        if len(_SKETCH_CACHE) >= 4:
+            _SKETCH_CACHE.pop(next(iter(_SKETCH_CACHE)))
+        _SKETCH_CACHE[key] = hit
+    return hit
+
+
+def sketch_matrix(ops, op, l, random_state, comm=NO_COMM, predrawn=None):
     """sklearn.utils.extmath.randomized_range_finder: Q = rng.normal(size=(M.shape[1], l)) with M the reference's
     compacted matrix (all-NaN samples / features dropped), generated on the host with numpy's RandomState so that
     the oracle and the device path share the sketch; rows are scattered to the entries that survive the Sanitizer."""
-    rng = random_state if isinstance(random_state, np.random.RandomState) else np.random.RandomState(random_state)
     n_valid_global = op.shape[1]
     n_local, side, mask = op.c[1], op.c[2], op.c_mask
-    Om = rng.normal(size=(n_valid_global, l))
+    if predrawn is not None and predrawn.shape[0] >= n_valid_global and predrawn.shape[1] == l:
+        Om = predrawn[:n_valid_global]
+    else:
+        Om = draw_sketch(random_state, n_valid_global, l)
     n_loc_valid = n_local if mask is None else int(mask.sum().item())
     offset = 0
     if side == 1 and comm.active:  # features are sharded: this rank's first valid feature in the global order
@@ -254,7 +290,8 @@ def sketch_matrix(ops, op, l, random_state, comm=NO_COMM):
     return buf
 
 
-def randomized_svd(ops, op, k, n_oversamples=10, n_iter="auto", random_state=None, comm=NO_COMM, Omega=None):
+def randomized_svd(ops, op, k, n_oversamples=10, n_iter="auto", random_state=None, comm=NO_COMM, Omega=None,
+                   predrawn=None):
     """Halko et al. range finder + small SVD, the arithmetic of sklearn.utils.extmath.randomized_svd
     (power_iteration_normalizer='auto', transpose='auto') with CholeskyQR as the normalizer.
 
@@ -271,13 +308,22 @@ def randomized_svd(ops, op, k, n_oversamples=10, n_iter="auto", random_state=Non
         n_iter = 7 if k < 0.1 * min(n_r, n_c) else 4
     infos = []
     if Omega is None:
-        Q = sketch_matrix(ops, op, l, random_state, comm)
+        Q = sketch_matrix(ops, op, l, random_state, comm, predrawn)
     else:
         Q = Omega
     for _ in range(int(n_iter)):
         Q = orthonormalize(ops, op.mul(Q, l), op.r, l, comm, 1, infos)
         Q = orthonormalize(ops, op.mul_t(Q, l), op.c, l, comm, 1, infos)
-    Q = orthonormalize(ops, op.mul(Q, l, accurate=True), op.r, l, comm, 2, infos)   # r-side, orthonormal
+    # The last two passes decide the singular values and run at fp32 accuracy.  For the first of them the small
+    # operand can be made TF32-exact beforehand — rounding the current iterate is harmless, any nearby iterate serves
+    # the range finder — and then two tensor-core products (field hi/lo x operand) do instead of three.  The range
+    # basis itself must not be rounded (B = Q^T M has to use the orthonormal Q exactly), so the second pass is 3xTF32.
+    if getattr(op, "supports_exact", False):
+        ops.round_tf32_(Q, *((op.c[1], lpad(l)) if op.c[2] == 0 else (lpad(l), op.c[1])))
+        Y = op.mul(Q, l, exact=True)
+    else:
+        Y = op.mul(Q, l, accurate=True)
+    Q = orthonormalize(ops, Y, op.r, l, comm, 2, infos)                         # r-side, orthonormal
     Bt = op.mul_t(Q, l, accurate=True)                                          # c-side: B^T = M^T Q
     # svd(B) through the l x l Gram of B^T: B B^T = Uh diag(s^2) Uh^T; V = B^T Uh / s; U = Q Uh
     G = _gram(ops, Bt, op.c, l, comm)

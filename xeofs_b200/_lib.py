@@ -13,8 +13,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libxeofs_b200.so")
 
-ALGO_AUTO, ALGO_SIMT, ALGO_TF32X1, ALGO_TF32X3, ALGO_AUTO_FAST = 0, 1, 2, 3, 4
-ALGO_NAMES = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tf32x1": ALGO_TF32X1, "tf32x3": ALGO_TF32X3}
+ALGO_AUTO, ALGO_SIMT, ALGO_TF32X1, ALGO_TF32X3, ALGO_AUTO_FAST, ALGO_TF32X2 = 0, 1, 2, 3, 4, 5
+ALGO_NAMES = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tf32x1": ALGO_TF32X1, "tf32x3": ALGO_TF32X3, "tf32x2": ALGO_TF32X2}
 F_CENTER, F_STANDARDIZE = 1, 2
 E_INVALID, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = -1, -2, -3, -4
 
@@ -32,6 +32,7 @@ SIGNATURES = {
     "xeofs_b200_project_workspace_bytes": (_i64, [_i64, _i64, _i64, _int]),
     "xeofs_b200_project_S": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _int, _p]),
     "xeofs_b200_project_T": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _int, _p]),
+    "xeofs_b200_round_tf32": (_int, [_p, _i64, _i64, _i64, _p]),
     "xeofs_b200_gram": (_int, [_p, _i64, _i64, _i64, _int, _p, _int, _p]),
     "xeofs_b200_chol_inv": (_int, [_p, _i64, _p, _p, _p]),
     "xeofs_b200_apply": (_int, [_p, _i64, _i64, _i64, _int, _p, _i64, _i64, _p, _p, _i64, _p]),

@@ -52,7 +52,7 @@ class Preprocessor:
         return t2, sample_shape, feature_shape
 
     # ------------------------------------------------------------------ fit
-    def fit_transform(self, X, sample_dims, weights=None):
+    def fit_transform(self, X, sample_dims, weights=None, overlap=None):
         data, dims, coords, self.as_xarray = L.unpack(X)
         self._dim = sample_dims
         X2, self.sample_shape, self.feature_shape = self._to_2d(data, dims, fit=True)
@@ -77,7 +77,7 @@ class Preprocessor:
         self.featw_host = None if featw is None else np.ascontiguousarray(featw.reshape(-1))
         featw_dev = None if featw is None else self.ops.to_device(self.featw_host, torch.float64)
         self.fitted = fit_field(self.ops, X2, featw_dev, center=self.with_center, standardize=self.with_std,
-                                check_nans=self.check_nans, comm=self.comm)
+                                check_nans=self.check_nans, comm=self.comm, overlap=overlap)
         return self.fitted
 
     # ------------------------------------------------------------------ transform of unseen data

@@ -56,12 +56,33 @@ extern "C" int xeofs_b200_has_tcgen05(void) {
 }
 
 static int resolve_algo(int algo, int64_t T, int64_t S, int64_t ldx, const float* X, int64_t l) {
+  if (algo == XEOFS_ALGO_TF32X2 && !(xeofs_b200_has_tcgen05() && tc_supported(T, S, ldx, X, l))) return XEOFS_ALGO_SIMT;
   if (algo == XEOFS_ALGO_AUTO || algo == XEOFS_ALGO_AUTO_FAST) {
     const bool tc = xeofs_b200_has_tcgen05() && tc_supported(T, S, ldx, X, l);
     if (!tc) return XEOFS_ALGO_SIMT;
     return algo == XEOFS_ALGO_AUTO ? XEOFS_ALGO_TF32X3 : XEOFS_ALGO_TF32X1;
   }
   return algo;
+}
+
+namespace xb {
+__global__ void round_tf32_kernel(float* __restrict__ M, int64_t rows, int64_t cols, int64_t ld) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+    float* q = M + r * ld + c;
+    *q = __uint_as_float(__float_as_uint(*q) & 0xffffe000u);
+  }
+}
+}  // namespace xb
+
+extern "C" int xeofs_b200_round_tf32(float* M, int64_t rows, int64_t cols, int64_t ld, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(M && rows > 0 && cols > 0 && ld >= cols, "round_tf32: bad arguments");
+  dim3 grid((unsigned)ceil_div(cols, 256), (unsigned)imin(rows, 16384));
+  round_tf32_kernel<<<grid, 256, 0, stream>>>(M, rows, cols, ld);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
 }
 
 extern "C" int64_t xeofs_b200_project_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo) {
@@ -78,7 +99,7 @@ static int check_project_args(const char* who, const float* X, int64_t T, int64_
   XB_CHECK_ARG(l > 0 && l <= 128, "%s: l=%lld must be in 1..128", who, (long long)l);
   XB_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0, "%s: leading dimensions of the small matrices must be multiples of 4", who);
   XB_CHECK_ARG(((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)ws % 256 == 0), "%s: misaligned buffer", who);
-  XB_CHECK_ARG(algo >= XEOFS_ALGO_AUTO && algo <= XEOFS_ALGO_AUTO_FAST, "%s: unknown algo %d", who, algo);
+  XB_CHECK_ARG(algo >= XEOFS_ALGO_AUTO && algo <= XEOFS_ALGO_TF32X2, "%s: unknown algo %d", who, algo);
   if (ws_bytes < xeofs_b200_project_workspace_bytes(T, S, l, algo)) {
     set_error("%s: workspace too small (%lld < %lld bytes)", who, (long long)ws_bytes,
               (long long)xeofs_b200_project_workspace_bytes(T, S, l, algo));

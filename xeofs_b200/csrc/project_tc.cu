@@ -32,7 +32,7 @@ namespace xb {
 
 // warps per TMEM lane quarter in the operand stage: the 3xTF32 kernels run one CTA per SM and need the extra warps to
 // hide the latencies of their longer conversion chain
-__host__ __device__ constexpr int tc_nw(int ns) { return ns == 3 ? 4 : 2; }
+__host__ __device__ constexpr int tc_nw(int ns) { return ns >= 2 ? 4 : 2; }
 __host__ __device__ constexpr int tc_threads(int ns) { return 64 + 128 * tc_nw(ns); }
 constexpr int TC_KC = 32;        // K elements per stage (= one 128-byte swizzle atom of fp32)
 constexpr int TC_TILE = 128;     // rows of D per CTA (TMEM lanes)
@@ -208,7 +208,6 @@ struct TcParams {
   const float* dscale;  // same
   const float* ccorr;   // project_S epilogue (may be null)
   const float* wsum;    // project_S epilogue: column sums of W [lp]
-  uint32_t exp_xor;     // timing experiments only (0 in production)
   const uint8_t* chunk_flags;  // project_S: [K-chunk] 1 if the 32 samples hold one that is NaN throughout (null: none)
   float* out;           // project_S: Yt (ldo = ldy);  project_T: partial sums [split][tiles*128][lp]
   int64_t ldo;
@@ -235,7 +234,8 @@ __global__ void __launch_bounds__(tc_threads(NS), (NS == 1 && !SIDE_T) ? 2 : 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBhi,
                   const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
   static_assert(SIDE_T || KB == 1, "project_S stages are 32 rows of t");
-  constexpr int NPART = NS == 3 ? 2 : 1;            // operand parts kept per value (hi | lo)
+  constexpr int NPART = NS >= 2 ? 2 : 1;            // parts of the big operand kept per value (hi | lo)
+  constexpr int BPART = NS == 3 ? 2 : 1;            // parts of the small operand (NS == 2: it is TF32-exact already)
   constexpr int NW = tc_nw(NS);                     // operand-stage warps per TMEM lane quarter
   constexpr int KW = TC_KC / NW;                    // K values of a slab converted by one warp
   // project_T: a stage holds 128 rows of KB*32 (+4) floats, KB*128 + 16 bytes apart: TMA fetches them as 128 long
@@ -244,15 +244,15 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   constexpr int XPITCH = SIDE_T ? KB * 128 + 16 : TC_TILE * 4;
   constexpr int XB = SIDE_T ? TC_TILE * XPITCH : TC_XBYTES;  // bytes of X per stage
   constexpr int ACOLS = TC_KC * KB * NPART;         // TMEM columns of one A-operand slot
-  constexpr int FLUSH_STAGES = TC_FLUSH / KB;       // stages per accumulator flush group (NS == 3)
+  constexpr int FLUSH_STAGES = TC_FLUSH / KB;       // stages per accumulator flush group (NS >= 2)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stages = p.stages, lp = p.lp;
   const int bbytes = lp * TC_KC * 4;                    // one K-major slab of the small operand
   uint8_t* xs = smem;                                   // [stages][XB]
-  uint8_t* bs = xs + (size_t)stages * XB;               // [stages][NPART][KB][bbytes]
-  uint8_t* pd = bs + (size_t)stages * NPART * KB * bbytes;  // [stages][pivot KB*128 B | dscale KB*128 B] (SIDE_T)
+  uint8_t* bs = xs + (size_t)stages * XB;               // [stages][BPART][KB][bbytes]
+  uint8_t* pd = bs + (size_t)stages * BPART * KB * bbytes;  // [stages][pivot KB*128 B | dscale KB*128 B] (SIDE_T)
   uint64_t* bars = (uint64_t*)(pd + (SIDE_T ? (size_t)stages * KB * 256 : 0));
   uint64_t* full = bars;                       // TMA bytes landed
   uint64_t* empty = bars + TC_MAX_STAGES;      // MMAs of the stage retired
@@ -282,12 +282,12 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t a_col0 = (NS == 3 ? 2 : 1) * p.dcols;  // first TMEM column of the A-operand ring
+  const uint32_t a_col0 = (NS >= 2 ? 2 : 1) * p.dcols;  // first TMEM column of the A-operand ring
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     // the whole warp walks the ring; one elected lane issues
-    const uint32_t tx = XB + bbytes * NPART * KB + (SIDE_T ? KB * 256 : 0);
+    const uint32_t tx = XB + bbytes * BPART * KB + (SIDE_T ? KB * 256 : 0);
     const int tile0i = (int)tile0;
     Pipe pp;
     for (int c = 0; c < nchunks; ++c, pp.advance(stages)) {
@@ -295,7 +295,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       mbar_wait(&empty[st], pp.ph ^ 1);
       if (elect_one()) {
         mbar_expect_tx(&full[st], tx);
-        uint8_t* b = bs + (size_t)st * NPART * KB * bbytes;
+        uint8_t* b = bs + (size_t)st * BPART * KB * bbytes;
         const int brow = (chunk0 + c) * KB * (lp >> 3);
         if (!SIDE_T) {
           tma_load_2d(xs + (size_t)st * XB, &mapX, tile0i, c * TC_KC, &full[st], HINT_EVICT_FIRST);
@@ -319,7 +319,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const int st = pp.st;
         uint32_t d_tmem = tmem_base;
         bool first = c == 0;
-        if (NS == 3) {
+        if (NS >= 2) {
           const int buf = g & 1;
           first = cg == 0;
           if (first) mbar_wait(&dempty[buf], (((uint32_t)g >> 1) & 1) ^ 1);  // registers hold what this buffer had
@@ -328,10 +328,10 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         mbar_wait(&full[st], pp.ph);
         mbar_wait(&aready[st], pp.ph);
         tc_fence_after();
-        const bool group_end = NS == 3 && (cg + 1 == FLUSH_STAGES || c == nchunks - 1);
+        const bool group_end = NS >= 2 && (cg + 1 == FLUSH_STAGES || c == nchunks - 1);
         if (elect_one()) {
           const uint32_t a_hi = tmem_base + a_col0 + st * ACOLS;
-          const uint32_t b0 = smem_u32(bs + (size_t)st * NPART * KB * bbytes);
+          const uint32_t b0 = smem_u32(bs + (size_t)st * BPART * KB * bbytes);
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
             const uint64_t dh = make_b_desc(b0 + kb * bbytes);
@@ -341,10 +341,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
               // +32 bytes (8 tf32) along K inside the swizzle atom = +2 in the (address >> 4) field
               const uint32_t a = a_hi + kb * TC_KC + k * 8;
               mma_tf32_ts(d_tmem, a, dh + 2 * k, idesc, !(first && kb == 0 && k == 0));
-              if (NS == 3) {
-                mma_tf32_ts(d_tmem ^ p.exp_xor, a, dl + 2 * k, idesc, 1);
-                mma_tf32_ts(d_tmem, a + TC_KC * KB, dh + 2 * k, idesc, 1);
-              }
+              if (NS == 3) mma_tf32_ts(d_tmem, a, dl + 2 * k, idesc, 1);
+              if (NS >= 2) mma_tf32_ts(d_tmem, a + TC_KC * KB, dh + 2 * k, idesc, 1);
             }
           }
           mma_commit(&empty[st]);
@@ -352,7 +350,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           if (NS == 1 && c == nchunks - 1) mma_commit(&dfull[0]);
         }
         __syncwarp();
-        if (NS == 3) {
+        if (NS >= 2) {
           if (group_end) { ++g; cg = 0; } else { ++cg; }
         }
       }
@@ -368,7 +366,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     float piv = 0.f;
     if (!SIDE_T) piv = (tile0 + row < p.S) ? p.pivot[tile0 + row] : 0.f;
 
-    constexpr int ACCN = NS == 3 ? 128 / NW : 1;
+    constexpr int ACCN = NS >= 2 ? 128 / NW : 1;
     const int cw = lp / NW;      // accumulator columns of this warp: [part*cw, +cw)
     const int groups = cw >> 2;  // in groups of 4
     float acc[ACCN];
@@ -387,7 +385,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           float v[4];
           tmem_ld4(tmem_base + lane_addr + buf * p.dcols + part * cw + gi * 4, v);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc[(NS == 3 ? gi * 4 + e : 0)] += v[e];
+          for (int e = 0; e < 4; ++e) acc[(NS >= 2 ? gi * 4 + e : 0)] += v[e];
         }
       }
       tc_fence_before();
@@ -399,7 +397,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     Pipe pp;
     for (int c = 0; c < nchunks; ++c, pp.advance(stages)) {
       const int st = pp.st;
-      if (NS == 3 && next_flush < nflush && c >= (next_flush + 1) * FLUSH_STAGES + 1) flush(next_flush++);
+      if (NS >= 2 && next_flush < nflush && c >= (next_flush + 1) * FLUSH_STAGES + 1) flush(next_flush++);
       // project_S: a NaN only spoils the row of D of its own feature (dropped in the epilogue if the feature is
       // invalid), except in samples that are NaN throughout: only stages holding such a sample test every value
       const bool check = SIDE_T || (p.chunk_flags != nullptr && p.chunk_flags[c] != 0);
@@ -421,7 +419,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           }
 #pragma unroll
           for (int r = 0; r < KW; ++r) {
-            if (NS == 3) {
+            if (NS >= 2) {
               hi[r] = __float_as_uint(v[r]) & 0xffffe000u;
               lo[r] = __float_as_uint(v[r] - __uint_as_float(hi[r]));
             } else {
@@ -445,7 +443,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             for (int e = 0; e < 4; ++e) {
               float v = xa[e] - pa[e];
               v = (fabsf(v) <= 3.4028234e38f) ? v * da[e] : 0.f;
-              if (NS == 3) {
+              if (NS >= 2) {
                 hi[cc * 4 + e] = __float_as_uint(v) & 0xffffe000u;
                 lo[cc * 4 + e] = __float_as_uint(v - __uint_as_float(hi[cc * 4 + e]));
               } else {
@@ -455,7 +453,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           }
         }
         tmem_st<KW>(a_slot + kb * TC_KC, hi);
-        if (NS == 3) tmem_st<KW>(a_slot + kb * TC_KC + TC_KC * KB, lo);
+        if (NS >= 2) tmem_st<KW>(a_slot + kb * TC_KC + TC_KC * KB, lo);
       }
       tmem_wait_st();
       tc_fence_before();
@@ -464,7 +462,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
 
     // ---- epilogue: D (128 x lp fp32: TMEM for x1, registers for x3) -> global
-    if (NS == 3) {
+    if (NS >= 2) {
       while (next_flush < nflush) flush(next_flush++);
     } else {
       mbar_wait(&dfull[0], 0);
@@ -483,9 +481,9 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       if (gi < groups) {
         const int j0 = part * cw + gi * 4;
         float v[4];
-        if (NS == 3) {
+        if (NS >= 2) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] = acc[(NS == 3 ? gi * 4 + e : 0)];
+          for (int e = 0; e < 4; ++e) v[e] = acc[(NS >= 2 ? gi * 4 + e : 0)];
         } else {
           tmem_ld4(tmem_base + lane_addr + j0, v);
         }
@@ -658,6 +656,7 @@ bool tc_supported(int64_t T, int64_t S, int64_t ldx, const float* X, int64_t l) 
 
 static inline int64_t align256(int64_t b) { return round_up(b, 256); }
 static inline bool is_x3(int algo) { return algo == XEOFS_ALGO_TF32X3 || algo == XEOFS_ALGO_AUTO; }
+static inline int algo_ns(int algo) { return algo == XEOFS_ALGO_TF32X3 ? 3 : algo == XEOFS_ALGO_TF32X2 ? 2 : 1; }
 
 // project_T: 32-wide K slabs per stage = bytes of a row fetched per bulk copy / 128.  The largest that leaves
 // at least two stages of shared memory and TMEM.
@@ -668,14 +667,14 @@ struct Shape {
 };
 static Shape pick_shape(int lp, int ns, bool side_t, int kb) {
   Shape sh;
-  const int npart = ns == 3 ? 2 : 1;
+  const int npart = ns >= 2 ? 2 : 1, bpart = ns == 3 ? 2 : 1;
   const bool two_ctas = !side_t && ns == 1;  // project_S x1: two CTAs per SM share the 512 TMEM columns
   const int xb = side_t ? TC_TILE * (kb * 128 + 16) : TC_XBYTES;
-  const int per_stage = xb + lp * TC_KC * 4 * npart * kb + (side_t ? kb * 256 : 0);
+  const int per_stage = xb + lp * TC_KC * 4 * bpart * kb + (side_t ? kb * 256 : 0);
   sh.kb = kb;
   sh.dcols = (int)round_up(lp, 32);
   sh.tmem_cols = two_ctas ? 256 : 512;
-  const int ring = (int)sh.tmem_cols - (ns == 3 ? 2 : 1) * sh.dcols;
+  const int ring = (int)sh.tmem_cols - (ns >= 2 ? 2 : 1) * sh.dcols;
   const int by_tmem = ring / (TC_KC * kb * npart);
   const int budget = (two_ctas ? 110 : 222) * 1024 - 2048;
   int st = budget / per_stage;
@@ -750,7 +749,7 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
                  int64_t ldy, void* workspace, int64_t workspace_bytes, int algo, cudaStream_t stream) {
   (void)workspace_bytes;
   const int lp = (int)lpad(l);
-  const int ns = algo == XEOFS_ALGO_TF32X3 ? 3 : 1;
+  const int ns = algo_ns(algo);
   const int64_t Tpad = round_up(T, TC_KC);
   uint8_t* ws = (uint8_t*)workspace;
   float* wsum = (float*)ws;
@@ -786,10 +785,10 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   p.out = Yt; p.ldo = ldy;
   p.X = X; p.ldx = ldx; p.bimg_hi = Whi; p.bimg_lo = Wlo;
   p.chunk_flags = row_valid ? flags : nullptr;
-  p.exp_xor = env_int("XEOFS_TC_EXP", 0) == 2 ? 64 : 0;
   dim3 grid((unsigned)ceil_div(S, TC_TILE));
-  return ns == 3 ? launch_tc<3, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
-                 : launch_tc<1, false, 1>(mx, mh, ml, p, grid, sh.smem, stream);
+  return ns == 3   ? launch_tc<3, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
+         : ns == 2 ? launch_tc<2, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
+                   : launch_tc<1, false, 1>(mx, mh, ml, p, grid, sh.smem, stream);
 }
 
 int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot, const float* dscale,
@@ -797,11 +796,11 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
                  int64_t ldz, void* workspace, int64_t workspace_bytes, int algo, cudaStream_t stream) {
   (void)workspace_bytes;
   const int lp = (int)lpad(l);
-  const int ns = algo == XEOFS_ALGO_TF32X3 ? 3 : 1;
+  const int ns = algo_ns(algo);
   const Shape sh = pick_shape_T(lp, ns, S, ldx);
   XB_CHECK_ARG(sh.stages >= 1, "project_T: no pipeline shape fits lp=%d", lp);
   const int kb = sh.kb;
-  const TGeom g = t_geometry(T, S, ns == 3, kb);
+  const TGeom g = t_geometry(T, S, ns >= 2, kb);
   XB_CHECK_ARG(g.splits <= 65535, "project_T: too many splits");
   uint8_t* ws = (uint8_t*)workspace;
   float* rvec = (float*)ws; ws += align256(lp * 4);
@@ -840,6 +839,7 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   }
 #define XB_T_LAUNCH(NSV, KBV) launch_tc<NSV, true, KBV>(mx, mh, ml, p, grid, sh.smem, stream)
   if (ns == 3) rc = kb == 1 ? XB_T_LAUNCH(3, 1) : kb == 2 ? XB_T_LAUNCH(3, 2) : XB_T_LAUNCH(3, 4);
+  else if (ns == 2) rc = kb == 1 ? XB_T_LAUNCH(2, 1) : kb == 2 ? XB_T_LAUNCH(2, 2) : XB_T_LAUNCH(2, 4);
   else rc = kb == 1 ? XB_T_LAUNCH(1, 1) : kb == 2 ? XB_T_LAUNCH(1, 2) : XB_T_LAUNCH(1, 4);
 #undef XB_T_LAUNCH
   if (rc) return rc;

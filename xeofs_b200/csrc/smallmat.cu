@@ -10,17 +10,30 @@
 namespace xb {
 
 // ------------------------------------------------------------------------------------------------
-// Gram matrix in fp64.  Persistent blocks sweep chunks of n; each thread keeps a TI x TI register tile
-// of the l x l result (16 x 16 threads), so the global atomics are one per entry per block.
+// Gram matrix in fp64 (CholeskyQR needs the Gram to cond^2 accuracy).  Persistent blocks sweep chunks of n; the
+// chunk is converted to fp64 once on its way into shared memory.  The l x l result is cut into TI x TI register
+// tiles (NT per side) and only the tiles on or above the diagonal are computed; with few tiles the rows of the
+// chunk are dealt to KG thread groups.  8 x 8 tiles read 16 doubles for 64 fma, which keeps the kernel on the fp64
+// pipe rather than on shared-memory bandwidth.  Global atomics: one per entry per group per block.
 constexpr int GR_CHUNK = 32;
 
-template <int TI, int SIDE>
+template <int TI, int NT, int KG, int SIDE>
 __global__ void __launch_bounds__(256)
 gram_kernel(const float* __restrict__ M, int64_t n, int l, int64_t ld, double* __restrict__ G) {
-  constexpr int LP = 16 * TI;
-  __shared__ __align__(16) float sm[GR_CHUNK][LP + 4];  // [n_local][column]
+  constexpr int LP = TI * NT;
+  constexpr int NTILES = NT * (NT + 1) / 2;
+  static_assert(NTILES * KG <= 256, "tiles x groups must fit the block");
+  __shared__ __align__(16) double sm[GR_CHUNK][LP + 2];  // [n_local][column]
   const int tid = threadIdx.x;
-  const int ti = tid >> 4, tj = tid & 15;
+  // thread -> (upper-triangular tile (ti <= tj), row group kg)
+  int ti = -1, tj = -1;
+  const int kg = tid / NTILES;
+  if (tid < NTILES * KG) {
+    int t = tid - kg * NTILES, row = 0;
+    while (t >= NT - row) { t -= NT - row; ++row; }
+    ti = row;
+    tj = row + t;
+  }
   double acc[TI][TI];
 #pragma unroll
   for (int a = 0; a < TI; ++a)
@@ -28,48 +41,72 @@ gram_kernel(const float* __restrict__ M, int64_t n, int l, int64_t ld, double* _
     for (int b = 0; b < TI; ++b) acc[a][b] = 0.0;
 
   const int64_t n_chunks = (n + GR_CHUNK - 1) / GR_CHUNK;
-  for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+  // the next chunk travels from global memory into registers while the current one is multiplied
+  constexpr int PER = GR_CHUNK * LP / 256;
+  float nxt[PER];
+  auto fetch = [&](int64_t ch) {
     const int64_t n0 = ch * GR_CHUNK;
     if (SIDE == 1) {
       // space-side: element (n, j) at M[j*ld + n]; 32 lanes read 32 consecutive n of one row j
       const int lane = tid & 31, w = tid >> 5;
-      for (int j = w; j < LP; j += 8) {
-        float v = 0.f;
-        if (j < l && n0 + lane < n) v = M[(int64_t)j * ld + n0 + lane];
-        sm[lane][j] = v;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int j = w + 8 * i;
+        nxt[i] = (ch < n_chunks && j < l && n0 + lane < n) ? M[(int64_t)j * ld + n0 + lane] : 0.f;
       }
     } else {
       // time-side: element (n, j) at M[n*ld + j]
-      for (int idx = tid; idx < GR_CHUNK * LP; idx += 256) {
-        const int r = idx / LP, j = idx % LP;
-        float v = 0.f;
-        if (j < l && n0 + r < n) v = M[(n0 + r) * ld + j];
-        sm[r][j] = v;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int idx = tid + 256 * i, r = idx / LP, j = idx % LP;
+        nxt[i] = (ch < n_chunks && j < l && n0 + r < n) ? M[(n0 + r) * ld + j] : 0.f;
+      }
+    }
+  };
+  fetch(blockIdx.x);
+  for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    __syncthreads();  // everyone is done with the previous chunk
+    if (SIDE == 1) {
+      const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) sm[lane][w + 8 * i] = (double)nxt[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int idx = tid + 256 * i;
+        sm[idx / LP][idx % LP] = (double)nxt[i];
       }
     }
     __syncthreads();
-#pragma unroll 4
-    for (int r = 0; r < GR_CHUNK; ++r) {
-      double a[TI], b[TI];
+    fetch(ch + gridDim.x);
+    if (ti >= 0) {
+#pragma unroll 2
+      for (int r = kg; r < GR_CHUNK; r += KG) {
+        double a[TI], b[TI];
 #pragma unroll
-      for (int x = 0; x < TI; ++x) {
-        a[x] = (double)sm[r][ti * TI + x];
-        b[x] = (double)sm[r][tj * TI + x];
+        for (int x = 0; x < TI; ++x) {
+          a[x] = sm[r][ti * TI + x];
+          b[x] = sm[r][tj * TI + x];
+        }
+#pragma unroll
+        for (int x = 0; x < TI; ++x)
+#pragma unroll
+          for (int y = 0; y < TI; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
       }
-#pragma unroll
-      for (int x = 0; x < TI; ++x)
-#pragma unroll
-        for (int y = 0; y < TI; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
     }
-    __syncthreads();
   }
+  if (ti >= 0) {
 #pragma unroll
-  for (int x = 0; x < TI; ++x)
+    for (int x = 0; x < TI; ++x)
 #pragma unroll
-    for (int y = 0; y < TI; ++y) {
-      const int i = ti * TI + x, j = tj * TI + y;
-      if (i < l && j < l) atomicAdd(&G[(int64_t)i * l + j], acc[x][y]);
-    }
+      for (int y = 0; y < TI; ++y) {
+        const int i = ti * TI + x, j = tj * TI + y;
+        if (i < l && j < l) {
+          if (ti != tj || j >= i) atomicAdd(&G[(int64_t)i * l + j], acc[x][y]);
+          if (j > i) atomicAdd(&G[(int64_t)j * l + i], acc[x][y]);
+        }
+      }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -81,19 +118,26 @@ gram_kernel(const float* __restrict__ M, int64_t n, int l, int64_t ld, double* _
 // info[1] = 1 if a NaN/Inf pivot was met (numpy.linalg.LinAlgError at the boundary).
 __global__ void __launch_bounds__(256)
 chol_inv_kernel(const double* __restrict__ G, int l, double* __restrict__ Rinv, int32_t* __restrict__ info) {
-  extern __shared__ double sh[];  // A: l x (l+1), then diag0[l], dead[l] (as doubles)
+  extern __shared__ double sh[];  // A: l x (l+1); diag0[l]; dead[l]; dinv[l]
+  // The upper triangle of A becomes R; the strict lower triangle then receives R^-1 transposed
+  // (Rinv[i][j], i < j, lives at A[j][i]) and dinv its diagonal: the whole factorisation stays in shared memory.
   const int ldA = l + 1;
   double* A = sh;
   double* diag0 = A + (size_t)l * ldA;
   double* dead = diag0 + l;
+  double* dinv = dead + l;
   __shared__ int n_dead, bad;
   const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
   if (tid == 0) { n_dead = 0; bad = 0; }
-  for (int idx = tid; idx < l * l; idx += blockDim.x) A[(idx / l) * ldA + (idx % l)] = G[idx];
+  for (int idx = tid; idx < l * l; idx += blockDim.x) {
+    const int i = idx / l, j = idx - i * l;
+    A[i * ldA + j] = G[idx];
+  }
   __syncthreads();
   for (int i = tid; i < l; i += blockDim.x) { diag0[i] = A[i * ldA + i]; dead[i] = 0.0; }
   __syncthreads();
-  // right-looking upper Cholesky: row k of R, then trailing update A[i][j] -= R[k][i] R[k][j]
+  // right-looking upper Cholesky: row k of R, then trailing update A[i][j] -= R[k][i] R[k][j]  (j >= i > k)
   for (int k = 0; k < l; ++k) {
     const double d = A[k * ldA + k];
     const bool finite = (d == d) && fabs(d) < 1e300;
@@ -105,41 +149,38 @@ chol_inv_kernel(const double* __restrict__ G, int l, double* __restrict__ Rinv, 
       __syncthreads();
       continue;
     }
-    const double rkk = sqrt(d);
-    for (int j = k + tid; j < l; j += blockDim.x) A[k * ldA + j] = (j == k) ? rkk : A[k * ldA + j] / rkk;
+    const double rkk = sqrt(d), rinv = 1.0 / rkk;
+    for (int j = k + tid; j < l; j += blockDim.x) A[k * ldA + j] = (j == k) ? rkk : A[k * ldA + j] * rinv;
     __syncthreads();
-    const int m = l - k - 1;
-    for (int idx = tid; idx < m * m; idx += blockDim.x) {
-      const int i = k + 1 + idx / m, j = k + 1 + idx % m;
-      if (j >= i) A[i * ldA + j] -= A[k * ldA + i] * A[k * ldA + j];
+    for (int i = k + 1 + ty; i < l; i += 16) {
+      const double rki = A[k * ldA + i];
+      for (int j = i + tx; j < l; j += 16) A[i * ldA + j] = fma(-rki, A[k * ldA + j], A[i * ldA + j]);
     }
     __syncthreads();
   }
   if (tid == 0) { info[0] = n_dead; info[1] = bad; }
   // inverse of upper-triangular R, row by row from the bottom:
   //   Rinv[i][i] = 1/R[i][i];  Rinv[i][j] = -(sum_{k=i+1..j} R[i][k] Rinv[k][j]) / R[i][i]   (j > i)
-  // Rinv is kept in global memory (one block; __ldcg/__stcg keep the traffic in L2, coherent after the barrier)
-  for (int idx = tid; idx < l * l; idx += blockDim.x) Rinv[idx] = 0.0;
+  for (int i = tid; i < l; i += blockDim.x) dinv[i] = dead[i] != 0.0 ? 0.0 : 1.0 / A[i * ldA + i];
   __syncthreads();
-  for (int i = l - 1; i >= 0; --i) {
-    const double rii = A[i * ldA + i];
-    for (int j = i + tid; j < l; j += blockDim.x) {
-      double v;
-      if (j == i) {
-        v = dead[i] != 0.0 ? 0.0 : 1.0 / rii;
-      } else {
-        double a0 = 0.0, a1 = 0.0;
-        int k = i + 1;
-        for (; k + 1 <= j; k += 2) {
-          a0 = fma(A[i * ldA + k], __ldcg(&Rinv[k * l + j]), a0);
-          a1 = fma(A[i * ldA + k + 1], __ldcg(&Rinv[(k + 1) * l + j]), a1);
-        }
-        if (k <= j) a0 = fma(A[i * ldA + k], __ldcg(&Rinv[k * l + j]), a0);
-        v = -(a0 + a1) / rii;
+  for (int i = l - 2; i >= 0; --i) {
+    const double ri = 1.0 / A[i * ldA + i];
+    for (int j = i + 1 + tid; j < l; j += blockDim.x) {
+      double a0 = 0.0, a1 = 0.0;
+      int k = i + 1;
+      for (; k + 1 < j; k += 2) {  // Rinv[k][j] (k < j) is stored at A[j][k]
+        a0 = fma(A[i * ldA + k], A[j * ldA + k], a0);
+        a1 = fma(A[i * ldA + k + 1], A[j * ldA + k + 1], a1);
       }
-      __stcg(&Rinv[i * l + j], v);
+      if (k < j) a0 = fma(A[i * ldA + k], A[j * ldA + k], a0);
+      a0 = fma(A[i * ldA + j], dinv[j], a0);
+      A[j * ldA + i] = -(a0 + a1) * ri;
     }
     __syncthreads();
+  }
+  for (int idx = tid; idx < l * l; idx += blockDim.x) {
+    const int i = idx / l, j = idx - i * l;
+    Rinv[idx] = (j > i) ? A[j * ldA + i] : (j == i ? dinv[i] : 0.0);
   }
 }
 
@@ -396,17 +437,14 @@ extern "C" int xeofs_b200_gram(const float* M, int64_t n, int64_t l, int64_t ld,
   XB_CHECK_ARG(side == 0 || side == 1, "gram: side must be 0 (time-side) or 1 (space-side)");
   if (!accumulate) XB_CUDA(cudaMemsetAsync(G, 0, (size_t)l * l * sizeof(double), stream));
   const int64_t chunks = ceil_div(n, GR_CHUNK);
-  const int blocks = (int)imin(chunks, 2 * (int64_t)num_sms());
-  const int ti = l <= 16 ? 1 : l <= 32 ? 2 : l <= 64 ? 4 : 8;
-#define XB_GRAM(TI)                                                                        \
-  if (side == 0) gram_kernel<TI, 0><<<blocks, 256, 0, stream>>>(M, n, (int)l, ld, G);     \
-  else gram_kernel<TI, 1><<<blocks, 256, 0, stream>>>(M, n, (int)l, ld, G)
-  switch (ti) {
-    case 1: XB_GRAM(1); break;
-    case 2: XB_GRAM(2); break;
-    case 4: XB_GRAM(4); break;
-    default: XB_GRAM(8); break;
-  }
+  const int blocks = (int)imin(chunks, (l <= 64 ? 6 : 3) * (int64_t)num_sms());
+#define XB_GRAM(TI, NT, KG)                                                                      \
+  if (side == 0) gram_kernel<TI, NT, KG, 0><<<blocks, 256, 0, stream>>>(M, n, (int)l, ld, G);           \
+  else gram_kernel<TI, NT, KG, 1><<<blocks, 256, 0, stream>>>(M, n, (int)l, ld, G)
+  if (l <= 16) { XB_GRAM(2, 8, 4); }
+  else if (l <= 32) { XB_GRAM(4, 8, 4); }
+  else if (l <= 64) { XB_GRAM(4, 16, 1); }
+  else { XB_GRAM(8, 16, 1); }
 #undef XB_GRAM
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
@@ -415,7 +453,7 @@ extern "C" int xeofs_b200_gram(const float* M, int64_t n, int64_t l, int64_t ld,
 extern "C" int xeofs_b200_chol_inv(const double* G, int64_t l, double* Rinv, int32_t* info, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   XB_CHECK_ARG(G && Rinv && info && l > 0 && l <= 128, "chol_inv: bad arguments (l=%lld must be in 1..128)", (long long)l);
-  const size_t smem = ((size_t)l * (l + 1) + 2 * (size_t)l) * sizeof(double);
+  const size_t smem = ((size_t)l * (l + 1) + 3 * (size_t)l) * sizeof(double);
   XB_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   chol_inv_kernel<<<1, 256, smem, stream>>>(G, (int)l, Rinv, info);
   XB_LAUNCH_CHECK();

@@ -44,9 +44,26 @@ class EOF:
         L.validate_input_type(X)
         if weights is not None:
             L.validate_input_type(weights)
-        ff = self.preprocessor.fit_transform(X, dim, weights)
+        self._predrawn = None
+        ff = self.preprocessor.fit_transform(X, dim, weights, overlap=lambda: self._predraw(X, dim))
         self._fit_algorithm(ff)
         return self
+
+    def _predraw(self, X, dim):
+        """Draw the Gaussian sketch on the host while the statistics pass streams the field (the draw needs the
+        number of samples only as an upper bound: rows of a numpy RandomState draw do not depend on later rows)."""
+        p = self._params
+        k = p["n_modes"]
+        if not isinstance(k, (int, np.integer)) or p["solver"] == "full":
+            return
+        shape = tuple(X.shape)
+        dims = tuple(X.dims)
+        sample = (dim,) if isinstance(dim, str) else tuple(dim)
+        T = int(np.prod([shape[dims.index(d)] for d in sample if d in dims]))
+        S = int(np.prod(shape)) // max(T, 1)
+        l = k + p["solver_kwargs"].get("n_oversamples", 10)
+        if T < S and l <= T and not isinstance(p["random_state"], np.random.RandomState):
+            self._predrawn = E.draw_sketch(p["random_state"], T, l)
 
     def _shard_offset(self, ff):
         if not self.comm.active:
@@ -87,7 +104,8 @@ class EOF:
         else:
             n_over, n_iter = kw.get("n_oversamples", 10), kw.get("n_iter", "auto")
         Ur, s, Vc, infos = E.randomized_svd(ops, op, k, n_oversamples=n_over, n_iter=n_iter,
-                                            random_state=p["random_state"], comm=comm)
+                                            random_state=p["random_state"], comm=comm,
+                                            predrawn=getattr(self, "_predrawn", None))
         E.check_infos(infos)
         # un-transpose: A = U s V^T with V on the space side
         Vt, Ut = (Ur, Vc) if op.transposed else (Vc, Ur)
