@@ -100,6 +100,18 @@ int xeofs_b200_project_T(const float* X, int64_t T, int64_t S, int64_t ldx, cons
                          float* Z, int64_t ldz, void* workspace, int64_t workspace_bytes, int algo,
                          void* stream);
 
+/* ---- P1/P4/P5 + D2 fused: statistics and the first product of the range finder from ONE read of X --------------
+ * What col_stats + scaling_finalize + project_S(TF32X1) give, for the case where M = A^T comes first (n_samples <
+ * n_features): the first sample of each feature is the shift of the sums and the pivot of this pass, the Scaler
+ * vectors are derived in the epilogue of the CTA that owns the feature and applied to its block of Yt.
+ * Every sample is taken as present: if row_nan then names samples that are NaN throughout, Yt's rank-1 term is off
+ * for un-centred data and the sketch rows do not line up with the reference's compacted matrix — redo project_S.
+ * Returns XEOFS_E_UNSUPPORTED where the tcgen05 path does not apply (use the three separate calls).               */
+int xeofs_b200_project_S_stats(const float* X, int64_t T, int64_t S, int64_t ldx, const double* featw, int flags,
+                               const float* W, int64_t ldw, int64_t l, float* mean, float* std, uint8_t* valid,
+                               float* pivot, float* dscale, float* ccorr, double* scalars_out, int32_t* row_nan,
+                               float* Yt, int64_t ldy, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* In place: every value of the (rows x cols, leading dimension ld) matrix keeps only the bits a TF32 operand has
  * (the low 13 mantissa bits are cleared), so that TF32X2 products with it as the small operand are exact.        */
 int xeofs_b200_round_tf32(float* M, int64_t rows, int64_t cols, int64_t ld, void* stream);

@@ -61,15 +61,19 @@ def test_planted_config1_shape():
     _compare(o, m, k)
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(standardize=True, use_coslat=True)])
-def test_planted_wide_with_land_mask(kw):
-    """T < S (sklearn transposes), n_iter=4 as in configs[1], 10 % of the columns all-NaN (Sanitizer)."""
+@pytest.mark.parametrize("missing_sample", [True, False])
+@pytest.mark.parametrize("kw", [dict(), dict(standardize=True, use_coslat=True), dict(center=False)])
+def test_planted_wide_with_land_mask(kw, missing_sample):
+    """T < S (sklearn transposes), n_iter=4 as in configs[1], 10 % of the columns all-NaN (Sanitizer).  Without a
+    missing sample the statistics and the first product come from one fused pass; with one the fit falls back to the
+    separate passes."""
     T, nlat, nlon, k = 600, 40, 90, 12
     X = planted(T, nlat * nlon, 2 * k, seed=1).reshape(T, nlat, nlon)
     rng = np.random.default_rng(9)
     land = rng.random((nlat, nlon)) < 0.1
     X[:, land] = np.nan
-    X[17] = np.nan  # a fully missing sample is dropped too
+    if missing_sample:
+        X[17] = np.nan  # a fully missing sample is dropped too
     coords = {"lat": np.linspace(88, -88, nlat), "lon": np.arange(nlon) * 4.0}
     o, m = _fit_both(X, coords, k, random_state=5, solver_kwargs={"n_iter": 4}, **kw)
     _compare(o, m, k)

@@ -222,3 +222,46 @@ def test_project_tcgen05(T, S, l, center, algo, tol):
     if algo != "simt":  # the SIMT validation kernels combine their split sums with atomics
         Z2 = ops.project_T(f, Yd, l, algo=a).cpu().numpy()
         np.testing.assert_array_equal(Z, Z2)
+
+
+@pytest.mark.parametrize("T,S,l", [(300, 1000, 20), (1000, 4096, 60), (8760, 2500, 60), (200, 70000, 40), (90, 132, 5)])
+@pytest.mark.parametrize("center,standardize", [(True, False), (True, True), (False, True)])
+def test_fused_stats_and_first_product(T, S, l, center, standardize):
+    """xeofs_b200_project_S_stats (one read of X) against col_stats + scaling_finalize + project_S: the Scaler vectors,
+    the masks, total variance, per-sample NaN counts, and A^T W to single-TF32 accuracy.  NaN features (a land mask)
+    but every sample present — the case the fused pass is for."""
+    from xeofs_b200 import _lib
+    from xeofs_b200._cuda_ops import CudaOps, Field
+    from xeofs_b200._lib import lpad
+    ops = CudaOps(algo="auto")
+    rng = np.random.default_rng(T + S + l)
+    X = (280 + 3 * rng.standard_normal((T, S))).astype(np.float32)
+    X[:, rng.random(S) < 0.1] = np.nan
+    X[:, 0] = np.nan
+    featw = rng.uniform(0.5, 1.5, S)
+    lp = lpad(l)
+    W = np.zeros((T, lp), np.float32)
+    W[:, :l] = rng.standard_normal((T, l))
+    Xd = ops.space_side(T, S)
+    Xd.copy_(torch.from_numpy(X))
+    fw = torch.as_tensor(featw, dtype=torch.float64).cuda()
+    Wd = torch.from_numpy(W).cuda()
+    fused = ops.stats_project_S(Xd, fw, center, standardize, Wd, l)
+    assert fused is not None
+    row_nan, fin, Yt = fused
+    st = ops.col_stats(Xd)
+    ref = ops.scaling_finalize(st, fw, center, standardize)
+    np.testing.assert_array_equal(row_nan.cpu().numpy(), st["row_nan"].cpu().numpy())
+    np.testing.assert_array_equal(fin["valid"].cpu().numpy(), ref["valid"].cpu().numpy())
+    v = ref["valid"].cpu().numpy().astype(bool)
+    for key, tol in (("mean", 3e-7), ("std", 2e-5), ("pivot", 3e-7), ("dscale", 2e-5)):
+        np.testing.assert_allclose(fin[key].cpu().numpy()[v], ref[key].cpu().numpy()[v], rtol=tol, err_msg=key)
+    assert np.isnan(fin["mean"].cpu().numpy()[~v]).all() and (fin["dscale"].cpu().numpy()[~v] == 0).all()
+    sc, sr = fin["scalars"].cpu().numpy(), ref["scalars"].cpu().numpy()
+    np.testing.assert_allclose(sc[0], sr[0], rtol=1e-5)
+    np.testing.assert_array_equal(sc[1:], sr[1:])
+    A = np.nan_to_num(_A_ref(X, featw, center, standardize), nan=0.0)
+    want = (A.T @ W[:, :l].astype(np.float64)).T
+    got = Yt.cpu().numpy()
+    np.testing.assert_allclose(got[:l], want, atol=3e-3 * np.abs(want).max())
+    assert (got[l:] == 0).all() and (got[:, ~v] == 0).all()

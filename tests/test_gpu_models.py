@@ -122,3 +122,64 @@ def test_eof_large_a_posteriori_properties():
     assert evr.sum() <= 1.0 + 1e-6 and (np.diff(evr) <= 1e-9).all()
     # the planted spectrum, seen through the coslat weights, bounds the leading value
     assert 0.3 * 1e5 < float(s[0]) < 1.01 * 1e5
+
+
+_DIST_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+root = sys.argv[1]
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests", "golden"))
+from _inputs import planted
+import xeofs_b200 as xb
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device(f"cuda:{rank}"))
+T, nlat, nlon, k = 700, 48, 96, 10
+X = planted(T, nlat * nlon, 2 * k, seed=12).reshape(T, nlat, nlon)
+X[:, 5, 7] = np.nan; X[:, 40, 3] = np.nan
+lat = np.linspace(88, -88, nlat)
+rows = slice(rank * nlat // world, (rank + 1) * nlat // world)
+coords = {"lat": lat[rows], "lon": np.arange(nlon) * 3.75}
+m = xb.single.EOF(n_modes=k, use_coslat=True, standardize=True, random_state=7, solver_kwargs={"n_iter": 4}, distributed=True)
+m.fit(xb.DataArray(X[:, rows], ("time", "lat", "lon"), coords), dim="time")
+r = xb.single.EOFRotator(n_modes=6).fit(m)
+np.savez(os.path.join(sys.argv[2], f"rank{rank}.npz"), s=m.singular_values().values, comps=m.components().values,
+         scores=m.scores().values, evr=m.explained_variance_ratio().values, rot_ev=r.explained_variance().values,
+         collectives=m.comm.collectives)
+dist.destroy_process_group()
+'''
+
+
+def test_feature_sharded_fit_two_gpus(tmp_path):
+    """§8e on real devices: the feature axis split over 2 GPUs (NCCL allreduce of the projected blocks / Gram
+    matrices) must reproduce the oracle like the single-GPU fit does."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(_DIST_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29741", str(script), root, str(tmp_path)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    T, nlat, nlon, k = 700, 48, 96, 10
+    X = planted(T, nlat * nlon, 2 * k, seed=12).reshape(T, nlat, nlon)
+    X[:, 5, 7] = np.nan
+    X[:, 40, 3] = np.nan
+    coords = {"lat": np.linspace(88, -88, nlat), "lon": np.arange(nlon) * 3.75}
+    o = oeof.eof_fit(X, DIMS, "time", coords=coords, n_modes=k, use_coslat=True, standardize=True, random_state=7,
+                     solver_kwargs={"n_iter": 4})
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    assert int(r0["collectives"]) > 0
+    for r in (r0, r1):
+        np.testing.assert_allclose(r["s"], o["singular_values"], rtol=1e-4)
+        np.testing.assert_allclose(r["evr"], o["explained_variance_ratio"], rtol=1e-4)
+    comps = np.concatenate([r0["comps"], r1["comps"]], axis=0).reshape(-1, k)
+    vf = o["fitted"]["is_valid_feature"]
+    dots = (comps[vf] * o["components_2d"]).sum(axis=0)
+    assert (dots >= 1 - 1e-4).all(), dots
+    ro = orot.eof_rotator_fit(o["components_2d"], o["explained_variance"], o["scores"], o["norms"], o["A"].shape[0], n_modes=6)
+    np.testing.assert_allclose(r0["rot_ev"], ro["explained_variance"], rtol=1e-4)

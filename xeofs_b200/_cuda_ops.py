@@ -126,14 +126,39 @@ class CudaOps:
         self.launches += 2
         return out
 
+    def stats_project_S(self, X, featw, center, standardize, W, l):
+        """col_stats + scaling_finalize + project_S(single TF32) from one read of X.  Returns (row_nan, fin, Yt) or
+        None where the fused kernel does not apply."""
+        T, S = int(X.shape[0]), int(X.shape[1])
+        ldx = int(X.stride(0))
+        if not (self.algo in (_lib.ALGO_AUTO_FAST, _lib.ALGO_TF32X1) and ldx % 4 == 0 and X.data_ptr() % 16 == 0
+                and bool(self.lib.xeofs_b200_has_tcgen05())):
+            return None
+        out = {
+            "mean": self.empty(S), "std": self.empty(S), "valid": self.empty(S, torch.uint8),
+            "pivot": self.empty(S), "dscale": self.empty(S), "ccorr": self.empty(S),
+            "scalars": self.empty(4, torch.float64),
+        }
+        row_nan = self.empty(T, torch.int32)
+        lp = lpad(l)
+        Yt = self.space_side(lp, S)
+        ws = self.workspace(T, S, l, _lib.ALGO_TF32X1)
+        flags = (_lib.F_CENTER if center else 0) | (_lib.F_STANDARDIZE if standardize else 0)
+        check(self._timed("project_S_stats", l, lambda: self.lib.xeofs_b200_project_S_stats(
+            ptr(X), T, S, ldx, ptr(featw), flags, ptr(W), int(W.stride(0)), l, ptr(out["mean"]), ptr(out["std"]),
+            ptr(out["valid"]), ptr(out["pivot"]), ptr(out["dscale"]), ptr(out["ccorr"]), ptr(out["scalars"]),
+            ptr(row_nan), ptr(Yt), int(Yt.stride(0)), ptr(ws), ws.numel(), self._stream())), "project_S_stats")
+        self.launches += 5
+        return row_nan, out, Yt
+
     # ------------------------------------------------------------------ streaming products
-    def project_S(self, f: Field, W, l, algo=None, out=None):
+    def project_S(self, f: Field, W, l, algo=None, out=None, tag="project_S"):
         """Yt (lp x S) = A^T W,  W time-side (T x lp)."""
         algo = self.algo if algo is None else algo
         lp = lpad(l)
         Yt = out if out is not None else self.space_side(lp, f.S)
         ws = self.workspace(f.T, f.S, l, algo)
-        check(self._timed("project_S", l, lambda: self.lib.xeofs_b200_project_S(
+        check(self._timed(tag, l, lambda: self.lib.xeofs_b200_project_S(
             ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr), ptr(f.row_valid), ptr(W),
             int(W.stride(0)), l,
             ptr(Yt), int(Yt.stride(0)), ptr(ws), ws.numel(), algo, self._stream())), "project_S")
@@ -194,7 +219,7 @@ class CudaOps:
             f = Field(In[:l, :n], zero, one, None, None)
             if out is None:
                 out = self.space_side(kp, n)
-            return self.project_S(f, W, k, algo=_lib.ALGO_TF32X3, out=out)
+            return self.project_S(f, W, k, algo=_lib.ALGO_TF32X3, out=out, tag="apply_S")
         if out is None:
             out = self.space_side(kp, n) if side == 1 else self.zeros((n, kp))
         check(self.lib.xeofs_b200_apply(ptr(In), n, l, int(In.stride(0)), side, ptr(Mat), int(Mat.stride(0)), k,

@@ -69,26 +69,37 @@ class FittedField:
         self.n_samples = 0           # T' (samples kept)
         self.n_features = 0          # S' (features kept, global over ranks)
         self.total_variance = 0.0
+        self.first_product = None    # A^T W of the fused statistics pass (space-side) or None
+        self.first_l = None
         self.T = self.S = 0          # local shape
         self.S_global = 0
         self.center = self.standardize = False
 
 
-def fit_field(ops, X, featw=None, center=True, standardize=False, check_nans=True, comm=NO_COMM, overlap=None):
+def fit_field(ops, X, featw=None, center=True, standardize=False, check_nans=True, comm=NO_COMM, overlap=None,
+              first=None):
     """One streaming pass of column statistics + the Scaler vectors (scaler.py:100-153), the Sanitizer
     masks and its isolated-NaN check (sanitizer.py:46-56, 108-122), total variance (utils/xarray_utils.py:236-253).
 
     X: (T, S_local) fp32 CUDA tensor (row stride arbitrary), featw: (S_local,) fp64 CUDA tensor or None.
     ``overlap``: host work to run while the statistics pass is in flight (before the one host sync).
+    ``first``: (W, l) — the time-side sketch of the range finder: where the fused kernel applies, the statistics and
+    the first product A^T W come from the same read of X (``ff.first_product``, valid if every sample is present).
     """
     from ._cuda_ops import Field
 
     T, S = int(X.shape[0]), int(X.shape[1])
-    st = ops.col_stats(X)
-    fin = ops.scaling_finalize(st, featw, center, standardize)
+    fused = ops.stats_project_S(X, featw, center, standardize, *first) if (
+        first is not None and hasattr(ops, "stats_project_S")) else None
+    if fused is not None:
+        row_nan32, fin, first_product = fused
+    else:
+        st = ops.col_stats(X)
+        fin = ops.scaling_finalize(st, featw, center, standardize)
+        row_nan32, first_product = st["row_nan"], None
     # scalars: total variance, number of valid features, max / min non-NaN count over valid features
     sc = fin["scalars"].clone()
-    row_nan = st["row_nan"].to(torch.int64)
+    row_nan = row_nan32.to(torch.int64)
     S_global = S
     if comm.active:
         head = torch.cat([sc[:2], torch.tensor([float(S)], dtype=torch.float64, device=sc.device)])
@@ -130,6 +141,9 @@ def fit_field(ops, X, featw=None, center=True, standardize=False, check_nans=Tru
     ff.total_variance = total_variance
     ff.T, ff.S, ff.S_global = T, S, S_global
     ff.center, ff.standardize = center, standardize
+    # the fused first product took every sample as present and l as given
+    ff.first_product = first_product if (first_product is not None and n_samples == T) else None
+    ff.first_l = first[1] if first is not None else None
     return ff
 
 
@@ -291,7 +305,7 @@ def sketch_matrix(ops, op, l, random_state, comm=NO_COMM, predrawn=None):
 
 
 def randomized_svd(ops, op, k, n_oversamples=10, n_iter="auto", random_state=None, comm=NO_COMM, Omega=None,
-                   predrawn=None):
+                   predrawn=None, first_product=None):
     """Halko et al. range finder + small SVD, the arithmetic of sklearn.utils.extmath.randomized_svd
     (power_iteration_normalizer='auto', transpose='auto') with CholeskyQR as the normalizer.
 
@@ -311,8 +325,10 @@ def randomized_svd(ops, op, k, n_oversamples=10, n_iter="auto", random_state=Non
         Q = sketch_matrix(ops, op, l, random_state, comm, predrawn)
     else:
         Q = Omega
-    for _ in range(int(n_iter)):
-        Q = orthonormalize(ops, op.mul(Q, l), op.r, l, comm, 1, infos)
+    for it in range(int(n_iter)):
+        # M @ Omega may already exist: the statistics pass computed it from the same read of the field
+        Y = first_product if (it == 0 and first_product is not None) else op.mul(Q, l)
+        Q = orthonormalize(ops, Y, op.r, l, comm, 1, infos)
         Q = orthonormalize(ops, op.mul_t(Q, l), op.c, l, comm, 1, infos)
     # The last two passes decide the singular values and run at fp32 accuracy.  For the first of them the small
     # operand can be made TF32-exact beforehand — rounding the current iterate is harmless, any nearby iterate serves

@@ -32,6 +32,8 @@ SIGNATURES = {
     "xeofs_b200_project_workspace_bytes": (_i64, [_i64, _i64, _i64, _int]),
     "xeofs_b200_project_S": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _int, _p]),
     "xeofs_b200_project_T": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _int, _p]),
+    "xeofs_b200_project_S_stats": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                          _i64, _p, _i64, _p]),
     "xeofs_b200_round_tf32": (_int, [_p, _i64, _i64, _i64, _p]),
     "xeofs_b200_gram": (_int, [_p, _i64, _i64, _i64, _int, _p, _int, _p]),
     "xeofs_b200_chol_inv": (_int, [_p, _i64, _p, _p, _p]),

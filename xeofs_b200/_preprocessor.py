@@ -52,7 +52,8 @@ class Preprocessor:
         return t2, sample_shape, feature_shape
 
     # ------------------------------------------------------------------ fit
-    def fit_transform(self, X, sample_dims, weights=None, overlap=None):
+    def fit_transform(self, X, sample_dims, weights=None, overlap=None, first=None):
+        """``first``: callable (T, S) -> (W, l) or None, the sketch for the fused statistics + first product pass."""
         data, dims, coords, self.as_xarray = L.unpack(X)
         self._dim = sample_dims
         X2, self.sample_shape, self.feature_shape = self._to_2d(data, dims, fit=True)
@@ -77,7 +78,8 @@ class Preprocessor:
         self.featw_host = None if featw is None else np.ascontiguousarray(featw.reshape(-1))
         featw_dev = None if featw is None else self.ops.to_device(self.featw_host, torch.float64)
         self.fitted = fit_field(self.ops, X2, featw_dev, center=self.with_center, standardize=self.with_std,
-                                check_nans=self.check_nans, comm=self.comm, overlap=overlap)
+                                check_nans=self.check_nans, comm=self.comm, overlap=overlap,
+                                first=first(int(X2.shape[0]), int(X2.shape[1])) if first is not None else None)
         return self.fitted
 
     # ------------------------------------------------------------------ transform of unseen data

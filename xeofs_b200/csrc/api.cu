@@ -41,6 +41,8 @@ int project_S_tc(const float*, int64_t, int64_t, int64_t, const float*, const fl
 int project_T_tc(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const uint8_t*,
                  const float*, int64_t, int64_t, float*, int64_t, void*, int64_t, int, cudaStream_t);
 
+int project_S_stats_tc(const float*, int64_t, int64_t, int64_t, const double*, int, const float*, int64_t, int64_t, float*,
+                       float*, uint8_t*, float*, float*, float*, double*, int32_t*, float*, int64_t, void*, cudaStream_t);
 }  // namespace xb
 
 using namespace xb;
@@ -142,4 +144,25 @@ extern "C" int xeofs_b200_project_T(const float* X, int64_t T, int64_t S, int64_
     return XEOFS_E_UNSUPPORTED;
   }
   return project_T_tc(X, T, S, ldx, pivot, dscale, ccorr, row_valid, Yt, ldy, l, Z, ldz, workspace, workspace_bytes, algo, stream);
+}
+
+extern "C" int xeofs_b200_project_S_stats(const float* X, int64_t T, int64_t S, int64_t ldx, const double* featw, int flags,
+                                          const float* W, int64_t ldw, int64_t l, float* mean, float* std, uint8_t* valid,
+                                          float* pivot, float* dscale, float* ccorr, double* scalars_out, int32_t* row_nan,
+                                          float* Yt, int64_t ldy, void* workspace, int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(X && W && mean && std && valid && pivot && dscale && ccorr && scalars_out && row_nan && Yt && workspace,
+               "project_S_stats: null pointer");
+  XB_CHECK_ARG(T > 0 && S > 0 && ldx >= S && l > 0 && l <= 128 && ldw >= lpad(l) && ldy >= S && ldw % 4 == 0,
+               "project_S_stats: bad shape");
+  if (workspace_bytes < xeofs_b200_project_workspace_bytes(T, S, l, XEOFS_ALGO_TF32X1)) {
+    set_error("project_S_stats: workspace too small");
+    return XEOFS_E_WORKSPACE;
+  }
+  if (!xeofs_b200_has_tcgen05() || !tc_supported(T, S, ldx, X, l)) {
+    set_error("project_S_stats: needs the tcgen05 path (sm_100, 16-byte aligned X, ldx %% 4 == 0)");
+    return XEOFS_E_UNSUPPORTED;
+  }
+  return project_S_stats_tc(X, T, S, ldx, featw, flags, W, ldw, l, mean, std, valid, pivot, dscale, ccorr, scalars_out,
+                            row_nan, Yt, ldy, workspace, stream);
 }

@@ -209,6 +209,18 @@ struct TcParams {
   const float* ccorr;   // project_S epilogue (may be null)
   const float* wsum;    // project_S epilogue: column sums of W [lp]
   const uint8_t* chunk_flags;  // project_S: [K-chunk] 1 if the 32 samples hold one that is NaN throughout (null: none)
+  // fused statistics (project_S_stats): Scaler.fit / Sanitizer masks / total variance from the same read of X
+  const double* featw;   // [S] coslat * weights (null = 1)
+  int stat_flags;        // XEOFS_F_CENTER | XEOFS_F_STANDARDIZE
+  float* mean_out;       // [S]
+  float* std_out;        // [S]
+  uint8_t* valid_out;    // [S]
+  float* pivot_out;      // [S] what later passes subtract (mean when centring, else the first sample)
+  float* dscale_out;     // [S]
+  float* ccorr_out;      // [S]
+  double* scalars_out;   // [4] total variance, valid features, max / min count (pre-initialised)
+  int32_t* row_delta;    // [T] NaN count of each sample minus that of the first sample (zero-initialised)
+  int32_t* base_nan;     // [1] NaN count of the first sample (zero-initialised)
   float* out;           // project_S: Yt (ldo = ldy);  project_T: partial sums [split][tiles*128][lp]
   int64_t ldo;
   uint32_t tmem_cols;
@@ -229,11 +241,12 @@ struct Pipe {
 // ------------------------------------------------------------------------------------------------ the kernel
 // NS: 1 = single TF32 product, 3 = 3xTF32.  SIDE_T: false = project_S, true = project_T.
 // KB: 32-wide K slabs per pipeline stage (project_T reads KB*128 contiguous bytes of every row per TMA box).
-template <int NS, bool SIDE_T, int KB>
+template <int NS, bool SIDE_T, int KB, bool STATS = false>
 __global__ void __launch_bounds__(tc_threads(NS), (NS == 1 && !SIDE_T) ? 2 : 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBhi,
                   const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
   static_assert(SIDE_T || KB == 1, "project_S stages are 32 rows of t");
+  static_assert(!STATS || (NS == 1 && !SIDE_T), "the statistics ride on the first (single TF32) project_S pass");
   constexpr int NPART = NS >= 2 ? 2 : 1;            // parts of the big operand kept per value (hi | lo)
   constexpr int BPART = NS == 3 ? 2 : 1;            // parts of the small operand (NS == 2: it is TF32-exact already)
   constexpr int NW = tc_nw(NS);                     // operand-stage warps per TMEM lane quarter
@@ -364,7 +377,20 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const int row = q * 32 + lane;      // row of D / TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float piv = 0.f;
-    if (!SIDE_T) piv = (tile0 + row < p.S) ? p.pivot[tile0 + row] : 0.f;
+    if (!SIDE_T && !STATS) piv = (tile0 + row < p.S) ? p.pivot[tile0 + row] : 0.f;
+    // fused statistics: the first sample is the shift of the sums and the pivot of this pass
+    bool n0 = false;           // the first sample of this feature is NaN
+    double sum1 = 0.0, sum2 = 0.0;
+    int cnt = 0;
+    if (STATS) {
+      const float x0 = (tile0 + row < p.S) ? p.X[tile0 + row] : 0.f;
+      n0 = !(x0 == x0);
+      piv = n0 ? 0.f : x0;
+      if (part == 0) {
+        const unsigned b0 = __ballot_sync(0xffffffffu, n0);
+        if (lane == 0 && b0) atomicAdd(p.base_nan, __popc(b0));
+      }
+    }
 
     constexpr int ACCN = NS >= 2 ? 128 / NW : 1;
     const int cw = lp / NW;      // accumulator columns of this warp: [part*cw, +cw)
@@ -413,7 +439,49 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           float v[KW];
 #pragma unroll
           for (int r = 0; r < KW; ++r) v[r] = lds32(src + r * TC_TILE * 4) - piv;
-          if (check) {
+          if (STATS) {
+            // sums of (x - shift), (x - shift)^2 and the count over the samples of this stage (fp32 within the
+            // stage, fp64 across stages).  A feature without NaN in the stage — seen from the sum itself — takes the
+            // short road; the per-value tests run only for NaN features, the ragged last stage and NaN first samples.
+            const int64_t t0 = (int64_t)c * TC_KC + part * KW;
+            const bool ragged = (c == nchunks - 1) && (p.T & (TC_KC - 1));
+            float s1 = 0.f, s2 = 0.f;
+            int cn = KW;
+            uint32_t devmask = 0;  // samples whose NaN flag differs from the first sample's
+#pragma unroll
+            for (int r = 0; r < KW; ++r) s1 += v[r];
+            if (!ragged && !n0 && fabsf(s1) <= 3.4028234e38f) {
+#pragma unroll
+              for (int r = 0; r < KW; ++r) s2 = fmaf(v[r], v[r], s2);
+            } else {
+              s1 = 0.f;
+              cn = 0;
+#pragma unroll
+              for (int r = 0; r < KW; ++r) {
+                const bool live = !ragged || t0 + r < p.T;
+                const bool ok = v[r] == v[r];
+                const float dz = (ok && live) ? v[r] : 0.f;
+                s1 += dz;
+                s2 = fmaf(dz, dz, s2);
+                cn += (ok && live) ? 1 : 0;
+                v[r] = dz;
+                if (live && ((!ok) != n0) && (tile0 + row < p.S)) devmask |= 1u << r;
+              }
+            }
+            if (__any_sync(0xffffffffu, devmask != 0)) {
+#pragma unroll
+              for (int r = 0; r < KW; ++r) {
+                const unsigned dev = __ballot_sync(0xffffffffu, (devmask >> r) & 1);
+                if (dev) {
+                  const unsigned pos = __ballot_sync(0xffffffffu, ((devmask >> r) & 1) && !n0);
+                  if (lane == 0) atomicAdd(&p.row_delta[t0 + r], 2 * __popc(pos) - __popc(dev));
+                }
+              }
+            }
+            sum1 += (double)s1;
+            sum2 += (double)s2;
+            cnt += cn;
+          } else if (check) {
 #pragma unroll
             for (int r = 0; r < KW; ++r) v[r] = (v[r] == v[r]) ? v[r] : 0.f;
           }
@@ -471,7 +539,60 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const int64_t rrow = tile0 + row;  // s (project_S) or t (project_T)
     const bool ok = SIDE_T ? true : rrow < p.S;
     float ds = 0.f, cs = 0.f;
-    if (!SIDE_T && ok) {
+    if (STATS) {
+      // the NW warps of a lane quarter each saw a share of the samples: combine, then every thread derives the
+      // Scaler vectors of its feature (scaling_finalize_kernel's arithmetic, stats.cu)
+      __shared__ double comb1[2][TC_TILE], comb2[2][TC_TILE];
+      __shared__ int combn[2][TC_TILE];
+      comb1[part][row] = sum1;
+      comb2[part][row] = sum2;
+      combn[part][row] = cnt;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const double t1 = comb1[0][row] + comb1[1][row], t2 = comb2[0][row] + comb2[1][row];
+      const int n = combn[0][row] + combn[1][row];
+      const bool center = p.stat_flags & XEOFS_F_CENTER, standardize = p.stat_flags & XEOFS_F_STANDARDIZE;
+      const bool val = ok && n > 0;
+      double mu = 0.0, m2 = 0.0;
+      if (val) {
+        const double a = t1 / n;
+        mu = (double)piv + a;
+        m2 = t2 - t1 * a;
+        if (m2 < 0) m2 = 0;
+      }
+      const float mu32 = (float)mu;
+      const float sd = val ? fmaxf((float)sqrt(m2 / (n > 0 ? n : 1)), 1.1920929e-07f) : nanf("");
+      double d = val ? (p.featw ? p.featw[rrow] : 1.0) : 0.0;
+      if (standardize && val) d /= (double)sd;
+      const float d32 = (float)d;
+      const float mu_eff = center ? mu32 : 0.f;
+      ds = d32;
+      cs = val ? (piv - mu_eff) * d32 : 0.f;   // A = (x - shift) d + (shift - mean_eff) d
+      double tv = (val && n > 1) ? (double)d32 * (double)d32 * m2 / (double)(n - 1) : 0.0;
+      int nv = val ? 1 : 0, cmax = val ? n : 0, cmin = val ? n : 0x7fffffff;
+      if (part == 0 && ok) {
+        const float newpiv = val ? (center ? mu32 : piv) : 0.f;
+        p.mean_out[rrow] = val ? mu32 : nanf("");
+        p.std_out[rrow] = sd;
+        p.valid_out[rrow] = val ? 1 : 0;
+        p.pivot_out[rrow] = newpiv;
+        p.dscale_out[rrow] = d32;
+        p.ccorr_out[rrow] = val ? (newpiv - mu_eff) * d32 : 0.f;
+      }
+      if (part != 0) { tv = 0.0; nv = 0; cmax = 0; cmin = 0x7fffffff; }
+      tv = warp_sum(tv);
+      nv = warp_sum(nv);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+        cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+      }
+      if (part == 0 && lane == 0) {
+        atomicAdd(&p.scalars_out[0], tv);
+        atomicAdd(&p.scalars_out[1], (double)nv);
+        atomicMax((unsigned long long*)&p.scalars_out[2], (unsigned long long)__double_as_longlong((double)cmax));
+        atomicMin((unsigned long long*)&p.scalars_out[3], (unsigned long long)__double_as_longlong((double)cmin));
+      }
+    } else if (!SIDE_T && ok) {
       ds = p.dscale[rrow];
       cs = p.ccorr ? p.ccorr[rrow] : 0.f;
     }
@@ -721,7 +842,8 @@ int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo) {
   const bool x3 = is_x3(algo);
   const int64_t Tpad = round_up(T, TC_KC);
   // project_S: wsum | chunk flags | W image hi | W image lo
-  const int64_t bs = align256(lp * 4) + align256(Tpad / TC_KC) + (x3 ? 2 : 1) * align256(lp * Tpad * 4);
+  const int64_t bs = align256(lp * 4) + align256(Tpad / TC_KC) + (x3 ? 2 : 1) * align256(lp * Tpad * 4) +
+                     align256((round_up(T, 64) + 64) * 4);  // + row_delta | base_nan of the fused statistics pass
   // project_T: rvec | pivot_pad | dscale_pad | partials | Y image hi | Y image lo
   // (the finest split has the largest partial buffer)
   int64_t part = 0;
@@ -789,6 +911,67 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   return ns == 3   ? launch_tc<3, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
          : ns == 2 ? launch_tc<2, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
                    : launch_tc<1, false, 1>(mx, mh, ml, p, grid, sh.smem, stream);
+}
+
+__global__ void stats_init_kernel(double* scalars, int32_t* row_delta, int64_t T, int32_t* base_nan) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < T) row_delta[i] = 0;
+  if (i == 0) {
+    scalars[0] = 0.0; scalars[1] = 0.0; scalars[2] = 0.0; scalars[3] = 2147483647.0;
+    *base_nan = 0;
+  }
+}
+__global__ void row_nan_kernel(const int32_t* __restrict__ row_delta, const int32_t* __restrict__ base_nan, int64_t T,
+                               int32_t* __restrict__ row_nan) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < T) row_nan[i] = *base_nan + row_delta[i];
+}
+
+// Statistics + first product in one read of X (every sample taken as present: the caller re-does the product if the
+// statistics then name samples that are NaN throughout).
+int project_S_stats_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const double* featw, int flags, const float* W,
+                       int64_t ldw, int64_t l, float* mean, float* stdv, uint8_t* valid, float* pivot, float* dscale,
+                       float* ccorr, double* scalars, int32_t* row_nan, float* Yt, int64_t ldy, void* workspace,
+                       cudaStream_t stream) {
+  const int lp = (int)lpad(l);
+  const int64_t Tpad = round_up(T, TC_KC);
+  uint8_t* ws = (uint8_t*)workspace;
+  float* wsum = (float*)ws;
+  uint8_t* flags_unused = ws + align256(lp * 4);
+  float* Whi = (float*)(flags_unused + align256(Tpad / TC_KC));
+  // row_delta | base_nan live behind the operand image
+  int32_t* row_delta = (int32_t*)((uint8_t*)Whi + align256(lp * Tpad * 4));
+  int32_t* base_nan = row_delta + round_up(T, 64);
+  int rc = launch_colsum(W, T, ldw, lp, nullptr, wsum, stream);
+  if (rc) return rc;
+  prep_W_kernel<<<(unsigned)(Tpad / TC_KC), 256, 0, stream>>>(W, T, ldw, lp, Whi, nullptr);
+  XB_LAUNCH_CHECK();
+  stats_init_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, stream>>>(scalars, row_delta, T, base_nan);
+  XB_LAUNCH_CHECK();
+  CUtensorMap mx, mh;
+  rc = make_map2(&mx, X, S, T, ldx, TC_TILE, TC_KC, false);
+  if (rc) return rc;
+  rc = make_map2(&mh, Whi, 256, (Tpad / TC_KC) * (lp / 8), 256, 256, lp / 8, false);
+  if (rc) return rc;
+  const Shape sh = pick_shape(lp, 1, false, 1);
+  TcParams p{};
+  p.T = T; p.S = S; p.lp = lp;
+  p.stages = sh.stages; p.dcols = sh.dcols; p.tmem_cols = sh.tmem_cols;
+  p.nchunks_total = (int)(Tpad / TC_KC);
+  p.chunks_per_cta = p.nchunks_total;
+  p.wsum = wsum;
+  p.out = Yt; p.ldo = ldy;
+  p.X = X; p.ldx = ldx; p.bimg_hi = Whi;
+  p.featw = featw; p.stat_flags = flags;
+  p.mean_out = mean; p.std_out = stdv; p.valid_out = valid; p.pivot_out = pivot; p.dscale_out = dscale; p.ccorr_out = ccorr;
+  p.scalars_out = scalars; p.row_delta = row_delta; p.base_nan = base_nan;
+  dim3 grid((unsigned)ceil_div(S, TC_TILE));
+  XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<1, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
+  project_tc_kernel<1, false, 1, true><<<grid, tc_threads(1), sh.smem, stream>>>(mx, mh, mh, p);
+  XB_LAUNCH_CHECK();
+  row_nan_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, stream>>>(row_delta, base_nan, T, row_nan);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
 }
 
 int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot, const float* dscale,

@@ -45,25 +45,39 @@ class EOF:
         if weights is not None:
             L.validate_input_type(weights)
         self._predrawn = None
-        ff = self.preprocessor.fit_transform(X, dim, weights, overlap=lambda: self._predraw(X, dim))
+        ff = self.preprocessor.fit_transform(X, dim, weights, first=self._first_sketch)
         self._fit_algorithm(ff)
         return self
 
-    def _predraw(self, X, dim):
-        """Draw the Gaussian sketch on the host while the statistics pass streams the field (the draw needs the
-        number of samples only as an upper bound: rows of a numpy RandomState draw do not depend on later rows)."""
+    def _first_sketch(self, T, S):
+        """The Gaussian sketch of the range finder, drawn before the statistics are known so that the statistics pass
+        can compute A^T Omega from the same read of the field.  Possible when the range finder starts on the time
+        side (n_samples < n_features), with every sample present (checked afterwards) and l = k + oversamples."""
         p = self._params
         k = p["n_modes"]
         if not isinstance(k, (int, np.integer)) or p["solver"] == "full":
-            return
-        shape = tuple(X.shape)
-        dims = tuple(X.dims)
-        sample = (dim,) if isinstance(dim, str) else tuple(dim)
-        T = int(np.prod([shape[dims.index(d)] for d in sample if d in dims]))
-        S = int(np.prod(shape)) // max(T, 1)
-        l = k + p["solver_kwargs"].get("n_oversamples", 10)
-        if T < S and l <= T and not isinstance(p["random_state"], np.random.RandomState):
-            self._predrawn = E.draw_sketch(p["random_state"], T, l)
+            return None
+        kw = p["solver_kwargs"]
+        l = k + kw.get("n_oversamples", 10)
+        n_iter = kw.get("n_iter", "auto")
+        S_glob = S * self.comm.world  # a lower bound is enough here
+        if not (T < S and l <= T and l <= E.MAX_L and (n_iter == "auto" or int(n_iter) >= 1)):
+            return None
+        if p["solver"] == "auto" and max(T, S_glob) < 500 and k > int(0.8 * min(T, S_glob)):
+            return None  # exact policy (decomposer.py:112-131)
+        if isinstance(p["random_state"], np.random.RandomState):
+            return None
+        self._predrawn = E.draw_sketch(p["random_state"], T, l)
+        lp = lpad(l)
+        W = np.zeros((T, lp), dtype=np.float32)
+        W[:, :l] = self._predrawn
+        return self.ops.to_device(W), l
+
+    @staticmethod
+    def _usable_first(ff, op, k, n_over):
+        l = min(k + n_over, *op.shape)
+        ok = ff.first_product is not None and op.transposed and ff.first_l == l and ff.n_samples == ff.T
+        return ff.first_product if ok else None
 
     def _shard_offset(self, ff):
         if not self.comm.active:
@@ -105,7 +119,8 @@ class EOF:
             n_over, n_iter = kw.get("n_oversamples", 10), kw.get("n_iter", "auto")
         Ur, s, Vc, infos = E.randomized_svd(ops, op, k, n_oversamples=n_over, n_iter=n_iter,
                                             random_state=p["random_state"], comm=comm,
-                                            predrawn=getattr(self, "_predrawn", None))
+                                            predrawn=getattr(self, "_predrawn", None),
+                                            first_product=self._usable_first(ff, op, k, n_over))
         E.check_infos(infos)
         # un-transpose: A = U s V^T with V on the space side
         Vt, Ut = (Ur, Vc) if op.transposed else (Vc, Ur)
