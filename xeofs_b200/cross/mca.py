@@ -111,21 +111,30 @@ class MCA:
         return self
 
     def _total_squared_covariance(self):
-        """cpcca.py:991-1000: sum |C|^2 = <X X^T, Y Y^T>_F / (n-1)^2, from the two T x T Gram matrices built
-        128 columns at a time with the streaming product."""
+        """cpcca.py:991-1000: sum |C|^2 = <X X^T, Y Y^T>_F / (n-1)^2, from the two T x T Gram matrices built 128
+        columns at a time with the streaming product.  The Gram matrices are symmetric: for the column block starting
+        at sample t0 only the samples t >= t0 are streamed, the strictly lower part counts twice."""
+        from .._cuda_ops import Field
         ops, comm = self.ops, self.comm
-        f1, f2 = self._f1, self._f2
-        T = f1.T
+        T = self._f1.T
         acc = torch.zeros((), dtype=torch.float64, device=ops.device)
+
+        def tail(f, t0):  # the field from sample t0 on (same Scaler vectors)
+            rv = None if f.row_valid is None else f.row_valid[t0:]
+            return Field(f.X[t0:], f.pivot, f.dscale, f.ccorr, f.valid, f.mean, f.std, rv)
+
         for t0 in range(0, T, 128):
             t1 = min(T, t0 + 128)
             w = t1 - t0
-            g1 = ops.project_T(f1.field, ops.scaled_rows(f1.field, t0, t1), w, algo=ops.accurate_algo)
-            g2 = ops.project_T(f2.field, ops.scaled_rows(f2.field, t0, t1), w, algo=ops.accurate_algo)
-            comm.sum_(g1)
-            comm.sum_(g2)
-            acc += (g1[:, :w].double() * g2[:, :w].double()).sum()
-        return float(acc.item()) / float(f1.n_samples - 1) ** 2
+            g = []
+            for ff in (self._f1, self._f2):
+                blk = ops.scaled_rows(ff.field, t0, t1)
+                gi = ops.project_T(tail(ff.field, t0), blk, w, algo=ops.accurate_algo)
+                comm.sum_(gi)
+                g.append(gi[:, :w].double())
+            prod = g[0] * g[1]
+            acc += prod[:w].sum() + 2.0 * prod[w:].sum()
+        return float(acc.item()) / float(self._f1.n_samples - 1) ** 2
 
     # ------------------------------------------------------------------ accessors
     def components(self, normalized=True):
