@@ -155,6 +155,14 @@ int xeofs_b200_finish_components(float* Vt, int64_t k, int64_t n, int64_t ld, co
 int xeofs_b200_varimax_accumulate(const float* L, int64_t S, int64_t m, int64_t ld, const float* rownorm,
                                   const double* R, double power, const double* colscale, double* Gout,
                                   double* Wout, float* absmax, int accumulate, void* stream);
+/* The varimax sweep (power = 3, colscale NULL, rownorm NULL: Ln already Kaiser-normalised) on the tensor cores:
+ * both products of _rotation.py:166-170 (B = X R and X^H B^3) as tcgen05 kind::tf32 MMAs with hi/lo split operands
+ * (~fp32 accuracy per product, fp64 accumulation across tiles), the tile of Ln read from HBM once.  Ln is space-side
+ * with lpad(m) rows (pad rows zero).  Returns XEOFS_E_UNSUPPORTED where tcgen05 does not apply (use
+ * xeofs_b200_varimax_accumulate).                                                                              */
+int64_t xeofs_b200_varimax_workspace_bytes(int64_t S, int64_t m);
+int xeofs_b200_varimax_sweep(const float* Ln, int64_t S, int64_t m, int64_t ld, const double* R, double* Gout,
+                             double* Wout, int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
 /* Kaiser norms (_rotation.py:155-160): h[s] = sqrt(sum_j L[j,s]^2); rownorm[s] = 1/(h+eps);
  * Ln[j,s] = L[j,s] * rownorm[s] (space-side, ldn >= S).  Any of h / rownorm / Ln may be NULL.             */
 int xeofs_b200_col_norms(const float* L, int64_t S, int64_t m, int64_t ld, float* h, float* rownorm, float* Ln,

@@ -185,7 +185,7 @@ class TorchCpuOps:
             Ln[:m] = L[:m, :S] * rn[None, :]
         return h, rn, Ln
 
-    def varimax_accumulate(self, L, S, m, R, power=3.0, colscale=None, want_absmax=False):
+    def varimax_accumulate(self, L, S, m, R, power=3.0, colscale=None, want_absmax=False, exact=False):
         X = L[:m, :S].double().t()
         B = X @ R
         Bc = B * colscale.double()[None, :] if colscale is not None else B

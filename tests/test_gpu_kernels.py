@@ -265,3 +265,43 @@ def test_fused_stats_and_first_product(T, S, l, center, standardize):
     got = Yt.cpu().numpy()
     np.testing.assert_allclose(got[:l], want, atol=3e-3 * np.abs(want).max())
     assert (got[l:] == 0).all() and (got[:, ~v] == 0).all()
+
+
+def _varimax_case(ops, S, m, seed):
+    from xeofs_b200._lib import lpad
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    Ln = ops.space_side(lpad(m), S, zero=True)
+    Ln[:m] = torch.randn((m, S), generator=g, device="cuda") * (0.2 + torch.rand((m, 1), generator=g, device="cuda"))
+    Ln[:m] /= Ln[:m].double().norm(dim=0).float()[None, :]  # Kaiser-normalised rows of the S x m loadings
+    R = torch.linalg.qr(torch.randn((m, m), generator=g, device="cuda", dtype=torch.float64))[0].contiguous()
+    X = Ln[:m].double().t()
+    B = X @ R
+    return Ln, R, X.t() @ B**3, (B * B).sum(0)
+
+
+@pytest.mark.parametrize("S,m", [(40, 3), (1001, 10), (5000, 33)])
+def test_varimax_accumulate_fp64(ops, S, m):
+    """linalg/_numpy/_rotation.py:166-170, the fp64 CUDA-core sweep."""
+    ops.varimax_algo = "simt"
+    Ln, R, Gref, Wref = _varimax_case(ops, S, m, seed=S)
+    G, W, _ = ops.varimax_accumulate(Ln, S, m, R)
+    np.testing.assert_allclose(G.cpu().numpy(), Gref.cpu().numpy(), atol=1e-12 * float(Gref.abs().max()))
+    np.testing.assert_allclose(W.cpu().numpy(), Wref.cpu().numpy(), rtol=1e-12)
+    ops.varimax_algo = "auto"
+
+
+@pytest.mark.parametrize("S,m", [(64, 8), (4096, 20), (20000, 50), (100037, 100), (30011, 128), (65536 + 17, 97)])
+def test_varimax_sweep_tcgen05(S, m):
+    """The same sweep on the tensor cores (both products kind::tf32 with hi/lo split operands, fp64 accumulation
+    across tiles): fp32-level agreement with the fp64 statement."""
+    from xeofs_b200._cuda_ops import CudaOps
+    ops = CudaOps()
+    ops.varimax_algo = "tc"
+    Ln, R, Gref, Wref = _varimax_case(ops, S, m, seed=m)
+    G, W, _ = ops.varimax_accumulate(Ln, S, m, R)
+    scale = float(Gref.abs().max())
+    np.testing.assert_allclose(G.cpu().numpy(), Gref.cpu().numpy(), atol=2e-6 * scale)
+    np.testing.assert_allclose(W.cpu().numpy(), Wref.cpu().numpy(), rtol=2e-6)
+    # the sweep is deterministic (fixed tile order per CTA, partial sums added in a fixed order)
+    G2, W2, _ = ops.varimax_accumulate(Ln, S, m, R)
+    assert torch.equal(G, G2) and torch.equal(W, W2)

@@ -86,6 +86,32 @@ def test_rotator_matches_oracle(power, m_rot):
     assert r.n_iter_ < 1000
 
 
+def test_rotator_tensor_core_sweep_matches_oracle():
+    """Enough features (S >= 16384) for EOFRotator to take the tcgen05 sweep: same oracle, same tolerances, and the
+    iteration stops where the fp64 sweep stops (the reference's rtol = 1e-8 on sum(svals) is above the noise floor)."""
+    import xeofs_b200 as xb
+    T, nlat, nlon, k, m_rot = 300, 120, 180, 12, 10
+    X = planted(T, nlat * nlon, 2 * k, seed=23).reshape(T, nlat, nlon)
+    coords = {"lat": np.linspace(85, -85, nlat), "lon": np.arange(nlon) * 2.0}
+    kw = dict(n_modes=k, use_coslat=True, random_state=2, solver_kwargs={"n_iter": 4})
+    o = oeof.eof_fit(X, DIMS, "time", coords=coords, **kw)
+    model = xb.single.EOF(**kw).fit(xb.DataArray(X, DIMS, coords), dim="time")
+    assert model.ops._varimax_tc_applies(model._Vt, nlat * nlon, m_rot, False)
+    r = xb.single.EOFRotator(n_modes=m_rot).fit(model)
+    model.ops.varimax_algo = "simt"
+    r64 = xb.single.EOFRotator(n_modes=m_rot).fit(model)
+    model.ops.varimax_algo = "auto"
+    assert abs(r.n_iter_ - r64.n_iter_) <= max(2, r64.n_iter_ // 10), (r.n_iter_, r64.n_iter_)
+    ro = orot.eof_rotator_fit(o["components_2d"], o["explained_variance"], o["scores"], o["norms"], o["A"].shape[0],
+                              n_modes=m_rot, power=1)
+    np.testing.assert_allclose(r.explained_variance().values, ro["explained_variance"], rtol=1e-4)
+    V = r.components().values.reshape(-1, m_rot)
+    dots = (V * ro["components_2d"]).sum(axis=0)
+    assert (dots >= 1 - 1e-4).all(), dots
+    np.testing.assert_allclose(r.explained_variance().values.sum(), model.explained_variance().values[:m_rot].sum(),
+                               rtol=1e-5)
+
+
 def test_rotator_not_converged_raises():
     import xeofs_b200 as xb
     X = planted(200, 600, 12, seed=5).reshape(200, 20, 30)

@@ -46,6 +46,7 @@ class CudaOps:
         else:
             self.algo = self.accurate_algo = self.exact_algo = a
         self._ws = None
+        self._vws = None
         self._unit = None
         self.launches = 0  # kernels enqueued through this object (bench.py reports it)
         self.time_products = False  # bench.py: CUDA events around every streaming product on the launch stream
@@ -281,9 +282,33 @@ class CudaOps:
         self.launches += 1
         return h, rn, Ln
 
-    def varimax_accumulate(self, L, S, m, R, power=3.0, colscale=None, want_absmax=False):
+    # the tensor-core sweep needs enough features for its fp32 rounding noise to average out below the reference's
+    # stopping threshold (rtol 1e-8 on sum(svals)): relative noise of G ~ 1e-7 / sqrt(S)
+    varimax_tc_min_S = 16384
+    varimax_algo = "auto"  # "auto" | "simt" (fp64 CUDA cores) | "tc" (tcgen05 sweep wherever it applies)
+
+    def _varimax_tc_applies(self, L, S, m, exact):
+        if self.varimax_algo == "simt" or exact or m < 2 or m > 128:
+            return False
+        if not (bool(self.lib.xeofs_b200_has_tcgen05()) and L.stride(0) % 4 == 0 and L.data_ptr() % 16 == 0
+                and int(L.shape[0]) >= lpad(m)):
+            return False
+        return self.varimax_algo == "tc" or (S >= self.varimax_tc_min_S and m >= 8)
+
+    def varimax_accumulate(self, L, S, m, R, power=3.0, colscale=None, want_absmax=False, exact=False):
+        """One sweep over the normalised loadings (linalg/_numpy/_rotation.py:166-170): Gout = Ln^T f(Ln R), W = colsum
+        ((Ln R)^2).  exact=True keeps every product in fp64 (stopping thresholds below ~1e-9)."""
         G = self.empty((m, m), torch.float64)
         Wv = self.empty(m, torch.float64)
+        if power == 3.0 and colscale is None and not want_absmax and self._varimax_tc_applies(L, S, m, exact):
+            need = int(self.lib.xeofs_b200_varimax_workspace_bytes(S, m))
+            if self._vws is None or self._vws.numel() < need:
+                self._vws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            check(self._timed("varimax_sweep", m, lambda: self.lib.xeofs_b200_varimax_sweep(
+                ptr(L), S, m, int(L.stride(0)), ptr(R), ptr(G), ptr(Wv), 0, ptr(self._vws), self._vws.numel(),
+                self._stream())), "varimax_sweep")
+            self.launches += 4
+            return G, Wv, None
         amax = self.empty(m) if want_absmax else None
         check(self.lib.xeofs_b200_varimax_accumulate(ptr(L), S, m, int(L.stride(0)), None, ptr(R), float(power),
                                                      ptr(colscale), ptr(G), ptr(Wv), ptr(amax), 0, self._stream()),

@@ -42,6 +42,8 @@ SIGNATURES = {
     "xeofs_b200_row_minmax": (_int, [_p, _i64, _i64, _i64, _p, _p, _p]),
     "xeofs_b200_finish_components": (_int, [_p, _i64, _i64, _i64, _p, _p, _p]),
     "xeofs_b200_varimax_accumulate": (_int, [_p, _i64, _i64, _i64, _p, _p, C.c_double, _p, _p, _p, _p, _int, _p]),
+    "xeofs_b200_varimax_workspace_bytes": (_i64, [_i64, _i64]),
+    "xeofs_b200_varimax_sweep": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _int, _p, _i64, _p]),
     "xeofs_b200_col_norms": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),
     "xeofs_b200_scaled_rows": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _p, _i64, _p]),
     "xeofs_b200_reconstruct": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, _p]),

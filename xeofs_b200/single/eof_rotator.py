@@ -47,7 +47,7 @@ class EOFRotator:
         alpha = 1.0 / n_rows  # gamma = 1 (varimax)
         d, converged, it = 0.0, False, 0
         for it in range(1, p["max_iter"] + 1):
-            G3, W, _ = ops.varimax_accumulate(Ln, S_local, m, R)
+            G3, W, _ = ops.varimax_accumulate(Ln, S_local, m, R, exact=p["rtol"] < 1e-9)
             comm.sum_(G3)
             comm.sum_(W)
             G = G3 - alpha * (XtX @ R) * W[None, :]
