@@ -41,14 +41,19 @@ CPU_SAMPLE_COLS = 16384  # columns of the field the CPU legs fit per step (8760 
 
 
 # ------------------------------------------------------------------------------------------------ synthetic field
-def planted_field_device(T, S, r, seed, device, sigma0=1.0e6, decay=0.9, eps=0.1, offset=280.0, nan_cols=None):
-    """offset + sum_i sigma_i u_i v_i^T + eps N(0,1) built on the device in row blocks."""
+def planted_field_device(T, S, r, seed, device, sigma0=1.0e6, decay=0.9, eps=0.1, offset=280.0, nan_cols=None,
+                         sparse=0.0):
+    """offset + sum_i sigma_i u_i v_i^T + eps N(0,1) built on the device in row blocks.
+    sparse > 0: every spatial pattern v_i lives on a random fraction `sparse` of the features (simple structure for
+    the varimax workload)."""
     import torch
 
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     U = torch.linalg.qr(torch.randn((T, r), generator=g, device=device))[0]
     V = torch.randn((S, r), generator=g, device=device)
+    if sparse > 0:
+        V *= (torch.rand((S, r), generator=g, device=device) < sparse)
     V /= V.norm(dim=0, keepdim=True)  # near-orthonormal for S >> r; avoids a QR of an S x r matrix
     sig = sigma0 * decay ** torch.arange(r, device=device, dtype=torch.float32)
     X = torch.empty((T, S), dtype=torch.float32, device=device)

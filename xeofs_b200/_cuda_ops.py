@@ -283,8 +283,8 @@ class CudaOps:
         return h, rn, Ln
 
     # the tensor-core sweep needs enough features for its fp32 rounding noise to average out below the reference's
-    # stopping threshold (rtol 1e-8 on sum(svals)): relative noise of G ~ 1e-7 / sqrt(S)
-    varimax_tc_min_S = 16384
+    # stopping threshold (rtol 1e-8 on sum(svals)): relative noise of G ~ 1e-6 / sqrt(S)
+    varimax_tc_min_S = 65536
     varimax_algo = "auto"  # "auto" | "simt" (fp64 CUDA cores) | "tc" (tcgen05 sweep wherever it applies)
 
     def _varimax_tc_applies(self, L, S, m, exact):

@@ -325,17 +325,27 @@ def randomized_svd(ops, op, k, n_oversamples=10, n_iter="auto", random_state=Non
         Q = sketch_matrix(ops, op, l, random_state, comm, predrawn)
     else:
         Q = Omega
+    lp = lpad(l)
+
+    def _shape2d(dim):  # (rows, cols) of a k-column block on this side
+        return (dim[1], lp) if dim[2] == 0 else (lp, dim[1])
+
     for it in range(int(n_iter)):
         # M @ Omega may already exist: the statistics pass computed it from the same read of the field
         Y = first_product if (it == 0 and first_product is not None) else op.mul(Q, l)
-        Q = orthonormalize(ops, Y, op.r, l, comm, 1, infos)
-        Q = orthonormalize(ops, op.mul_t(Q, l), op.c, l, comm, 1, infos)
+        # sklearn normalises after both half-steps.  From the second iteration on the columns of Q are graded (column j
+        # is dominated by the j-th singular direction), M^T (M Q) keeps them graded, and one normalisation per full
+        # iteration (on M's column side) holds the same span to fp32 accuracy: the row-side one is left out.
+        if it == 0:
+            Y = orthonormalize(ops, Y, op.r, l, comm, 1, infos)
+        Q = orthonormalize(ops, op.mul_t(Y, l), op.c, l, comm, 1, infos)
     # The last two passes decide the singular values and run at fp32 accuracy.  For the first of them the small
     # operand can be made TF32-exact beforehand — rounding the current iterate is harmless, any nearby iterate serves
     # the range finder — and then two tensor-core products (field hi/lo x operand) do instead of three.  The range
-    # basis itself must not be rounded (B = Q^T M has to use the orthonormal Q exactly), so the second pass is 3xTF32.
+    # basis itself must not be rounded: a perturbation delta of its span costs (sigma_1 delta)^2 / sigma_j in the small
+    # singular values, so B = Q^T M takes the orthonormal Q as it is, in 3xTF32.
     if getattr(op, "supports_exact", False):
-        ops.round_tf32_(Q, *((op.c[1], lpad(l)) if op.c[2] == 0 else (lpad(l), op.c[1])))
+        ops.round_tf32_(Q, *_shape2d(op.c))
         Y = op.mul(Q, l, exact=True)
     else:
         Y = op.mul(Q, l, accurate=True)

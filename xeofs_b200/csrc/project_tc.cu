@@ -325,7 +325,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           for (int r = 0; r < KW; ++r) {
             if (NS >= 2) {
               hi[r] = __float_as_uint(v[r]) & 0xffffe000u;
-              lo[r] = __float_as_uint(v[r] - __uint_as_float(hi[r]));
+              lo[r] = to_tf32(v[r] - __uint_as_float(hi[r]));  // rounded: the hardware would truncate
             } else {
               hi[r] = __float_as_uint(v[r]);  // the tensor core reads the upper 19 bits
             }
@@ -349,7 +349,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
               v = (fabsf(v) <= 3.4028234e38f) ? v * da[e] : 0.f;
               if (NS >= 2) {
                 hi[cc * 4 + e] = __float_as_uint(v) & 0xffffe000u;
-                lo[cc * 4 + e] = __float_as_uint(v - __uint_as_float(hi[cc * 4 + e]));
+                lo[cc * 4 + e] = to_tf32(v - __uint_as_float(hi[cc * 4 + e]));
               } else {
                 hi[cc * 4 + e] = __float_as_uint(v);
               }
@@ -479,7 +479,7 @@ prep_W_kernel(const float* __restrict__ W, int64_t T, int64_t ldw, int lp, float
     if (lo) {
       const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
       hi[img_offset(j, kk)] = h;
-      lo[img_offset(j, kk)] = v - h;
+      lo[img_offset(j, kk)] = __uint_as_float(to_tf32(v - h));
     } else {
       hi[img_offset(j, kk)] = v;
     }
@@ -524,7 +524,7 @@ tile_Y_kernel(const float* __restrict__ Yt, int64_t S, int64_t ldy, int lp, floa
     if (lo) {
       const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
       hi[img_offset(j, kk)] = h;
-      lo[img_offset(j, kk)] = v - h;
+      lo[img_offset(j, kk)] = __uint_as_float(to_tf32(v - h));
     } else {
       hi[img_offset(j, kk)] = v;
     }
@@ -573,8 +573,9 @@ int env_int(const char* name, int dflt) {
 }
 
 // fp32 tensor map of rank 2 (inner, outer) or rank 3 (inner, mid, outer); strides in elements
+// swizzle: 0 none, 1 = 128-byte (16-byte chunks), 2 = 128-byte with 32-byte atoms (the MN-major image of 32-bit operands)
 static int make_map(CUtensorMap* m, const float* base, int rank, const int64_t* dims, const int64_t* strides,
-                    const int* box, bool swizzle128) {
+                    const int* box, int swizzle) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -587,7 +588,10 @@ static int make_map(CUtensorMap* m, const float* base, int rank, const int64_t* 
   static const CUtensorMapL2promotion promo[4] = {CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, gdim, gstr, bx, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle == 2   ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                   : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : CU_TENSOR_MAP_SWIZZLE_NONE,
                    promo[env_int("XEOFS_TC_PROMO", 3) & 3], CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d extent %lld x %lld box %d x %d", (int)r, rank, (long long)dims[0],
@@ -597,10 +601,10 @@ static int make_map(CUtensorMap* m, const float* base, int rank, const int64_t* 
   return XEOFS_OK;
 }
 int make_map2(CUtensorMap* m, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
-                     int box_outer, bool swizzle128) {
+                     int box_outer, int swizzle) {
   const int64_t dims[2] = {inner, outer}, str[1] = {ld};
   const int box[2] = {box_inner, box_outer};
-  return make_map(m, base, 2, dims, str, box, swizzle128);
+  return make_map(m, base, 2, dims, str, box, swizzle);
 }
 
 bool tensor_maps_available() { return get_encode() != nullptr; }

@@ -223,7 +223,8 @@ struct Pipe {
 int env_int(const char* name, int dflt);
 bool tensor_maps_available();
 // fp32 tensor map of rank 2: inner extent (contiguous), outer extent, row stride ld (elements), box
+// swizzle: 0 none, 1 = 128-byte, 2 = 128-byte with 32-byte atoms
 int make_map2(CUtensorMap* m, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer,
-              bool swizzle128);
+              int swizzle);
 
 }  // namespace xb
