@@ -25,5 +25,14 @@ print(f"gram T-side   {timeit(lambda: ops.gram(Z, T, l, 0)):.3f} ms")
 print(f"chol_inv      {timeit(lambda: ops.chol_inv(G)):.3f} ms")
 print(f"apply S-side  {timeit(lambda: ops.apply(Y, S, l, 1, Rinv, l)):.3f} ms")
 print(f"apply T-side  {timeit(lambda: ops.apply(Z, T, l, 0, Rinv, l)):.3f} ms")
-print(f"sym_eig       {timeit(lambda: ops.sym_eig(G)):.3f} ms")
+for thr in (1024,):
+    for n in (20, 60, 100, 110, 128):
+        A = torch.randn((n, n), device="cuda", dtype=torch.float64)
+        A = (A @ A.t()).contiguous()
+        ms = timeit(lambda: ops.sym_eig(A))
+        ev, V = ops.sym_eig(A)
+        err = float(((V * ev[None, :]) @ V.t() - A).abs().max() / A.abs().max())
+        D = torch.diag(ev) + 1e-3 * A / A.abs().max() * ev.mean()  # nearly diagonal: the warm-started case
+        ms2 = timeit(lambda: ops.sym_eig(D.contiguous()))
+        print(f"sym_eig threads={thr} n={n}: {ms:.3f} ms (err {err:.1e}); nearly diagonal: {ms2:.3f} ms")
 print(f"row_minmax    {timeit(lambda: ops.row_minmax(Y, l, S)):.3f} ms")

@@ -8,6 +8,8 @@
 #include "common.cuh"
 
 namespace xb {
+int env_int(const char* name, int dflt);  // project_tc.cu
+
 
 // ------------------------------------------------------------------------------------------------
 // Gram matrix in fp64 (CholeskyQR needs the Gram to cond^2 accuracy).  Persistent blocks sweep chunks of n; the
@@ -267,30 +269,62 @@ apply_kernel(const float* __restrict__ In, int64_t n, int l, int64_t ld_in, cons
 
 // ------------------------------------------------------------------------------------------------
 // Symmetric eigen-decomposition by parallel cyclic Jacobi (round-robin pairing), one block, fp64.
-// A (l x l) lives in dynamic smem; the eigenvector matrix is accumulated TRANSPOSED in `work` (global,
-// row p = eigenvector p) and written out as columns at the end, sorted by descending eigenvalue.
-__global__ void __launch_bounds__(256)
+// A (l x l) lives in dynamic smem; the eigenvector matrix is accumulated TRANSPOSED (row p = eigenvector p) in
+// shared memory when both fit (VS: l <= 118), else in `work` (global), and written out as columns at the end, sorted
+// by descending eigenvalue.  Every round is two block-wide phases (rotations of the rows, then of the columns); the
+// seating of the round-robin tournament is computed, not stored.
+constexpr int EIG_THREADS = 1024;
+
+// player at seat q (0 .. le-1) in round r (< le-1) of the circle method: seat 0 keeps player 0, the others rotate
+__device__ __forceinline__ int eig_seat(int q, int r, int le) {
+  if (q == 0) return 0;
+  int x = q - 1 + r;
+  if (x >= le - 1) x -= le - 1;
+  return 1 + x;
+}
+// the two players of pair q in round r, smaller index first
+__device__ __forceinline__ void eig_pair(int q, int r, int le, int& p, int& s) {
+  p = eig_seat(q, r, le);
+  s = eig_seat(le - 1 - q, r, le);
+  if (p > s) { const int t = p; p = s; s = t; }
+}
+
+template <bool VS>
+__global__ void __launch_bounds__(EIG_THREADS)
 sym_eig_kernel(const double* __restrict__ G, int l, double* __restrict__ evals, double* __restrict__ evecs,
-               double* __restrict__ Vt, int32_t* __restrict__ info) {
+               double* __restrict__ work, int32_t* __restrict__ info) {
   extern __shared__ double sh[];
   const int le = (l + 1) & ~1;  // even size for the tournament
   const int ldA = le + 1;
   double* A = sh;                      // le x ldA
   double* cs = A + (size_t)le * ldA;   // le/2 cosines, le/2 sines
-  int* pairs = reinterpret_cast<int*>(cs + le);  // le ints: current seating
+  int* dest = reinterpret_cast<int*>(cs + le);  // le ints: output column of every eigenvector
+  int* pr = dest + le;                          // le ints: the two players of every pair in this round (p < r)
+  double* Vt = VS ? reinterpret_cast<double*>(pr + le) : work;  // le x le
   __shared__ double offnorm;
   __shared__ double diagnorm;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int half = le / 2;
-
-  for (int idx = tid; idx < le * le; idx += nt) {
-    const int i = idx / le, j = idx % le;
-    double v = 0.0;
-    if (i < l && j < l) v = 0.5 * (G[(int64_t)i * l + j] + G[(int64_t)j * l + i]);
-    A[i * ldA + j] = v;
-    Vt[idx] = (i == j) ? 1.0 : 0.0;
+  // 2 x 2 blocks (row pair qa, column pair qb) of this thread: fixed for the whole kernel (EIG_THREADS threads,
+  // half <= 64: at most 4), packed qa << 8 | qb
+  constexpr int NBLK = 4;
+  int blk[NBLK];
+#pragma unroll
+  for (int i = 0; i < NBLK; ++i) {
+    const int b = tid + i * nt;
+    blk[i] = b < half * half ? ((b / half) << 8 | (b % half)) : -1;
   }
-  for (int i = tid; i < le; i += nt) pairs[i] = i;
+  // eigenvector rows: tpq threads share the two rows of a pair
+  const int tpq = nt / half > 0 ? nt / half : 1;
+  const int vq = tid / tpq, vsub = tid - vq * tpq;
+
+  for (int i = tid >> 5; i < le; i += nt >> 5)
+    for (int j = tid & 31; j < le; j += 32) {
+      double v = 0.0;
+      if (i < l && j < l) v = 0.5 * (G[(int64_t)i * l + j] + G[(int64_t)j * l + i]);
+      A[i * ldA + j] = v;
+      Vt[i * le + j] = (i == j) ? 1.0 : 0.0;
+    }
   __syncthreads();
 
   int sweeps_done = 0;
@@ -299,11 +333,11 @@ sym_eig_kernel(const double* __restrict__ G, int l, double* __restrict__ evals, 
     if (tid == 0) { offnorm = 0.0; diagnorm = 0.0; }
     __syncthreads();
     double off = 0.0, dg = 0.0;
-    for (int idx = tid; idx < le * le; idx += nt) {
-      const int i = idx / le, j = idx % le;
-      const double v = A[i * ldA + j];
-      if (i == j) dg += v * v; else off += v * v;
-    }
+    for (int i = tid >> 5; i < le; i += nt >> 5)
+      for (int j = tid & 31; j < le; j += 32) {
+        const double v = A[i * ldA + j];
+        if (i == j) dg += v * v; else off += v * v;
+      }
     off = warp_sum(off); dg = warp_sum(dg);
     if ((tid & 31) == 0) { atomicAdd(&offnorm, off); atomicAdd(&diagnorm, dg); }
     __syncthreads();
@@ -313,52 +347,61 @@ sym_eig_kernel(const double* __restrict__ G, int l, double* __restrict__ evals, 
     sweeps_done = sweep + 1;
 
     for (int round = 0; round < le - 1; ++round) {
-      // pair q-th: (pairs[q], pairs[le-1-q])
-      for (int q = tid; q < half; q += nt) {
-        int p = pairs[q], r = pairs[le - 1 - q];
-        if (p > r) { int tmp = p; p = r; r = tmp; }
+      // rotation of pair q: zeroes A[p][r]
+      if (tid < half) {
+        int p, r;
+        eig_pair(tid, round, le, p, r);
         const double apq = A[p * ldA + r];
-        double c = 1.0, s = 0.0;
+        double c = 1.0, sn = 0.0;
         if (fabs(apq) > 1e-300) {
+          // fp64 division and square root are long software sequences and this is the serial part of every round: the
+          // tangent is taken in fp32 (the rotation then leaves ~1e-7 |apq| behind instead of 0, which the next sweep
+          // removes), while c and s are made orthonormal to fp64 accuracy from it
           const double app = A[p * ldA + p], aqq = A[r * ldA + r];
-          const double tau = (aqq - app) / (2.0 * apq);
-          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c = 1.0 / sqrt(1.0 + t * t);
-          s = t * c;
+          const double d = aqq - app;
+          int e;  // a power-of-two scale keeps both inside the fp32 range
+          (void)frexp(fmax(fabs(d), fabs(apq)), &e);
+          const float tau = (float)ldexp(d, -e) / (2.f * (float)ldexp(apq, -e));
+          const float t32 = (tau >= 0.f ? 1.f : -1.f) / (fabsf(tau) + sqrtf(1.f + tau * tau));
+          const double t = isfinite(t32) ? (double)t32 : 0.0;
+          c = rsqrt(1.0 + t * t);
+          sn = t * c;
         }
-        cs[q] = c; cs[half + q] = s;
+        cs[tid] = c; cs[half + tid] = sn;
+        pr[tid] = p; pr[half + tid] = r;
       }
       __syncthreads();
-      // rows: A <- J^T A   (row p, row r), and the eigenvector accumulator rows
-      for (int idx = tid; idx < half * le; idx += nt) {
-        const int q = idx / le, col = idx % le;
-        int p = pairs[q], r = pairs[le - 1 - q];
-        if (p > r) { int tmp = p; p = r; r = tmp; }
-        const double c = cs[q], s = cs[half + q];
-        const double ap = A[p * ldA + col], ar = A[r * ldA + col];
-        A[p * ldA + col] = c * ap - s * ar;
-        A[r * ldA + col] = s * ap + c * ar;
-        const double vp = __ldcg(&Vt[p * le + col]), vr = __ldcg(&Vt[r * le + col]);
-        __stcg(&Vt[p * le + col], c * vp - s * vr);
-        __stcg(&Vt[r * le + col], s * vp + c * vr);
+      // A <- J^T A J, one 2 x 2 block (row pair qa, column pair qb) at a time: every element is touched once
+#pragma unroll
+      for (int i = 0; i < NBLK; ++i) {
+        if (blk[i] < 0) continue;
+        const int qa = blk[i] >> 8, qb = blk[i] & 255;
+        const int pa = pr[qa], ra = pr[half + qa], pb = pr[qb], rb = pr[half + qb];
+        const double ca = cs[qa], sa = cs[half + qa], cb = cs[qb], sb = cs[half + qb];
+        const double a00 = A[pa * ldA + pb], a01 = A[pa * ldA + rb], a10 = A[ra * ldA + pb], a11 = A[ra * ldA + rb];
+        const double b00 = ca * a00 - sa * a10, b01 = ca * a01 - sa * a11;
+        const double b10 = sa * a00 + ca * a10, b11 = sa * a01 + ca * a11;
+        A[pa * ldA + pb] = cb * b00 - sb * b01;
+        A[pa * ldA + rb] = sb * b00 + cb * b01;
+        A[ra * ldA + pb] = cb * b10 - sb * b11;
+        A[ra * ldA + rb] = sb * b10 + cb * b11;
       }
-      __syncthreads();
-      // columns: A <- A J
-      for (int idx = tid; idx < half * le; idx += nt) {
-        const int q = idx % half, row = idx / half;
-        int p = pairs[q], r = pairs[le - 1 - q];
-        if (p > r) { int tmp = p; p = r; r = tmp; }
-        const double c = cs[q], s = cs[half + q];
-        const double ap = A[row * ldA + p], ar = A[row * ldA + r];
-        A[row * ldA + p] = c * ap - s * ar;
-        A[row * ldA + r] = s * ap + c * ar;
+      // eigenvector accumulator: rows p, r <- J^T rows
+      for (int q = vq; q < half; q += (nt + tpq - 1) / tpq) {
+        const int p = pr[q], r = pr[half + q];
+        const double c = cs[q], sn = cs[half + q];
+        for (int col = vsub; col < le; col += tpq) {
+          if (VS) {
+            const double vp = Vt[p * le + col], vr = Vt[r * le + col];
+            Vt[p * le + col] = c * vp - sn * vr;
+            Vt[r * le + col] = sn * vp + c * vr;
+          } else {
+            const double vp = __ldcg(&Vt[p * le + col]), vr = __ldcg(&Vt[r * le + col]);
+            __stcg(&Vt[p * le + col], c * vp - sn * vr);
+            __stcg(&Vt[r * le + col], sn * vp + c * vr);
+          }
+        }
       }
-      __syncthreads();
-      // rotate seating: position 0 fixed, others shift by one
-      int newv = -1;
-      if (tid < le && tid >= 1) newv = pairs[tid == 1 ? le - 1 : tid - 1];
-      __syncthreads();
-      if (tid < le && tid >= 1) pairs[tid] = newv;
       __syncthreads();
     }
   }
@@ -371,12 +414,12 @@ sym_eig_kernel(const double* __restrict__ G, int l, double* __restrict__ evals, 
       rank += (vj > vi) || (vj == vi && j < i);
     }
     evals[rank] = vi;
-    pairs[i] = rank;  // reuse as destination column
+    dest[i] = rank;
   }
   __syncthreads();
   for (int idx = tid; idx < l * l; idx += nt) {
     const int i = idx / l, comp = idx % l;  // eigenvector i, component comp
-    evecs[(int64_t)comp * l + pairs[i]] = __ldcg(&Vt[i * le + comp]);
+    evecs[(int64_t)comp * l + dest[i]] = VS ? Vt[i * le + comp] : __ldcg(&Vt[i * le + comp]);
   }
   if (tid == 0) info[0] = sweeps_done;
 }
@@ -491,9 +534,16 @@ extern "C" int xeofs_b200_sym_eig(const double* G, int64_t l, double* evals, dou
   cudaStream_t stream = (cudaStream_t)stream_;
   XB_CHECK_ARG(G && evals && evecs && work && info && l > 0 && l <= 128, "sym_eig: bad arguments (l=%lld must be in 1..128)", (long long)l);
   const int le = ((int)l + 1) & ~1;
-  const size_t smem = ((size_t)le * (le + 1) + le) * sizeof(double) + (size_t)le * sizeof(int);
-  XB_CUDA(cudaFuncSetAttribute(sym_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sym_eig_kernel<<<1, 256, smem, stream>>>(G, (int)l, evals, evecs, work, info);
+  const size_t base = ((size_t)le * (le + 1) + le) * sizeof(double) + (size_t)2 * le * sizeof(int);
+  const size_t with_v = base + (size_t)le * le * sizeof(double);
+  const int threads = EIG_THREADS;  // the kernel's block table assumes half^2 <= 4 * threads
+  if (with_v <= 227 * 1024) {
+    XB_CUDA(cudaFuncSetAttribute(sym_eig_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_v));
+    sym_eig_kernel<true><<<1, threads, with_v, stream>>>(G, (int)l, evals, evecs, work, info);
+  } else {
+    XB_CUDA(cudaFuncSetAttribute(sym_eig_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));
+    sym_eig_kernel<false><<<1, threads, base, stream>>>(G, (int)l, evals, evecs, work, info);
+  }
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
 }
