@@ -48,6 +48,7 @@ extern "C" {
 #define XEOFS_ALGO_TF32X2 5 /* tcgen05 kind::tf32, field split hi/lo, the small operand (W / Yt) must hold TF32-exact
                                values (xeofs_b200_round_tf32): 2 products, ~fp32 accuracy; SIMT where tcgen05 does
                                not apply                                                                        */
+#define XEOFS_ALGO_TF32X1R 6 /* TF32X1 with both operands rounded to TF32 to nearest (unbiased sums; else as TF32X1) */
 
 /* flags for xeofs_b200_scaling_finalize */
 #define XEOFS_F_CENTER 1

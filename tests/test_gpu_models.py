@@ -56,6 +56,27 @@ def test_mca_matches_explicit_cross_covariance_oracle(shape, kw):
         np.testing.assert_allclose(sc.values / scale, osc / scale, atol=2e-3)
 
 
+def test_mca_total_squared_covariance_wide_fields():
+    """cpcca.py:991-1000 at a width (S >= 2^16) where the sample Gram matrices take the single rounded TF32 product
+    (XEOFS_ALGO_TF32X1R): sum |C|^2 = <A1 A1^T, A2 A2^T> / (n-1)^2 against fp64 torch on the preprocessed fields."""
+    import xeofs_b200 as xb
+    from xeofs_b200 import _lib
+    T, S1, S2, k = 300, 70000, 66000, 4
+    X, Y = _coupled_fields(T, S1, S2, 2 * k, seed=11)
+    X = X.reshape(T, 70, 1000)
+    Y = Y.reshape(T, 66, 1000)
+    m = xb.cross.MCA(n_modes=k, random_state=3, total_squared_covariance=False)
+    m.fit(xb.DataArray(X, DIMS), xb.DataArray(Y, DIMS), dim="time")
+    assert m.ops.sum_algo == _lib.ALGO_TF32X1R
+    tsc = m.total_squared_covariance()
+    A1 = torch.from_numpy(X.reshape(T, -1)).cuda().double()
+    A2 = torch.from_numpy(Y.reshape(T, -1)).cuda().double()
+    A1 -= A1.mean(0)
+    A2 -= A2.mean(0)
+    ref = float(((A1 @ A1.t()) * (A2 @ A2.t())).sum()) / (T - 1) ** 2
+    np.testing.assert_allclose(tsc, ref, rtol=2e-5)
+
+
 @pytest.mark.parametrize("power", [1, 2])
 @pytest.mark.parametrize("m_rot", [2, 10])
 def test_rotator_matches_oracle(power, m_rot):

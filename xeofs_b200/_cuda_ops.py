@@ -39,6 +39,9 @@ class CudaOps:
         # algo: arithmetic of the power-iteration products; accurate_algo: of the two products the singular
         # values are read from (the final range basis and B = Q^T M)
         # exact_algo: the same two products when the caller has made the small operand TF32-exact (round_tf32_)
+        # sum_algo: products whose entries are summed as numbers over ~1e5 features or more (the sample Gram matrices
+        # behind MCA's total squared covariance): one TF32 product with operands rounded to nearest, unbiased
+        self.sum_algo = _lib.ALGO_TF32X1R if a in (_lib.ALGO_AUTO, _lib.ALGO_TF32X1) else a
         if a == _lib.ALGO_AUTO:
             self.algo, self.accurate_algo, self.exact_algo = _lib.ALGO_AUTO_FAST, _lib.ALGO_AUTO, _lib.ALGO_TF32X2
         elif a == _lib.ALGO_TF32X1:

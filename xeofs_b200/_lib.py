@@ -13,8 +13,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libxeofs_b200.so")
 
-ALGO_AUTO, ALGO_SIMT, ALGO_TF32X1, ALGO_TF32X3, ALGO_AUTO_FAST, ALGO_TF32X2 = 0, 1, 2, 3, 4, 5
-ALGO_NAMES = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tf32x1": ALGO_TF32X1, "tf32x3": ALGO_TF32X3, "tf32x2": ALGO_TF32X2}
+ALGO_AUTO, ALGO_SIMT, ALGO_TF32X1, ALGO_TF32X3, ALGO_AUTO_FAST, ALGO_TF32X2, ALGO_TF32X1R = 0, 1, 2, 3, 4, 5, 6
+ALGO_NAMES = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tf32x1": ALGO_TF32X1, "tf32x3": ALGO_TF32X3, "tf32x2": ALGO_TF32X2, "tf32x1r": ALGO_TF32X1R}
 F_CENTER, F_STANDARDIZE = 1, 2
 E_INVALID, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = -1, -2, -3, -4
 

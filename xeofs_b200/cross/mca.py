@@ -118,6 +118,10 @@ class MCA:
         ops, comm = self.ops, self.comm
         T = self._f1.T
         acc = torch.zeros((), dtype=torch.float64, device=ops.device)
+        # each Gram entry is a sum over all features: with >= 2^16 of them the rounding noise of a single TF32 product
+        # (operands rounded to nearest, 2e-4 per term) averages out below 1e-6; smaller fields take the 3xTF32 product
+        S_all = min(self._f1.S_global, self._f2.S_global)
+        algo = getattr(ops, "sum_algo", ops.accurate_algo) if S_all >= 65536 else ops.accurate_algo
 
         def tail(f, t0):  # the field from sample t0 on (same Scaler vectors)
             rv = None if f.row_valid is None else f.row_valid[t0:]
@@ -129,7 +133,7 @@ class MCA:
             g = []
             for ff in (self._f1, self._f2):
                 blk = ops.scaled_rows(ff.field, t0, t1)
-                gi = ops.project_T(tail(ff.field, t0), blk, w, algo=ops.accurate_algo)
+                gi = ops.project_T(tail(ff.field, t0), blk, w, algo=algo)
                 comm.sum_(gi)
                 g.append(gi[:, :w].double())
             prod = g[0] * g[1]

@@ -77,7 +77,9 @@ struct TcParams {
 // ------------------------------------------------------------------------------------------------ the kernel
 // NS: 1 = single TF32 product, 3 = 3xTF32.  SIDE_T: false = project_S, true = project_T.
 // KB: 32-wide K slabs per pipeline stage (project_T reads KB*128 contiguous bytes of every row per TMA box).
-template <int NS, bool SIDE_T, int KB, bool STATS = false>
+// RN (single TF32 only): round the operands to TF32 (to nearest) instead of letting the tensor core truncate them — the
+// product is then unbiased (XEOFS_ALGO_TF32X1R: sums that are read as numbers, not only as a subspace).
+template <int NS, bool SIDE_T, int KB, bool STATS = false, bool RN = false>
 __global__ void __launch_bounds__(tc_threads(NS), (NS == 1 && !SIDE_T) ? 2 : 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBhi,
                   const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
@@ -327,7 +329,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
               hi[r] = __float_as_uint(v[r]) & 0xffffe000u;
               lo[r] = to_tf32(v[r] - __uint_as_float(hi[r]));  // rounded: the hardware would truncate
             } else {
-              hi[r] = __float_as_uint(v[r]);  // the tensor core reads the upper 19 bits
+              hi[r] = RN ? to_tf32(v[r]) : __float_as_uint(v[r]);  // the tensor core reads the upper 19 bits
             }
           }
         } else {
@@ -351,7 +353,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 hi[cc * 4 + e] = __float_as_uint(v) & 0xffffe000u;
                 lo[cc * 4 + e] = to_tf32(v - __uint_as_float(hi[cc * 4 + e]));
               } else {
-                hi[cc * 4 + e] = __float_as_uint(v);
+                hi[cc * 4 + e] = RN ? to_tf32(v) : __float_as_uint(v);
               }
             }
           }
@@ -467,7 +469,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 // W (T x ldw, time-side) -> images of the K slabs of W^T (K = t): hi = value with the TF32 bits only, lo = fp32
 // remainder (3xTF32 only, else the value goes in unsplit).  Zero beyond T.
 __global__ void __launch_bounds__(256)
-prep_W_kernel(const float* __restrict__ W, int64_t T, int64_t ldw, int lp, float* __restrict__ Whi, float* __restrict__ Wlo) {
+prep_W_kernel(const float* __restrict__ W, int64_t T, int64_t ldw, int lp, float* __restrict__ Whi, float* __restrict__ Wlo,
+              int rn = 0) {
   // one block per slab of 32 t: thread (j, 4 k's)
   const int64_t t0 = (int64_t)blockIdx.x * 32;
   float* hi = Whi + (size_t)blockIdx.x * lp * 32;
@@ -481,7 +484,7 @@ prep_W_kernel(const float* __restrict__ W, int64_t T, int64_t ldw, int lp, float
       hi[img_offset(j, kk)] = h;
       lo[img_offset(j, kk)] = __uint_as_float(to_tf32(v - h));
     } else {
-      hi[img_offset(j, kk)] = v;
+      hi[img_offset(j, kk)] = rn ? __uint_as_float(to_tf32(v)) : v;
     }
   }
 }
@@ -512,7 +515,8 @@ __global__ void chunk_flags_kernel(const uint8_t* __restrict__ row_valid, int64_
 
 // Yt (lp x ldy, space-side) -> images of its K slabs (K = s), zero beyond S.  One block per slab.
 __global__ void __launch_bounds__(256)
-tile_Y_kernel(const float* __restrict__ Yt, int64_t S, int64_t ldy, int lp, float* __restrict__ Yhi, float* __restrict__ Ylo) {
+tile_Y_kernel(const float* __restrict__ Yt, int64_t S, int64_t ldy, int lp, float* __restrict__ Yhi, float* __restrict__ Ylo,
+              int rn = 0) {
   const int64_t s0 = (int64_t)blockIdx.x * 32;
   float* hi = Yhi + (size_t)blockIdx.x * lp * 32;
   float* lo = Ylo ? Ylo + (size_t)blockIdx.x * lp * 32 : nullptr;
@@ -526,7 +530,7 @@ tile_Y_kernel(const float* __restrict__ Yt, int64_t S, int64_t ldy, int lp, floa
       hi[img_offset(j, kk)] = h;
       lo[img_offset(j, kk)] = __uint_as_float(to_tf32(v - h));
     } else {
-      hi[img_offset(j, kk)] = v;
+      hi[img_offset(j, kk)] = rn ? __uint_as_float(to_tf32(v)) : v;
     }
   }
 }
@@ -617,6 +621,7 @@ bool tc_supported(int64_t T, int64_t S, int64_t ldx, const float* X, int64_t l) 
 static inline int64_t align256(int64_t b) { return round_up(b, 256); }
 static inline bool is_x3(int algo) { return algo == XEOFS_ALGO_TF32X3 || algo == XEOFS_ALGO_AUTO; }
 static inline int algo_ns(int algo) { return algo == XEOFS_ALGO_TF32X3 ? 3 : algo == XEOFS_ALGO_TF32X2 ? 2 : 1; }
+static inline bool algo_rn(int algo) { return algo == XEOFS_ALGO_TF32X1R; }
 
 // project_T: 32-wide K slabs per stage = bytes of a row fetched per bulk copy / 128.  The largest that leaves
 // at least two stages of shared memory and TMEM.
@@ -660,7 +665,11 @@ struct TGeom {
   int64_t t_tiles, rows_pad, Spad;
   int chunks_total, chunks_per_cta, splits;
 };
-static TGeom t_geometry(int64_t T, int64_t S, bool x3, int kb) {
+// cap: the longest K range (in 32-wide slabs) one TMEM accumulator may sum before its truncating adds show: 0 = no cap
+// (the 3xTF32 / 2xTF32 kernels flush into fp32 registers every TC_FLUSH slabs), 1024 for the power-iteration products
+// (a bias of ~1e-4 that only rescales the iterate), 64 for XEOFS_ALGO_TF32X1R (~5e-6)
+static int t_cap(int algo) { return algo_ns(algo) >= 2 ? 0 : algo_rn(algo) ? 64 : 1024; }
+static TGeom t_geometry(int64_t T, int64_t S, int cap, int kb) {
   TGeom g;
   g.t_tiles = ceil_div(T, TC_TILE);
   g.rows_pad = g.t_tiles * TC_TILE;
@@ -670,8 +679,7 @@ static TGeom t_geometry(int64_t T, int64_t S, bool x3, int kb) {
   if (want < 1) want = 1;
   if (want > g.chunks_total) want = g.chunks_total;
   g.chunks_per_cta = (int)ceil_div(g.chunks_total, want);
-  // single-TF32 kernels keep one TMEM accumulator for the whole K range of a CTA: bound its truncation bias
-  if (!x3 && g.chunks_per_cta > 1024 / kb) g.chunks_per_cta = 1024 / kb;
+  if (cap > 0 && g.chunks_per_cta > cap / kb) g.chunks_per_cta = cap / kb;
   g.splits = (int)ceil_div(g.chunks_total, g.chunks_per_cta);
   return g;
 }
@@ -687,7 +695,7 @@ int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo) {
   // (the finest split has the largest partial buffer)
   int64_t part = 0;
   for (int kb = 1; kb <= 4; kb *= 2) {
-    const TGeom g = t_geometry(T, S, false, kb);
+    const TGeom g = t_geometry(T, S, t_cap(algo), kb);
     const int64_t b = (int64_t)g.splits * g.rows_pad * lp * 4;
     if (b > part) part = b;
   }
@@ -696,11 +704,11 @@ int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo) {
   return (bs > bt ? bs : bt) + 256;
 }
 
-template <int NS, bool SIDE_T, int KB>
+template <int NS, bool SIDE_T, int KB, bool RN = false>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p, dim3 grid,
                      size_t smem, cudaStream_t stream) {
-  XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<NS, SIDE_T, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  project_tc_kernel<NS, SIDE_T, KB><<<grid, tc_threads(NS), smem, stream>>>(mx, mh, ml, p);
+  XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<NS, SIDE_T, KB, false, RN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  project_tc_kernel<NS, SIDE_T, KB, false, RN><<<grid, tc_threads(NS), smem, stream>>>(mx, mh, ml, p);
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
 }
@@ -723,7 +731,7 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
     chunk_flags_kernel<<<(unsigned)ceil_div(Tpad / TC_KC, 128), 128, 0, stream>>>(row_valid, T, (int)(Tpad / TC_KC), flags);
     XB_LAUNCH_CHECK();
   }
-  prep_W_kernel<<<(unsigned)(Tpad / TC_KC), 256, 0, stream>>>(W, T, ldw, lp, Whi, Wlo);
+  prep_W_kernel<<<(unsigned)(Tpad / TC_KC), 256, 0, stream>>>(W, T, ldw, lp, Whi, Wlo, algo_rn(algo) ? 1 : 0);
   XB_LAUNCH_CHECK();
   CUtensorMap mx, mh, ml;
   rc = make_map2(&mx, X, S, T, ldx, TC_TILE, TC_KC, false);
@@ -747,9 +755,10 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   p.X = X; p.ldx = ldx; p.bimg_hi = Whi; p.bimg_lo = Wlo;
   p.chunk_flags = row_valid ? flags : nullptr;
   dim3 grid((unsigned)ceil_div(S, TC_TILE));
-  return ns == 3   ? launch_tc<3, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
-         : ns == 2 ? launch_tc<2, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
-                   : launch_tc<1, false, 1>(mx, mh, ml, p, grid, sh.smem, stream);
+  return ns == 3        ? launch_tc<3, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
+         : ns == 2      ? launch_tc<2, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
+         : algo_rn(algo) ? launch_tc<1, false, 1, true>(mx, mh, ml, p, grid, sh.smem, stream)
+                        : launch_tc<1, false, 1>(mx, mh, ml, p, grid, sh.smem, stream);
 }
 
 __global__ void stats_init_kernel(double* scalars, int32_t* row_delta, int64_t T, int32_t* base_nan) {
@@ -822,7 +831,7 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   const Shape sh = pick_shape_T(lp, ns, S, ldx);
   XB_CHECK_ARG(sh.stages >= 1, "project_T: no pipeline shape fits lp=%d", lp);
   const int kb = sh.kb;
-  const TGeom g = t_geometry(T, S, ns >= 2, kb);
+  const TGeom g = t_geometry(T, S, t_cap(algo), kb);
   XB_CHECK_ARG(g.splits <= 65535, "project_T: too many splits");
   uint8_t* ws = (uint8_t*)workspace;
   float* rvec = (float*)ws; ws += align256(lp * 4);
@@ -832,7 +841,7 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   float* Ylo = ns == 3 ? (float*)ws : nullptr;
   pad_vectors_kernel<<<(unsigned)ceil_div(g.Spad, 256), 256, 0, stream>>>(pivot, dscale, S, g.Spad, pdpad);
   XB_LAUNCH_CHECK();
-  tile_Y_kernel<<<(unsigned)(g.Spad / TC_KC), 256, 0, stream>>>(Yt, S, ldy, lp, Yhi, Ylo);
+  tile_Y_kernel<<<(unsigned)(g.Spad / TC_KC), 256, 0, stream>>>(Yt, S, ldy, lp, Yhi, Ylo, algo_rn(algo) ? 1 : 0);
   XB_LAUNCH_CHECK();
   int rc;
   if (ccorr) {
@@ -862,6 +871,10 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
 #define XB_T_LAUNCH(NSV, KBV) launch_tc<NSV, true, KBV>(mx, mh, ml, p, grid, sh.smem, stream)
   if (ns == 3) rc = kb == 1 ? XB_T_LAUNCH(3, 1) : kb == 2 ? XB_T_LAUNCH(3, 2) : XB_T_LAUNCH(3, 4);
   else if (ns == 2) rc = kb == 1 ? XB_T_LAUNCH(2, 1) : kb == 2 ? XB_T_LAUNCH(2, 2) : XB_T_LAUNCH(2, 4);
+  else if (algo_rn(algo))
+    rc = kb == 1   ? launch_tc<1, true, 1, true>(mx, mh, ml, p, grid, sh.smem, stream)
+         : kb == 2 ? launch_tc<1, true, 2, true>(mx, mh, ml, p, grid, sh.smem, stream)
+                   : launch_tc<1, true, 4, true>(mx, mh, ml, p, grid, sh.smem, stream);
   else rc = kb == 1 ? XB_T_LAUNCH(1, 1) : kb == 2 ? XB_T_LAUNCH(1, 2) : XB_T_LAUNCH(1, 4);
 #undef XB_T_LAUNCH
   if (rc) return rc;
