@@ -295,12 +295,23 @@ def run_ours(args):
             by.setdefault(name, []).append(t_ms)
         lp = (min(k + 10, T, S_local) + 15) // 16 * 16
         alg = bytes_local + S_local * lp * 4 + T * lp * 4
-        streaming = {n: v for n, v in by.items() if n in ("project_S", "project_T", "project_S_stats", "col_stats")}
+        streaming = {n: v for n, v in by.items() if n.startswith(("project_S", "project_T", "col_stats"))}
         dom = max(streaming or by, key=lambda n: sum(by[n]))
         avg_ms = float(np.mean(by[dom]))
         ach = alg / (avg_ms * 1e-3) / 1e9
+        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this workload (a profiler
+        # figure, taken once per change — not measured in this run); null when the local slab is not the profiled one
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tj.get("workload") == args.workload and bytes_local == WORKLOADS[args.workload][0] * \
+                    WORKLOADS[args.workload][1] * WORKLOADS[args.workload][2] * 4 and dom in tj:
+                traffic, traffic_src = float(tj[dom]), "profiles/r01_traffic.json (ncu --set full, dram read + write)"
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "launch_ms": avg_ms, "launches_timed": len(by[dom]),
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launch_ms": avg_ms,
+                "launches_timed": len(by[dom]),
                 "algorithmic_bytes_per_launch": alg,
                 "per_kernel_ms": {n: float(np.mean(v)) for n, v in by.items()},
                 "share_of_step": float(sum(sum(v) for v in by.values()) / ms)}

@@ -100,3 +100,35 @@ def eof_rotator_fit(components_2d, explained_variance, scores, norms, n_samples,
         "phi_matrix": phi,
         "modes_sign": sgn[idx],
     }
+
+
+def mca_rotator_fit(components1_2d, components2_2d, singular_values, scores1, scores2,
+                    n_modes=2, power=1, max_iter=None, rtol=1e-8):
+    """MCARotator / CPCCARotator with identity whitening and no PCA stage (cross/cpcca_rotator.py:122-305;
+    cross/mca_rotator.py:5): varimax/promax of the concatenated, sqrt(s)-weighted singular vectors.
+    components*_2d (S', k) valid features only, scores* (n, k) = X Q."""
+    if max_iter is None:
+        max_iter = 1000  # compute=True default, cpcca_rotator.py:86-87
+    m = n_modes
+    scaling = np.sqrt(singular_values[:m])                                   # :154-155
+    S1 = components1_2d.shape[0]
+    loadings = np.concatenate([components1_2d[:, :m], components2_2d[:, :m]], axis=0) * scaling   # :171
+    Lrot, R, phi = promax(loadings, power=power, max_iter=max_iter, rtol=rtol)   # :175-180
+    Q1r, Q2r = Lrot[:S1], Lrot[S1:]                                          # :193-198
+    n1 = np.linalg.norm(Q1r, axis=0)                                         # :211-232
+    n2 = np.linalg.norm(Q2r, axis=0)
+    Q1r, Q2r = Q1r / n1, Q2r / n2                                            # :235-236
+    sqcov = (n1 * n2) ** 2                                                   # :239-240
+    idx = np.argsort(sqcov)[::-1]                                            # :243
+    RinvT = R
+    if power > 1:                                                            # :445-469
+        RinvT = np.linalg.inv(R).conj().T
+    sc1 = (scores1[:, :m] / scaling) @ RinvT * n1                            # :254-268
+    sc2 = (scores2[:, :m] / scaling) @ RinvT * n2
+    sgn = sign_multiplier(Lrot.T)                                            # :271 (rule on the combined loadings)
+    return {
+        "components1_2d": (Q1r * sgn)[:, idx], "components2_2d": (Q2r * sgn)[:, idx],
+        "scores1": (sc1 * sgn)[:, idx], "scores2": (sc2 * sgn)[:, idx],
+        "squared_covariance": sqcov[idx], "norm1": n1[idx], "norm2": n2[idx],
+        "idx_modes_sorted": idx, "rotation_matrix": R, "phi_matrix": phi, "modes_sign": sgn[idx],
+    }

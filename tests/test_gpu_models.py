@@ -56,6 +56,35 @@ def test_mca_matches_explicit_cross_covariance_oracle(shape, kw):
         np.testing.assert_allclose(sc.values / scale, osc / scale, atol=2e-3)
 
 
+@pytest.mark.parametrize("power", [1, 2])
+def test_mca_rotator_matches_oracle(power):
+    """MCARotator (cross/cpcca_rotator.py:122-305) on the device against the numpy restatement: squared covariance
+    rtol 1e-4, both sets of rotated singular vectors up to the reference's sign rule, rotated scores."""
+    import xeofs_b200 as xb
+    T, S1, S2, k, mr = 300, 40 * 30, 20 * 37, 8, 5
+    X, Y = _coupled_fields(T, S1, S2, 2 * k, seed=5)
+    X = X.reshape(T, 40, 30)
+    Y = Y.reshape(T, 20, 37)
+    X[:, 3, 5] = np.nan
+    o = omca.mca_fit(X, Y, DIMS, DIMS, "time", n_modes=k, random_state=3)
+    m = xb.cross.MCA(n_modes=k, random_state=3, total_squared_covariance=False)
+    m.fit(xb.DataArray(X, DIMS), xb.DataArray(Y, DIMS), dim="time")
+    r = xb.cross.MCARotator(n_modes=mr, power=power).fit(m)
+    ro = orot.mca_rotator_fit(o["components1_2d"], o["components2_2d"], o["singular_values"], o["scores1"],
+                              o["scores2"], n_modes=mr, power=power)
+    np.testing.assert_allclose(r.squared_covariance().values, ro["squared_covariance"], rtol=1e-4)
+    c1, c2 = r.components()
+    for c, oc, f in ((c1, ro["components1_2d"], o["fitted1"]), (c2, ro["components2_2d"], o["fitted2"])):
+        V = c.values.reshape(-1, mr)
+        np.testing.assert_array_equal(np.isnan(V).any(axis=1), ~f["is_valid_feature"])
+        dots = (V[f["is_valid_feature"]] * oc).sum(axis=0)
+        assert (dots >= 1 - 1e-4).all(), dots
+    s1, s2 = r.scores()
+    for sc, osc in ((s1, ro["scores1"]), (s2, ro["scores2"])):
+        scale = np.abs(osc).max(axis=0)
+        np.testing.assert_allclose(sc.values / scale, osc / scale, atol=2e-3)
+
+
 def test_mca_total_squared_covariance_wide_fields():
     """cpcca.py:991-1000 at a width (S >= 2^16) where the sample Gram matrices take the single rounded TF32 product
     (XEOFS_ALGO_TF32X1R): sum |C|^2 = <A1 A1^T, A2 A2^T> / (n-1)^2 against fp64 torch on the preprocessed fields."""

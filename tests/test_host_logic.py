@@ -141,6 +141,37 @@ def test_mca_host_logic():
     assert ((c2.values * o["components2_2d"]).sum(axis=0) > 1 - 1e-5).all()
 
 
+def test_mca_rotator_host_logic():
+    """cross/cpcca_rotator.py:122-305 (identity whitening, no PCA) against its numpy restatement."""
+    import xeofs_b200 as xb
+    T, k, mr = 150, 6, 4
+    rng = np.random.default_rng(1)
+    U = np.linalg.qr(rng.standard_normal((T, 2 * k)))[0]
+    sig = 100 * 0.8 ** np.arange(2 * k)
+    X = ((U * sig) @ np.linalg.qr(rng.standard_normal((83, 2 * k)))[0].T + 0.01 * rng.standard_normal((T, 83))).astype(np.float32)
+    Y = ((U * sig) @ np.linalg.qr(rng.standard_normal((60, 2 * k)))[0].T + 0.01 * rng.standard_normal((T, 60))).astype(np.float32)
+    X[:, 7] = np.nan
+    o = omca.mca_fit(X, Y, ("time", "x"), ("time", "y"), "time", n_modes=k, random_state=3)
+    m = xb.cross.MCA(n_modes=k, random_state=3, ops=TorchCpuOps())
+    m.fit(xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")
+    for power in (1, 2):
+        r = xb.cross.MCARotator(n_modes=mr, power=power).fit(m)
+        ro = orot.mca_rotator_fit(o["components1_2d"], o["components2_2d"], o["singular_values"], o["scores1"],
+                                  o["scores2"], n_modes=mr, power=power)
+        np.testing.assert_allclose(r.squared_covariance().values, ro["squared_covariance"], rtol=1e-4)
+        np.testing.assert_allclose(r.data["norm1"].cpu().numpy(), ro["norm1"], rtol=1e-4)
+        c1, c2 = r.components()
+        v1 = c1.values[~np.isnan(c1.values).any(axis=1)]
+        assert ((v1 * ro["components1_2d"]).sum(axis=0) > 1 - 1e-5).all()
+        assert ((c2.values * ro["components2_2d"]).sum(axis=0) > 1 - 1e-5).all()
+        s1, s2 = r.scores()
+        for sc, osc in ((s1, ro["scores1"]), (s2, ro["scores2"])):
+            scale = np.abs(osc).max(axis=0)
+            np.testing.assert_allclose(sc.values / scale, osc / scale, atol=1e-3)
+    with pytest.raises(ValueError, match="exceeds"):
+        xb.cross.MCARotator(n_modes=k + 1).fit(m)
+
+
 def test_rotator_host_logic():
     import xeofs_b200 as xb
     X = planted(200, 300, 12, seed=4).reshape(200, 10, 30)

@@ -39,7 +39,7 @@ def main():
         return e0.elapsed_time(e1) / n
 
     def run(tag):
-        for name, algo in (("x1", _lib.ALGO_TF32X1), ("x3", _lib.ALGO_TF32X3)):
+        for name, algo in (("x1", _lib.ALGO_TF32X1), ("x1r", _lib.ALGO_TF32X1R), ("x2", _lib.ALGO_TF32X2), ("x3", _lib.ALGO_TF32X3)):
             ms_s = timeit(lambda: ops.project_S(f, W, l, algo=algo))
             ms_t = timeit(lambda: ops.project_T(f, Y, l, algo=algo))
             print(f"{tag:28s} {name}  project_S {ms_s:7.3f} ms {alg_bytes / ms_s / 1e6:7.0f} GB/s   "

@@ -93,6 +93,12 @@ class CudaOps:
         self._prod_events.append((name, e0, e1, l))
         return rc
 
+    @staticmethod
+    def _algo_tag(algo):
+        """Suffix of the timing tag: the single-TF32 products (the bulk of a fit) carry none."""
+        return {_lib.ALGO_AUTO: "_x3", _lib.ALGO_TF32X3: "_x3", _lib.ALGO_TF32X2: "_x2", _lib.ALGO_SIMT: "_simt",
+                _lib.ALGO_TF32X1R: "_x1r"}.get(algo, "")
+
     def product_times(self):
         """[(kernel name, milliseconds, l)] of the timed products (synchronises)."""
         torch.cuda.synchronize(self.device)
@@ -162,7 +168,7 @@ class CudaOps:
         lp = lpad(l)
         Yt = out if out is not None else self.space_side(lp, f.S)
         ws = self.workspace(f.T, f.S, l, algo)
-        check(self._timed(tag, l, lambda: self.lib.xeofs_b200_project_S(
+        check(self._timed(tag + self._algo_tag(algo), l, lambda: self.lib.xeofs_b200_project_S(
             ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr), ptr(f.row_valid), ptr(W),
             int(W.stride(0)), l,
             ptr(Yt), int(Yt.stride(0)), ptr(ws), ws.numel(), algo, self._stream())), "project_S")
@@ -175,7 +181,7 @@ class CudaOps:
         lp = lpad(l)
         Z = out if out is not None else self.empty((f.T, lp))
         ws = self.workspace(f.T, f.S, l, algo)
-        check(self._timed("project_T", l, lambda: self.lib.xeofs_b200_project_T(
+        check(self._timed("project_T" + self._algo_tag(algo), l, lambda: self.lib.xeofs_b200_project_T(
             ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr), ptr(f.row_valid), ptr(Yt),
             int(Yt.stride(0)), l,
             ptr(Z), int(Z.stride(0)), ptr(ws), ws.numel(), algo, self._stream())), "project_T")

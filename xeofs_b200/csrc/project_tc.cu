@@ -32,8 +32,11 @@ namespace xb {
 
 // warps per TMEM lane quarter in the operand stage: the 3xTF32 kernels run one CTA per SM and need the extra warps to
 // hide the latencies of their longer conversion chain
-__host__ __device__ constexpr int tc_nw(int ns) { return ns >= 2 ? 4 : 2; }
-__host__ __device__ constexpr int tc_threads(int ns) { return 64 + 128 * tc_nw(ns); }
+// (wide: one CTA per SM — every instantiation but the plain single-TF32 project_S, which runs two CTAs of 8 operand warps)
+__host__ __device__ constexpr int tc_nw(bool wide) { return wide ? 4 : 2; }
+__host__ __device__ constexpr int tc_threads(bool wide) { return 64 + 128 * tc_nw(wide); }
+// (16 operand warps were tried for the single-TF32 project_T: 3-5 % slower than 8)
+__host__ __device__ constexpr bool tc_wide(int ns, bool side_t, bool rn) { return ns >= 2; }
 constexpr int TC_KC = 32;        // K elements per stage (= one 128-byte swizzle atom of fp32)
 constexpr int TC_XBYTES = TC_TILE * TC_KC * 4;  // 16 KB of X per stage
 constexpr int TC_MAX_STAGES = 6;
@@ -80,14 +83,17 @@ struct TcParams {
 // RN (single TF32 only): round the operands to TF32 (to nearest) instead of letting the tensor core truncate them — the
 // product is then unbiased (XEOFS_ALGO_TF32X1R: sums that are read as numbers, not only as a subspace).
 template <int NS, bool SIDE_T, int KB, bool STATS = false, bool RN = false>
-__global__ void __launch_bounds__(tc_threads(NS), (NS == 1 && !SIDE_T) ? 2 : 1)
+__global__ void __launch_bounds__(tc_threads(tc_wide(NS, SIDE_T, RN)), (NS == 1 && !SIDE_T && !RN) ? 2 : 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBhi,
                   const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
   static_assert(SIDE_T || KB == 1, "project_S stages are 32 rows of t");
   static_assert(!STATS || (NS == 1 && !SIDE_T), "the statistics ride on the first (single TF32) project_S pass");
   constexpr int NPART = NS >= 2 ? 2 : 1;            // parts of the big operand kept per value (hi | lo)
   constexpr int BPART = NS == 3 ? 2 : 1;            // parts of the small operand (NS == 2: it is TF32-exact already)
-  constexpr int NW = tc_nw(NS);                     // operand-stage warps per TMEM lane quarter
+  // FL: two TMEM accumulators that take turns, each moved into fp32 registers (round-to-nearest adds) after TC_FLUSH
+  // slabs — the tensor core's own adds truncate.  All multi-product modes, and the rounded single product.
+  constexpr bool FL = NS >= 2 || RN;
+  constexpr int NW = tc_nw(tc_wide(NS, SIDE_T, RN));  // operand-stage warps per TMEM lane quarter
   constexpr int KW = TC_KC / NW;                    // K values of a slab converted by one warp
   // project_T: a stage holds 128 rows of KB*32 (+4) floats, KB*128 + 16 bytes apart: TMA fetches them as 128 long
   // pieces (the engine's cost is per piece, about 7 cycles, whatever its length), one thread then reads one row, and
@@ -133,7 +139,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t a_col0 = (NS >= 2 ? 2 : 1) * p.dcols;  // first TMEM column of the A-operand ring
+  const uint32_t a_col0 = (FL ? 2 : 1) * p.dcols;  // first TMEM column of the A-operand ring
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -170,7 +176,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const int st = pp.st;
         uint32_t d_tmem = tmem_base;
         bool first = c == 0;
-        if (NS >= 2) {
+        if (FL) {
           const int buf = g & 1;
           first = cg == 0;
           if (first) mbar_wait(&dempty[buf], (((uint32_t)g >> 1) & 1) ^ 1);  // registers hold what this buffer had
@@ -179,7 +185,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         mbar_wait(&full[st], pp.ph);
         mbar_wait(&aready[st], pp.ph);
         tc_fence_after();
-        const bool group_end = NS >= 2 && (cg + 1 == FLUSH_STAGES || c == nchunks - 1);
+        const bool group_end = FL && (cg + 1 == FLUSH_STAGES || c == nchunks - 1);
         if (elect_one()) {
           const uint32_t a_hi = tmem_base + a_col0 + st * ACOLS;
           const uint32_t b0 = smem_u32(bs + (size_t)st * BPART * KB * bbytes);
@@ -198,10 +204,10 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           }
           mma_commit(&empty[st]);
           if (group_end) mma_commit(&dfull[g & 1]);
-          if (NS == 1 && c == nchunks - 1) mma_commit(&dfull[0]);
+          if (!FL && c == nchunks - 1) mma_commit(&dfull[0]);
         }
         __syncwarp();
-        if (NS >= 2) {
+        if (FL) {
           if (group_end) { ++g; cg = 0; } else { ++cg; }
         }
       }
@@ -230,7 +236,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       }
     }
 
-    constexpr int ACCN = NS >= 2 ? 128 / NW : 1;
+    constexpr int ACCN = FL ? 128 / NW : 1;
     const int cw = lp / NW;      // accumulator columns of this warp: [part*cw, +cw)
     const int groups = cw >> 2;  // in groups of 4
     float acc[ACCN];
@@ -249,7 +255,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           float v[4];
           tmem_ld4(tmem_base + lane_addr + buf * p.dcols + part * cw + gi * 4, v);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc[(NS >= 2 ? gi * 4 + e : 0)] += v[e];
+          for (int e = 0; e < 4; ++e) acc[(FL ? gi * 4 + e : 0)] += v[e];
         }
       }
       tc_fence_before();
@@ -261,7 +267,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     Pipe pp;
     for (int c = 0; c < nchunks; ++c, pp.advance(stages)) {
       const int st = pp.st;
-      if (NS >= 2 && next_flush < nflush && c >= (next_flush + 1) * FLUSH_STAGES + 1) flush(next_flush++);
+      if (FL && next_flush < nflush && c >= (next_flush + 1) * FLUSH_STAGES + 1) flush(next_flush++);
       // project_S: a NaN only spoils the row of D of its own feature (dropped in the epilogue if the feature is
       // invalid), except in samples that are NaN throughout: only stages holding such a sample test every value
       const bool check = SIDE_T || (p.chunk_flags != nullptr && p.chunk_flags[c] != 0);
@@ -327,7 +333,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           for (int r = 0; r < KW; ++r) {
             if (NS >= 2) {
               hi[r] = __float_as_uint(v[r]) & 0xffffe000u;
-              lo[r] = to_tf32(v[r] - __uint_as_float(hi[r]));  // rounded: the hardware would truncate
+              lo[r] = __float_as_uint(v[r] - __uint_as_float(hi[r]));  // the hardware truncates it: -2^-22, see DESIGN.md
             } else {
               hi[r] = RN ? to_tf32(v[r]) : __float_as_uint(v[r]);  // the tensor core reads the upper 19 bits
             }
@@ -351,7 +357,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
               v = (fabsf(v) <= 3.4028234e38f) ? v * da[e] : 0.f;
               if (NS >= 2) {
                 hi[cc * 4 + e] = __float_as_uint(v) & 0xffffe000u;
-                lo[cc * 4 + e] = to_tf32(v - __uint_as_float(hi[cc * 4 + e]));
+                lo[cc * 4 + e] = __float_as_uint(v - __uint_as_float(hi[cc * 4 + e]));
               } else {
                 hi[cc * 4 + e] = RN ? to_tf32(v) : __float_as_uint(v);
               }
@@ -368,7 +374,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
 
     // ---- epilogue: D (128 x lp fp32: TMEM for x1, registers for x3) -> global
-    if (NS >= 2) {
+    if (FL) {
       while (next_flush < nflush) flush(next_flush++);
     } else {
       mbar_wait(&dfull[0], 0);
@@ -440,9 +446,9 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       if (gi < groups) {
         const int j0 = part * cw + gi * 4;
         float v[4];
-        if (NS >= 2) {
+        if (FL) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] = acc[(NS >= 2 ? gi * 4 + e : 0)];
+          for (int e = 0; e < 4; ++e) v[e] = acc[(FL ? gi * 4 + e : 0)];
         } else {
           tmem_ld4(tmem_base + lane_addr + j0, v);
         }
@@ -630,16 +636,16 @@ struct Shape {
   uint32_t tmem_cols;
   size_t smem;
 };
-static Shape pick_shape(int lp, int ns, bool side_t, int kb) {
+static Shape pick_shape(int lp, int ns, bool side_t, int kb, bool rn = false) {
   Shape sh;
   const int npart = ns >= 2 ? 2 : 1, bpart = ns == 3 ? 2 : 1;
-  const bool two_ctas = !side_t && ns == 1;  // project_S x1: two CTAs per SM share the 512 TMEM columns
+  const bool two_ctas = !side_t && ns == 1 && !rn;  // project_S x1: two CTAs per SM share the 512 TMEM columns
   const int xb = side_t ? TC_TILE * (kb * 128 + 16) : TC_XBYTES;
   const int per_stage = xb + lp * TC_KC * 4 * bpart * kb + (side_t ? kb * 256 : 0);
   sh.kb = kb;
   sh.dcols = (int)round_up(lp, 32);
   sh.tmem_cols = two_ctas ? 256 : 512;
-  const int ring = (int)sh.tmem_cols - (ns >= 2 ? 2 : 1) * sh.dcols;
+  const int ring = (int)sh.tmem_cols - ((ns >= 2 || rn) ? 2 : 1) * sh.dcols;
   const int by_tmem = ring / (TC_KC * kb * npart);
   const int budget = (two_ctas ? 110 : 222) * 1024 - 2048;
   int st = budget / per_stage;
@@ -649,14 +655,14 @@ static Shape pick_shape(int lp, int ns, bool side_t, int kb) {
   sh.smem = (size_t)(st > 0 ? st : 1) * per_stage + 1024 /*alignment*/ + 256 /*barriers*/;
   return sh;
 }
-static Shape pick_shape_T(int lp, int ns, int64_t S, int64_t ldx) {
+static Shape pick_shape_T(int lp, int ns, int64_t S, int64_t ldx, bool rn = false) {
   int kb = env_int("XEOFS_TC_KB", 2);
   if (kb != 1 && kb != 2 && kb != 4) kb = 2;
   (void)S; (void)ldx;
-  Shape sh = pick_shape(lp, ns, true, kb);
+  Shape sh = pick_shape(lp, ns, true, kb, rn);
   while (sh.stages < 2 && kb > 1) {
     kb >>= 1;
-    sh = pick_shape(lp, ns, true, kb);
+    sh = pick_shape(lp, ns, true, kb, rn);
   }
   return sh;
 }
@@ -666,9 +672,10 @@ struct TGeom {
   int chunks_total, chunks_per_cta, splits;
 };
 // cap: the longest K range (in 32-wide slabs) one TMEM accumulator may sum before its truncating adds show: 0 = no cap
-// (the 3xTF32 / 2xTF32 kernels flush into fp32 registers every TC_FLUSH slabs), 1024 for the power-iteration products
-// (a bias of ~1e-4 that only rescales the iterate), 64 for XEOFS_ALGO_TF32X1R (~5e-6)
-static int t_cap(int algo) { return algo_ns(algo) >= 2 ? 0 : algo_rn(algo) ? 64 : 1024; }
+// (the 3xTF32 / 2xTF32 / rounded-TF32 kernels flush into fp32 registers every TC_FLUSH slabs), 1024 for the
+// power-iteration products
+// (a bias of ~1e-4 that only rescales the iterate)
+static int t_cap(int algo) { return (algo_ns(algo) >= 2 || algo_rn(algo)) ? 0 : 1024; }
 static TGeom t_geometry(int64_t T, int64_t S, int cap, int kb) {
   TGeom g;
   g.t_tiles = ceil_div(T, TC_TILE);
@@ -708,7 +715,7 @@ template <int NS, bool SIDE_T, int KB, bool RN = false>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p, dim3 grid,
                      size_t smem, cudaStream_t stream) {
   XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<NS, SIDE_T, KB, false, RN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  project_tc_kernel<NS, SIDE_T, KB, false, RN><<<grid, tc_threads(NS), smem, stream>>>(mx, mh, ml, p);
+  project_tc_kernel<NS, SIDE_T, KB, false, RN><<<grid, tc_threads(tc_wide(NS, SIDE_T, RN)), smem, stream>>>(mx, mh, ml, p);
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
 }
@@ -744,7 +751,7 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
     rc = make_map2(&ml, Wlo, 256, (Tpad / TC_KC) * (lp / 8), 256, 256, lp / 8, false);
     if (rc) return rc;
   }
-  const Shape sh = pick_shape(lp, ns, false, 1);
+  const Shape sh = pick_shape(lp, ns, false, 1, algo_rn(algo));
   TcParams p{};
   p.T = T; p.S = S; p.lp = lp;
   p.stages = sh.stages; p.dcols = sh.dcols; p.tmem_cols = sh.tmem_cols;
@@ -815,7 +822,7 @@ int project_S_stats_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const 
   p.scalars_out = scalars; p.row_delta = row_delta; p.base_nan = base_nan;
   dim3 grid((unsigned)ceil_div(S, TC_TILE));
   XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<1, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
-  project_tc_kernel<1, false, 1, true><<<grid, tc_threads(1), sh.smem, stream>>>(mx, mh, mh, p);
+  project_tc_kernel<1, false, 1, true><<<grid, tc_threads(false), sh.smem, stream>>>(mx, mh, mh, p);
   XB_LAUNCH_CHECK();
   row_nan_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, stream>>>(row_delta, base_nan, T, row_nan);
   XB_LAUNCH_CHECK();
@@ -828,7 +835,7 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   (void)workspace_bytes;
   const int lp = (int)lpad(l);
   const int ns = algo_ns(algo);
-  const Shape sh = pick_shape_T(lp, ns, S, ldx);
+  const Shape sh = pick_shape_T(lp, ns, S, ldx, algo_rn(algo));
   XB_CHECK_ARG(sh.stages >= 1, "project_T: no pipeline shape fits lp=%d", lp);
   const int kb = sh.kb;
   const TGeom g = t_geometry(T, S, t_cap(algo), kb);

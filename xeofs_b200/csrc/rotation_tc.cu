@@ -43,7 +43,7 @@ struct VtParams {
   int k1;         // K of GEMM1 (m rounded up to 8)
   int stages;
   int ntiles;
-  int flags;      // debug: 1 = SBO of the MN-major descriptor 1024 instead of 512, 4 = print the first tile
+  int flags;      // debug: 1 = SBO of the MN-major descriptor 1024 instead of 512
   const float* rhi;  // [128][128]: rhi[j'][i] = TF32 bits of (float)R[i][j']
   const float* rlo;  // [128][128]: remainder
   double* gpart;     // [grid][128][ng]
@@ -267,8 +267,6 @@ varimax_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
       const uint32_t col = b * VT_TS + h * 16;
       float v[16];
       tmem_ld16(tmem_base + lane_addr + VT_COL_D1 + col, v);
-      if ((p.flags & 4) && i == 0 && blockIdx.x == 0 && h == 0 && q == 0 && lane < 3)
-        printf("D1[j'=%d][s=0..3] = %g %g %g %g\n", row, v[0], v[1], v[2], v[3]);
       float w2 = 0.f;
       uint32_t fh[16], fl[16];
 #pragma unroll
@@ -294,8 +292,6 @@ varimax_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
       for (int gi = 0; gi < NH / 8; ++gi) {
         float v[8];
         tmem_ld8(tmem_base + lane_addr + VT_COL_G + h * NH + gi * 8, v);
-        if ((p.flags & 4) && j == 0 && gi == 0 && blockIdx.x == 0 && h == 0 && q == 0 && lane < 3)
-          printf("G'[j'=%d][i=0..3] = %g %g %g %g\n", row, v[0], v[1], v[2], v[3]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[gi * 8 + e] += (double)v[e];
       }
