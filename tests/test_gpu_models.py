@@ -85,6 +85,33 @@ def test_mca_rotator_matches_oracle(power):
         np.testing.assert_allclose(sc.values / scale, osc / scale, atol=2e-3)
 
 
+def test_bootstrapper_matches_oracle():
+    """EOFBootstrapper (validation/bootstrapper.py:56-135) on the device: resampled fits + projection of the original
+    samples against the numpy restatement, members seeded on both sides."""
+    import xeofs_b200 as xb
+    from oracle import bootstrap as oboot
+    T, nlat, nlon, k, nb = 300, 40, 50, 6, 3
+    X = planted(T, nlat * nlon, 2 * k, seed=31).reshape(T, nlat, nlon)
+    X[:, 5, 7] = np.nan
+    coords = {"lat": np.linspace(70, -70, nlat), "lon": np.arange(nlon) * 5.0}
+    kw = dict(n_modes=k, use_coslat=True, random_state=1)
+    m = xb.single.EOF(**kw).fit(xb.DataArray(X, DIMS, coords), dim="time")
+    o = oeof.eof_fit(X, DIMS, "time", coords=coords, **kw)
+    b = xb.validation.EOFBootstrapper(n_bootstraps=nb, seed=5, random_state=2).fit(m)
+    ob = oboot.eof_bootstrap(o["A"], o["scores"], k, n_bootstraps=nb, seed=5, random_state=2)
+    np.testing.assert_allclose(b.explained_variance().values, ob["explained_variance"], rtol=1e-4)
+    np.testing.assert_allclose(b.total_variance().values, ob["total_variance"], rtol=1e-5)
+    valid = ~np.isnan(X[0]).reshape(-1)
+    for i, c in enumerate(b.components()):
+        V = c.values.reshape(-1, k)
+        np.testing.assert_array_equal(np.isnan(V).any(axis=1), ~valid)
+        dots = (V[valid] * ob["components"][i]).sum(axis=0)
+        assert (dots > 1 - 1e-4).all(), dots
+    for i, sc in enumerate(b.scores()):
+        scale = np.abs(ob["scores"][i]).max(axis=0)
+        np.testing.assert_allclose(sc.values / scale, ob["scores"][i] / scale, atol=2e-3)
+
+
 def test_mca_total_squared_covariance_wide_fields():
     """cpcca.py:991-1000 at a width (S >= 2^16) where the sample Gram matrices take the single rounded TF32 product
     (XEOFS_ALGO_TF32X1R): sum |C|^2 = <A1 A1^T, A2 A2^T> / (n-1)^2 against fp64 torch on the preprocessed fields."""

@@ -192,6 +192,32 @@ def test_rotator_host_logic():
                                        rtol=1e-5)
 
 
+def test_bootstrapper_host_logic():
+    """validation/bootstrapper.py:56-135 against its numpy restatement (members seeded for reproducibility)."""
+    import xeofs_b200 as xb
+    from oracle import bootstrap as oboot
+    T, nlat, nlon, k, nb = 120, 10, 12, 4, 3
+    X = planted(T, nlat * nlon, 2 * k, seed=9).reshape(T, nlat, nlon)
+    X[:, 2, 3] = np.nan
+    coords = {"lat": np.linspace(50, -50, nlat), "lon": np.arange(nlon) * 10.0}
+    kw = dict(n_modes=k, use_coslat=True, random_state=1)
+    m = xb.single.EOF(ops=TorchCpuOps(), **kw).fit(xb.DataArray(X, DIMS, coords), dim="time")
+    o = oeof.eof_fit(X, DIMS, "time", coords=coords, **kw)
+    b = xb.validation.EOFBootstrapper(n_bootstraps=nb, seed=5, random_state=2).fit(m)
+    ob = oboot.eof_bootstrap(o["A"], o["scores"], k, n_bootstraps=nb, seed=5, random_state=2)
+    np.testing.assert_allclose(b.explained_variance().values, ob["explained_variance"], rtol=1e-4)
+    np.testing.assert_allclose(b.total_variance().values, ob["total_variance"], rtol=1e-5)
+    valid = o["fitted"]["is_valid_feature"] if "fitted" in o else ~np.isnan(X[0]).reshape(-1)
+    for i, c in enumerate(b.components()):
+        V = c.values.reshape(-1, k)
+        np.testing.assert_array_equal(np.isnan(V).any(axis=1), ~valid)
+        dots = (V[valid] * ob["components"][i]).sum(axis=0)
+        assert (dots > 1 - 1e-4).all(), dots
+    for i, sc in enumerate(b.scores()):
+        scale = np.abs(ob["scores"][i]).max(axis=0)
+        np.testing.assert_allclose(sc.values / scale, ob["scores"][i] / scale, atol=1e-3)
+
+
 # ---------------------------------------------------------------- feature sharding over gloo, world size 2
 _WORKER = r'''
 import os, sys
