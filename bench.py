@@ -203,6 +203,12 @@ def run_ours(args):
     coords = {"lat": lat_all[lat0:lat0 + lat_rows], "lon": np.arange(n_lon) * (360.0 / n_lon)}
     dims = ("time", "lat", "lon")
     X = planted_field_device(T, S_local, 2 * k, seed=1 + rank, device=device).reshape(T, lat_rows, n_lon)
+    if args.land_frac > 0:
+        # a land mask: a fixed fraction of the grid points is NaN at every time step (the Sanitizer's full-dimensional
+        # NaN case, sanitizer.py:46-56); every 1/frac-th block of 64 points
+        mask = (torch.arange(S_local, device=device) // 64) % max(2, int(round(1.0 / args.land_frac))) == 0
+        X.view(T, -1)[:, mask] = float("nan")
+        del mask
     bytes_local = T * S_local * 4
     total_bytes = T * n_lat_total * n_lon * 4
 
@@ -334,7 +340,8 @@ def run_ours(args):
         "config": {"workload": f"{args.workload}: EOF n_modes={k} n_iter={n_iter} randomized SVD on "
                                f"{T}x({n_lat_total}x{n_lon}) fp32 ({total_bytes / 1e9:.2f} GB), "
                                f"{'feature-sharded over %d GPUs' % world if world > 1 else '1 GPU'}",
-                   "l2": "inputs larger than L2 (no flush needed)", "algo": args.algo, "extra": kw},
+                   "l2": "inputs larger than L2 (no flush needed)", "algo": args.algo,
+                   "extra": dict(kw, **({"land_frac": args.land_frac} if args.land_frac > 0 else {}))},
         "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(),
         "singular_values_head": [float(v) for v in s_vals[:3]],
     }
@@ -355,6 +362,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--land-frac", type=float, default=0.0, help="fraction of grid points that are NaN at every step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print(f"note: warmup {args.warmup} < 3", file=sys.stderr)

@@ -457,7 +457,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             // an invalid feature (dscale 0) gives a zero row even if its accumulator holds NaN
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              p.out[(int64_t)(j0 + e) * p.ldo + rrow] = ds != 0.f ? fmaf(ds, v[e], cs * p.wsum[j0 + e]) : 0.f;
+              p.out[(int64_t)(j0 + e) * p.ldo + rrow] =
+                  ds != 0.f ? fmaf(ds, v[e], (STATS || p.ccorr) ? cs * p.wsum[j0 + e] : 0.f) : 0.f;
           }
         } else {
           *reinterpret_cast<float4*>(dstT + j0) = make_float4(v[0], v[1], v[2], v[3]);
@@ -732,8 +733,11 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   uint8_t* flags = ws + align256(lp * 4);
   float* Whi = (float*)(flags + align256(Tpad / TC_KC));
   float* Wlo = ns == 3 ? (float*)((uint8_t*)Whi + align256(lp * Tpad * 4)) : nullptr;
-  int rc = launch_colsum(W, T, ldw, lp, row_valid, wsum, stream);
-  if (rc) return rc;
+  int rc = XEOFS_OK;
+  if (ccorr) {  // the rank-1 term ccorr[s] * colsum(W)[j] exists only for un-centred fields
+    rc = launch_colsum(W, T, ldw, lp, row_valid, wsum, stream);
+    if (rc) return rc;
+  }
   if (row_valid) {
     chunk_flags_kernel<<<(unsigned)ceil_div(Tpad / TC_KC, 128), 128, 0, stream>>>(row_valid, T, (int)(Tpad / TC_KC), flags);
     XB_LAUNCH_CHECK();
