@@ -71,3 +71,25 @@ def eof_inverse_transform(result, scores):
     p = result["params"]
     rec = scores @ result["components_2d"].conj().T
     return pp.inverse_scale(rec, result["fitted"], p["center"], p["standardize"], p["use_coslat"])
+
+
+def eof_fit_list(Xs, dims_list, sample_dims, coords_list=None, n_modes=2, center=True, standardize=False,
+                 use_coslat=False, check_nans=True, weights=None, random_state=None, solver="auto", solver_kwargs=None):
+    """EOF.fit on a LIST of arrays (DataList): every array goes through its own Scaler / Stacker / Sanitizer
+    (preprocessing/preprocessor.py:208-228), the 2D matrices are concatenated along the feature axis
+    (preprocessing/concatenator.py:58-81) and decomposed as one; the components are split back per array."""
+    coords_list = coords_list or [None] * len(Xs)
+    weights = weights or [None] * len(Xs)
+    fits = [pp.preprocess(X, d, sample_dims, coords=c, center=center, standardize=standardize, use_coslat=use_coslat,
+                          weights=w, check_nans=check_nans)
+            for X, d, c, w in zip(Xs, dims_list, coords_list, weights)]
+    A = np.concatenate([f["A"] for f in fits], axis=1)
+    total_variance = A.var(axis=0, ddof=1).sum()
+    U, s, V = decompose(A, n_modes=n_modes, solver=solver, random_state=random_state, solver_kwargs=solver_kwargs)
+    n = A.shape[0]
+    offs = np.concatenate([[0], np.cumsum([f["A"].shape[1] for f in fits])])
+    return {
+        "A": A, "fitted": fits,
+        "components_2d": [V[a:b] for a, b in zip(offs[:-1], offs[1:])],
+        "scores": U * s, "singular_values": s, "explained_variance": s**2 / (n - 1), "total_variance": total_variance,
+    }

@@ -85,6 +85,31 @@ def test_mca_rotator_matches_oracle(power):
         np.testing.assert_allclose(sc.values / scale, osc / scale, atol=2e-3)
 
 
+@pytest.mark.parametrize("shapes", [((40, 50), (30, 20)), ((8, 9), (5, 7))])
+def test_eof_list_input_matches_oracle(shapes):
+    """EOF.fit on a list of arrays (two variables, different grids and units): concatenated along the feature axis
+    (preprocessing/preprocessor.py:208-228); tensor-core path for the aligned case, fp32 SIMT for the ragged one."""
+    import xeofs_b200 as xb
+    T, k = 200, 5
+    (a1, b1), (a2, b2) = shapes
+    full = planted(T, a1 * b1 + a2 * b2, 2 * k, seed=13)
+    X1 = full[:, : a1 * b1].reshape(T, a1, b1).copy()
+    X2 = (3.0 * full[:, a1 * b1:] + 1000.0).reshape(T, a2, b2).astype(np.float32)
+    X1[:, 1, 2] = np.nan
+    c1 = {"lat": np.linspace(40, -40, a1), "lon": np.arange(b1) * 1.0}
+    c2 = {"lat": np.linspace(30, -30, a2), "lon": np.arange(b2) * 2.0}
+    kw = dict(n_modes=k, standardize=True, use_coslat=True, random_state=4)
+    o = oeof.eof_fit_list([X1, X2], [DIMS, DIMS], "time", coords_list=[c1, c2], **kw)
+    m = xb.single.EOF(**kw).fit([xb.DataArray(X1, DIMS, c1), xb.DataArray(X2, DIMS, c2)], dim="time")
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    dots = 0.0
+    for c, oc, f in zip(m.components(), o["components_2d"], o["fitted"]):
+        V = c.values.reshape(-1, k)
+        np.testing.assert_array_equal(np.isnan(V).any(axis=1), ~f["is_valid_feature"])
+        dots = dots + (V[f["is_valid_feature"]] * oc).sum(axis=0)
+    assert (np.abs(dots) > 1 - 1e-4).all(), dots
+
+
 def test_bootstrapper_matches_oracle():
     """EOFBootstrapper (validation/bootstrapper.py:56-135) on the device: resampled fits + projection of the original
     samples against the numpy restatement, members seeded on both sides."""

@@ -192,6 +192,42 @@ def test_rotator_host_logic():
                                        rtol=1e-5)
 
 
+def test_eof_list_input_host_logic():
+    """A list of arrays (two variables on different grids): each scaled on its own, concatenated along the feature
+    axis (preprocessing/preprocessor.py:208-228, concatenator.py:58-81); components come back one array per input."""
+    import xeofs_b200 as xb
+    T, k = 150, 4
+    full = planted(T, 8 * 9 + 5 * 7, 2 * k, seed=12)
+    X1 = full[:, :72].reshape(T, 8, 9).copy()
+    X2 = (3.0 * full[:, 72:] + 1000.0).reshape(T, 5, 7).astype(np.float32)
+    X1[:, 1, 2] = np.nan
+    c1 = {"lat": np.linspace(40, -40, 8), "lon": np.arange(9) * 10.0}
+    c2 = {"lat": np.linspace(30, -30, 5), "lon": np.arange(7) * 20.0}
+    kw = dict(n_modes=k, standardize=True, use_coslat=True, random_state=4)
+    o = oeof.eof_fit_list([X1, X2], [DIMS, DIMS], "time", coords_list=[c1, c2], **kw)
+    m = xb.single.EOF(ops=TorchCpuOps(), **kw).fit([xb.DataArray(X1, DIMS, c1), xb.DataArray(X2, DIMS, c2)], dim="time")
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    np.testing.assert_allclose(m.explained_variance().values, o["explained_variance"], rtol=1e-4)
+    comps = m.components()
+    assert isinstance(comps, list) and [c.shape for c in comps] == [(8, 9, k), (5, 7, k)]
+    dots = 0.0
+    for c, oc, f in zip(comps, o["components_2d"], o["fitted"]):
+        V = c.values.reshape(-1, k)
+        np.testing.assert_array_equal(np.isnan(V).any(axis=1), ~f["is_valid_feature"])
+        dots = dots + (V[f["is_valid_feature"]] * oc).sum(axis=0)
+    assert (np.abs(dots) > 1 - 1e-5).all(), dots
+    sc = m.scores().values
+    scale = np.abs(o["scores"]).max(axis=0)
+    np.testing.assert_allclose(np.abs(sc) / scale, np.abs(o["scores"]) / scale, atol=1e-3)
+    # transform of the training data reproduces the scores; inverse_transform returns one array per input
+    np.testing.assert_allclose(m.transform([xb.DataArray(X1, DIMS, c1), xb.DataArray(X2, DIMS, c2)]).values, sc,
+                               rtol=1e-3, atol=1e-3 * np.abs(sc).max())
+    rec = m.inverse_transform(m.scores())
+    assert isinstance(rec, list) and rec[0].shape == X1.shape and rec[1].shape == X2.shape
+    with pytest.raises(ValueError, match="same sample"):
+        xb.single.EOF(ops=TorchCpuOps(), **kw).fit([xb.DataArray(X1, DIMS, c1), xb.DataArray(X2[:-1], DIMS, c2)], dim="time")
+
+
 def test_bootstrapper_host_logic():
     """validation/bootstrapper.py:56-135 against its numpy restatement (members seeded for reproducibility)."""
     import xeofs_b200 as xb

@@ -14,6 +14,34 @@ from . import _labels as L
 from ._engine import NO_COMM, fit_field
 
 
+def _new_field(ops, comm, ff, X2, check_nans):
+    """Unseen data behind the fitted scaling vectors + the Sanitizer's checks on it (sanitizer.py:108-122)."""
+    from ._cuda_ops import Field
+
+    f = ff.field
+    new = Field(X2, f.pivot, f.dscale, f.ccorr, f.valid, f.mean, f.std, None)
+    valid_sample = None
+    if check_nans:
+        st = ops.col_stats(X2)
+        new_valid = st["cnt"] > 0
+        row_nan = st["row_nan"].to(torch.int64)
+        if comm.active:
+            comm.sum_(row_nan)
+        mism = (new_valid != ff.valid.bool()).any().to(torch.int32)
+        if comm.active:
+            comm.max_(mism)
+        if bool(mism.item()):
+            raise ValueError("Input data had NaN features in different locations than the original data.")
+        n_invalid = ff.S_global - ff.n_features
+        ok = (row_nan == n_invalid) | (row_nan == ff.S_global)
+        if not bool(ok.all().item()):
+            raise ValueError("Input data contains partial NaN entries, which will cause the the SVD to fail.")
+        valid_sample = row_nan < ff.S_global
+        if not bool(valid_sample.all().item()):
+            new.row_valid = valid_sample.to(torch.uint8)
+    return new, valid_sample
+
+
 class Preprocessor:
     def __init__(self, ops, with_center=True, with_std=False, with_coslat=False, check_nans=True,
                  sample_name="sample", feature_name="feature", comm=NO_COMM):
@@ -52,8 +80,8 @@ class Preprocessor:
         return t2, sample_shape, feature_shape
 
     # ------------------------------------------------------------------ fit
-    def fit_transform(self, X, sample_dims, weights=None, overlap=None, first=None):
-        """``first``: callable (T, S) -> (W, l) or None, the sketch for the fused statistics + first product pass."""
+    def _prepare(self, X, sample_dims, weights=None):
+        """Labels + stacking + the per-feature weight vector (coslat * weights, fp64, host) of one array."""
         data, dims, coords, self.as_xarray = L.unpack(X)
         self._dim = sample_dims
         X2, self.sample_shape, self.feature_shape = self._to_2d(data, dims, fit=True)
@@ -75,6 +103,11 @@ class Preprocessor:
                 shape[self.feature_dims.index(d)] = w.shape[i]
             w = np.broadcast_to(w.reshape(shape).astype(np.float64), self.feature_shape)
             featw = w if featw is None else featw * w
+        return X2, featw
+
+    def fit_transform(self, X, sample_dims, weights=None, overlap=None, first=None):
+        """``first``: callable (T, S) -> (W, l) or None, the sketch for the fused statistics + first product pass."""
+        X2, featw = self._prepare(X, sample_dims, weights)
         self.featw_host = None if featw is None else np.ascontiguousarray(featw.reshape(-1))
         featw_dev = None if featw is None else self.ops.to_device(self.featw_host, torch.float64)
         self.fitted = fit_field(self.ops, X2, featw_dev, center=self.with_center, standardize=self.with_std,
@@ -85,36 +118,13 @@ class Preprocessor:
     # ------------------------------------------------------------------ transform of unseen data
     def transform(self, X):
         """preprocessor.py:232-259: re-apply the fitted scaling; sanitizer.py:108-113 NaN-pattern check."""
-        from ._cuda_ops import Field
-
         if self.fitted is None:
             raise ValueError("The preprocessor has not been fitted.")
         data, dims, coords, _ = L.unpack(X)
         X2, sample_shape, feature_shape = self._to_2d(data, dims, fit=False)
         if feature_shape != self.feature_shape:
             raise ValueError(f"Feature shape {feature_shape} differs from the fitted one {self.feature_shape}.")
-        ff = self.fitted
-        f = ff.field
-        new = Field(X2, f.pivot, f.dscale, f.ccorr, f.valid, f.mean, f.std, None)
-        valid_sample = None
-        if self.check_nans:
-            st = self.ops.col_stats(X2)
-            new_valid = st["cnt"] > 0
-            row_nan = st["row_nan"].to(torch.int64)
-            if self.comm.active:
-                self.comm.sum_(row_nan)
-            mism = (new_valid != ff.valid.bool()).any().to(torch.int32)
-            if self.comm.active:
-                self.comm.max_(mism)
-            if bool(mism.item()):
-                raise ValueError("Input data had NaN features in different locations than the original data.")
-            n_invalid = ff.S_global - ff.n_features
-            ok = (row_nan == n_invalid) | (row_nan == ff.S_global)
-            if not bool(ok.all().item()):
-                raise ValueError("Input data contains partial NaN entries, which will cause the the SVD to fail.")
-            valid_sample = row_nan < ff.S_global
-            if not bool(valid_sample.all().item()):
-                new.row_valid = valid_sample.to(torch.uint8)
+        new, valid_sample = _new_field(self.ops, self.comm, self.fitted, X2, self.check_nans)
         sample_coords = {d: coords[d] for d in self.sample_dims if d in coords}
         return new, sample_shape, sample_coords, valid_sample
 
@@ -157,3 +167,88 @@ class Preprocessor:
         if isinstance(arr, torch.Tensor):
             arr = arr.cpu().numpy()
         return L.wrap(arr, self.dims_in, coords, name, self.as_xarray)
+
+
+class _PartFit:
+    """What a part's label bookkeeping reads from the fit: its slice of the feature mask and the sample mask."""
+
+    def __init__(self, valid, valid_sample):
+        self.valid, self.valid_sample = valid, valid_sample
+
+
+class MultiPreprocessor:
+    """A LIST of arrays as input (the reference's DataList): every array is scaled and weighted on its own, stacked,
+    and the 2D matrices are concatenated along the feature axis (preprocessing/preprocessor.py:208-228,
+    concatenator.py:58-81).  Per-feature statistics make "on its own" and "after concatenation" the same arithmetic,
+    so the concatenated field goes through the same single pass as one array; feature-shaped results come back as one
+    array per input.  All arrays must share the sample dimensions and their lengths."""
+
+    def __init__(self, ops, **kw):
+        self.ops, self.kw = ops, kw
+        self.comm = kw.get("comm", NO_COMM)
+        self.check_nans = kw.get("check_nans", True)
+        self.parts, self.fitted = [], None
+
+    def fit_transform(self, Xs, sample_dims, weights=None, overlap=None, first=None):
+        if self.comm.active:
+            raise NotImplementedError("list inputs are not supported together with distributed=True")
+        ws = list(weights) if isinstance(weights, (list, tuple)) else [weights] * len(Xs)
+        if len(ws) != len(Xs):
+            raise ValueError("weights must be a list with one entry (or None) per input array")
+        mats, fws = [], []
+        self.parts = []
+        for Xi, wi in zip(Xs, ws):
+            p = Preprocessor(self.ops, **self.kw)
+            X2, fw = p._prepare(Xi, sample_dims, wi)
+            self.parts.append(p)
+            mats.append(X2)
+            fws.append(fw)
+        shapes = {p.sample_shape for p in self.parts}
+        if len(shapes) != 1:
+            raise ValueError(f"All arrays must have the same sample dimensions; found shapes {sorted(shapes)}.")
+        sizes = [int(m.shape[1]) for m in mats]
+        self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(int)
+        X2 = torch.cat(mats, dim=1)
+        del mats
+        featw = None
+        if any(fw is not None for fw in fws):
+            featw = np.concatenate([np.ones(n) if fw is None else np.ascontiguousarray(fw.reshape(-1))
+                                    for fw, n in zip(fws, sizes)])
+        self.featw_host = featw
+        featw_dev = None if featw is None else self.ops.to_device(featw, torch.float64)
+        p0 = self.parts[0]
+        self.fitted = fit_field(self.ops, X2, featw_dev, center=p0.with_center, standardize=p0.with_std,
+                                check_nans=self.check_nans, comm=self.comm, overlap=overlap,
+                                first=first(int(X2.shape[0]), int(X2.shape[1])) if first is not None else None)
+        for p, a, b in zip(self.parts, self.offsets[:-1], self.offsets[1:]):
+            p.fitted = _PartFit(self.fitted.valid[a:b], self.fitted.valid_sample)
+        self.as_xarray = p0.as_xarray
+        self.sample_shape, self.sample_dims = p0.sample_shape, p0.sample_dims
+        return self.fitted
+
+    def transform(self, Xs):
+        if self.fitted is None:
+            raise ValueError("The preprocessor has not been fitted.")
+        if not isinstance(Xs, (list, tuple)) or len(Xs) != len(self.parts):
+            raise ValueError(f"Expected a list of {len(self.parts)} arrays.")
+        mats = []
+        for p, Xi in zip(self.parts, Xs):
+            data, dims, coords, _ = L.unpack(Xi)
+            X2, sample_shape, feature_shape = p._to_2d(data, dims, fit=False)
+            if feature_shape != p.feature_shape:
+                raise ValueError(f"Feature shape {feature_shape} differs from the fitted one {p.feature_shape}.")
+            mats.append(X2)
+        new, valid_sample = _new_field(self.ops, self.comm, self.fitted, torch.cat(mats, dim=1), self.check_nans)
+        sample_coords = {d: coords[d] for d in self.parts[0].sample_dims if d in coords}
+        return new, sample_shape, sample_coords, valid_sample
+
+    def components_to_nd(self, Vt, k, name="components", nan_invalid=True):
+        return [p.components_to_nd(Vt[:, a:b], k, name, nan_invalid)
+                for p, a, b in zip(self.parts, self.offsets[:-1], self.offsets[1:])]
+
+    def scores_to_nd(self, Sc, k, name="scores", sample_shape=None, sample_coords=None, valid_sample=None):
+        return self.parts[0].scores_to_nd(Sc, k, name, sample_shape, sample_coords, valid_sample)
+
+    def data_to_nd(self, A2d, sample_shape, sample_coords=None, name="reconstructed_data"):
+        return [p.data_to_nd(A2d[:, a:b], sample_shape, sample_coords, name)
+                for p, a, b in zip(self.parts, self.offsets[:-1], self.offsets[1:])]

@@ -14,7 +14,7 @@ from .. import _engine as E
 from .. import _labels as L
 from .._cuda_ops import CudaOps
 from .._lib import lpad
-from .._preprocessor import Preprocessor
+from .._preprocessor import MultiPreprocessor, Preprocessor
 
 
 class EOF:
@@ -34,16 +34,26 @@ class EOF:
         self.attrs = {"model": "EOF analysis", "backend": "xeofs_b200"}
         self.ops = ops if ops is not None else CudaOps(device=device, algo=algo)
         self.comm = E.Comm() if distributed else E.NO_COMM
-        self.preprocessor = Preprocessor(self.ops, with_center=center, with_std=standardize,
-                                         with_coslat=use_coslat, check_nans=check_nans,
-                                         sample_name=sample_name, feature_name=feature_name, comm=self.comm)
+        self._pp_kw = dict(with_center=center, with_std=standardize, with_coslat=use_coslat, check_nans=check_nans,
+                           sample_name=sample_name, feature_name=feature_name, comm=self.comm)
+        self.preprocessor = Preprocessor(self.ops, **self._pp_kw)
         self.data = {}
 
     # ------------------------------------------------------------------ fit
     def fit(self, X, dim, weights=None):
-        L.validate_input_type(X)
-        if weights is not None:
-            L.validate_input_type(weights)
+        if isinstance(X, (list, tuple)):  # DataList: one array per variable, concatenated along the feature axis
+            for a in X:
+                L.validate_input_type(a)
+            for w in (weights if isinstance(weights, (list, tuple)) else []):
+                if w is not None:
+                    L.validate_input_type(w)
+            self.preprocessor = MultiPreprocessor(self.ops, **self._pp_kw)
+        else:
+            L.validate_input_type(X)
+            if weights is not None:
+                L.validate_input_type(weights)
+            if isinstance(self.preprocessor, MultiPreprocessor):
+                self.preprocessor = Preprocessor(self.ops, **self._pp_kw)
         self._predrawn = None
         ff = self.preprocessor.fit_transform(X, dim, weights, first=self._first_sketch)
         self._fit_algorithm(ff)
@@ -148,7 +158,8 @@ class EOF:
     # ------------------------------------------------------------------ transform / inverse_transform
     def transform(self, data, normalized=False):
         """eof.py:123-132 via base_model_single_set.py:180-203: ((new - mean)/std*w)[:, valid] . V."""
-        L.validate_input_type(data)
+        if not isinstance(data, (list, tuple)):
+            L.validate_input_type(data)
         new, sample_shape, sample_coords, valid_sample = self.preprocessor.transform(data)
         Z = self.ops.project_T(new, self._Vt, self.k, algo=self.ops.accurate_algo)
         self.comm.sum_(Z)
