@@ -36,6 +36,7 @@ def mca_fit(
     n_modes=2, standardize=False, use_coslat=False, check_nans=True,
     weights_x=None, weights_y=None,
     random_state=None, solver="auto", solver_kwargs=None,
+    use_pca=False, n_pca_modes=0.999, pca_init_rank_reduction=0.3, pca_random_state=None,
 ):
     """use_pca=False path (the configuration BASELINE.json config 3 is built on; the default
     use_pca=True path is unseeded in the reference, cross/base_model_cross_set.py:165-179)."""
@@ -47,13 +48,26 @@ def mca_fit(
     f2 = pp.preprocess(Y, dims_y, sample_dims, coords=coords_y, center=True, standardize=std[1],
                        use_coslat=cos[1], weights=weights_y, check_nans=chk[1])
     A1, A2 = f1["A"], f2["A"]
+    V1 = V2 = None
+    if use_pca:
+        # cross/base_model_cross_set.py:165-179, 307-308; preprocessing/pca.py:94-131: the fields are replaced by their
+        # projections on the leading principal components (SVD class of linalg/_numpy/_svd.py = decompose(); the
+        # reference leaves its random_state unset, pca_random_state makes this restatement reproducible)
+        _, _, V1 = decompose(A1, n_modes=n_pca_modes, init_rank_reduction=pca_init_rank_reduction,
+                             random_state=pca_random_state)
+        _, _, V2 = decompose(A2, n_modes=n_pca_modes, init_rank_reduction=pca_init_rank_reduction,
+                             random_state=pca_random_state)
+        A1, A2 = A1 @ V1, A2 @ V2
     C = cross_covariance(A1, A2)
     Q1, s, Q2 = decompose(C, n_modes=n_modes, solver=solver, random_state=random_state,
                           solver_kwargs=solver_kwargs)
     tsc = (np.abs(C) ** 2).sum()
     scores1 = A1 @ Q1
     scores2 = A2 @ Q2
+    if use_pca:  # the accessors return the patterns in physical space (pca.py:161-171)
+        Q1, Q2 = V1 @ Q1, V2 @ Q2
     return {
+        "n_pca_modes": None if V1 is None else (V1.shape[1], V2.shape[1]),
         "A1": A1, "A2": A2, "fitted1": f1, "fitted2": f2, "C": C,
         "components1_2d": Q1, "components2_2d": Q2,
         "scores1": scores1, "scores2": scores2,

@@ -40,7 +40,7 @@ def test_mca_matches_explicit_cross_covariance_oracle(shape, kw):
     cx = {"lat": np.linspace(80, -80, n1), "lon": np.arange(S1 // n1) * 1.0}
     cy = {"lat": np.linspace(60, -60, n2), "lon": np.arange(S2 // n2) * 1.0}
     o = omca.mca_fit(X, Y, DIMS, DIMS, "time", coords_x=cx, coords_y=cy, n_modes=k, random_state=3, **kw)
-    m = xb.cross.MCA(n_modes=k, random_state=3, **kw)
+    m = xb.cross.MCA(n_modes=k, random_state=3, use_pca=False, **kw)
     m.fit(xb.DataArray(X, DIMS, cx), xb.DataArray(Y, DIMS, cy), dim="time")
     np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
     np.testing.assert_allclose(m.total_squared_covariance(), o["total_squared_covariance"], rtol=1e-4)
@@ -67,7 +67,7 @@ def test_mca_rotator_matches_oracle(power):
     Y = Y.reshape(T, 20, 37)
     X[:, 3, 5] = np.nan
     o = omca.mca_fit(X, Y, DIMS, DIMS, "time", n_modes=k, random_state=3)
-    m = xb.cross.MCA(n_modes=k, random_state=3, total_squared_covariance=False)
+    m = xb.cross.MCA(n_modes=k, random_state=3, use_pca=False, total_squared_covariance=False)
     m.fit(xb.DataArray(X, DIMS), xb.DataArray(Y, DIMS), dim="time")
     r = xb.cross.MCARotator(n_modes=mr, power=power).fit(m)
     ro = orot.mca_rotator_fit(o["components1_2d"], o["components2_2d"], o["singular_values"], o["scores1"],
@@ -137,6 +137,37 @@ def test_bootstrapper_matches_oracle():
         np.testing.assert_allclose(sc.values / scale, ob["scores"][i] / scale, atol=2e-3)
 
 
+@pytest.mark.parametrize("npm", [0.999, 10])
+def test_mca_default_pca_stage_matches_oracle(npm):
+    """MCA with the reference's default use_pca=True: PCA of both fields from the sample Gram matrices (device) vs the
+    reference's randomized-SVD PCA (oracle, seeded); singular values rtol 1e-4, patterns up to the sign rule."""
+    import xeofs_b200 as xb
+    T, S1, S2, k = 300, 40 * 30, 20 * 36, 5
+    X, Y = _coupled_fields(T, S1, S2, 2 * k, seed=7)
+    X = X.reshape(T, 40, 30)
+    Y = Y.reshape(T, 20, 36)
+    X[:, 3, 5] = np.nan
+    o = omca.mca_fit(X, Y, DIMS, DIMS, "time", n_modes=k, random_state=3, use_pca=True, n_pca_modes=npm,
+                     pca_random_state=1)
+    m = xb.cross.MCA(n_modes=k, random_state=3, n_pca_modes=npm)
+    m.fit(xb.DataArray(X, DIMS), xb.DataArray(Y, DIMS), dim="time")
+    # the 99.9 % cut falls among noise-level modes, where the reference's randomized PCA and the exact one may differ
+    # by a mode or two; an integer n_pca_modes is kept exactly
+    assert all(abs(a - b) <= (2 if isinstance(npm, float) else 0) for a, b in zip(m.n_pca_modes_, o["n_pca_modes"]))
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    np.testing.assert_allclose(m.total_squared_covariance(), o["total_squared_covariance"], rtol=1e-4)
+    c1, c2 = m.components()
+    for c, oc, f in ((c1, o["components1_2d"], o["fitted1"]), (c2, o["components2_2d"], o["fitted2"])):
+        V = c.values.reshape(-1, k)
+        np.testing.assert_array_equal(np.isnan(V).any(axis=1), ~f["is_valid_feature"])
+        dots = (V[f["is_valid_feature"]] * oc).sum(axis=0)
+        assert (dots >= 1 - 1e-4).all(), dots
+    s1, s2 = m.scores()
+    for sc, osc in ((s1, o["scores1"]), (s2, o["scores2"])):
+        scale = np.abs(osc).max(axis=0)
+        np.testing.assert_allclose(sc.values / scale, osc / scale, atol=2e-3)
+
+
 def test_mca_total_squared_covariance_wide_fields():
     """cpcca.py:991-1000 at a width (S >= 2^16) where the sample Gram matrices take the single rounded TF32 product
     (XEOFS_ALGO_TF32X1R): sum |C|^2 = <A1 A1^T, A2 A2^T> / (n-1)^2 against fp64 torch on the preprocessed fields."""
@@ -146,7 +177,7 @@ def test_mca_total_squared_covariance_wide_fields():
     X, Y = _coupled_fields(T, S1, S2, 2 * k, seed=11)
     X = X.reshape(T, 70, 1000)
     Y = Y.reshape(T, 66, 1000)
-    m = xb.cross.MCA(n_modes=k, random_state=3, total_squared_covariance=False)
+    m = xb.cross.MCA(n_modes=k, random_state=3, use_pca=False, total_squared_covariance=False)
     m.fit(xb.DataArray(X, DIMS), xb.DataArray(Y, DIMS), dim="time")
     assert m.ops.sum_algo == _lib.ALGO_TF32X1R
     tsc = m.total_squared_covariance()

@@ -107,7 +107,7 @@ def test_error_conventions():
     with pytest.raises(ValueError, match="latitude"):
         xb.single.EOF(n_modes=2, use_coslat=True, ops=TorchCpuOps()).fit(xb.DataArray(X, ("time", "y", "x")), dim="time")
     with pytest.raises(NotImplementedError):
-        xb.cross.MCA(n_modes=2, use_pca=True, ops=TorchCpuOps())
+        xb.cross.MCA(n_modes=2, use_pca=(True, False), ops=TorchCpuOps())
 
 
 def test_transform_inverse_transform_host_logic():
@@ -130,7 +130,7 @@ def test_mca_host_logic():
     Y = ((U * sig) @ np.linalg.qr(rng.standard_normal((60, 2 * k)))[0].T + 0.01 * rng.standard_normal((T, 60))).astype(np.float32)
     X[:, 5] = np.nan
     o = omca.mca_fit(X, Y, ("time", "x"), ("time", "y"), "time", n_modes=k, random_state=3)
-    m = xb.cross.MCA(n_modes=k, random_state=3, ops=TorchCpuOps())
+    m = xb.cross.MCA(n_modes=k, random_state=3, use_pca=False, ops=TorchCpuOps())
     m.fit(xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")
     np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-5)
     np.testing.assert_allclose(m.total_squared_covariance(), o["total_squared_covariance"], rtol=1e-5)
@@ -139,6 +139,37 @@ def test_mca_host_logic():
     dots = np.abs((v1 * o["components1_2d"]).sum(axis=0))
     assert (dots > 1 - 1e-5).all(), dots
     assert ((c2.values * o["components2_2d"]).sum(axis=0) > 1 - 1e-5).all()
+
+
+def test_mca_pca_stage_host_logic():
+    """use_pca=True (the reference's default): PCA projection of both fields (preprocessing/pca.py:94-131 with the
+    variance cut of linalg/_numpy/_svd.py:214-241), MCA on the scores, patterns mapped back to physical space."""
+    import xeofs_b200 as xb
+    T, k = 150, 4
+    rng = np.random.default_rng(2)
+    U = np.linalg.qr(rng.standard_normal((T, 2 * k)))[0]
+    sig = 100 * 0.7 ** np.arange(2 * k)
+    X = ((U * sig) @ np.linalg.qr(rng.standard_normal((300, 2 * k)))[0].T + 0.01 * rng.standard_normal((T, 300))).astype(np.float32)
+    Y = ((U * sig) @ np.linalg.qr(rng.standard_normal((200, 2 * k)))[0].T + 0.01 * rng.standard_normal((T, 200))).astype(np.float32)
+    X[:, 5] = np.nan
+    for npm in (0.999, 12):
+        o = omca.mca_fit(X, Y, ("time", "x"), ("time", "y"), "time", n_modes=k, random_state=3, use_pca=True,
+                         n_pca_modes=npm, pca_random_state=1)
+        m = xb.cross.MCA(n_modes=k, random_state=3, n_pca_modes=npm, ops=TorchCpuOps())   # use_pca defaults to True
+        m.fit(xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")
+        # the 99.9 % cut falls among noise-level modes, where the reference's randomized PCA and the exact one may
+        # differ by a mode or two; an integer n_pca_modes is kept exactly
+        assert all(abs(a - b) <= (2 if isinstance(npm, float) else 0) for a, b in zip(m.n_pca_modes_, o["n_pca_modes"]))
+        np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+        np.testing.assert_allclose(m.total_squared_covariance(), o["total_squared_covariance"], rtol=1e-4)
+        c1, c2 = m.components()
+        v1 = c1.values[~np.isnan(c1.values).any(axis=1)]
+        assert ((v1 * o["components1_2d"]).sum(axis=0) > 1 - 1e-4).all()
+        assert ((c2.values * o["components2_2d"]).sum(axis=0) > 1 - 1e-4).all()
+        s1, s2 = m.scores()
+        for sc, osc in ((s1, o["scores1"]), (s2, o["scores2"])):
+            scale = np.abs(osc).max(axis=0)
+            np.testing.assert_allclose(sc.values / scale, osc / scale, atol=1e-3)
 
 
 def test_mca_rotator_host_logic():
@@ -152,7 +183,7 @@ def test_mca_rotator_host_logic():
     Y = ((U * sig) @ np.linalg.qr(rng.standard_normal((60, 2 * k)))[0].T + 0.01 * rng.standard_normal((T, 60))).astype(np.float32)
     X[:, 7] = np.nan
     o = omca.mca_fit(X, Y, ("time", "x"), ("time", "y"), "time", n_modes=k, random_state=3)
-    m = xb.cross.MCA(n_modes=k, random_state=3, ops=TorchCpuOps())
+    m = xb.cross.MCA(n_modes=k, random_state=3, use_pca=False, ops=TorchCpuOps())
     m.fit(xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")
     for power in (1, 2):
         r = xb.cross.MCARotator(n_modes=mr, power=power).fit(m)

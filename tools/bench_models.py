@@ -53,13 +53,23 @@ def mca(scale):
     coords = {"lat": np.linspace(89.75, -89.75, nlat), "lon": np.arange(nlon) * 0.5}
 
     def fit(tsc):
-        m = xb.cross.MCA(n_modes=k, random_state=5, total_squared_covariance=tsc)
+        m = xb.cross.MCA(n_modes=k, random_state=5, use_pca=False, total_squared_covariance=tsc)
         return m.fit(xb.DataArray(X, DIMS, coords), xb.DataArray(Y, DIMS, coords), dim="time")
 
     ms, m = timed(lambda: fit(False))
     gb = 2 * T * nlat * nlon * 4 / 1e9
     ms_tsc, m2 = timed(lambda: fit(True), n=1)
     s = m.singular_values().values
+    if os.environ.get("XEOFS_BENCH_MCA_PCA", "1") != "0":
+        def fit_pca():
+            mp = xb.cross.MCA(n_modes=k, random_state=5)   # reference defaults: use_pca=True, 99.9 % of variance
+            mp.fit(xb.DataArray(X, DIMS, coords), xb.DataArray(Y, DIMS, coords), dim="time")
+            return mp
+        ms_pca, mp = timed(fit_pca, n=1)
+        print(json.dumps({"config": f"MCA n_modes={k} with the default PCA stage (use_pca=True, n_pca_modes=0.999) on the "
+                                    f"same fields", "fit_ms": ms_pca, "pca_modes_kept": mp.n_pca_modes_,
+                          "singular_values_head": [float(v) for v in mp.singular_values().values[:3]]}), flush=True)
+        del mp
     print(json.dumps({"config": f"MCA n_modes={k} (n_iter auto=7) on two {T}x({nlat}x{nlon}) fp32 fields, implicit C",
                       "input_GB": gb, "fit_ms": ms, "GBps_of_input": gb / ms * 1e3, "launches": m.ops.launches,
                       "fit_with_total_squared_covariance_ms": ms_tsc, "tsc": m2.total_squared_covariance(),

@@ -16,7 +16,7 @@ A1 -= A1.mean(0); A2 -= A2.mean(0)
 G1, G2 = A1 @ A1.t(), A2 @ A2.t()
 ref = float((G1 * G2).sum()) / (T - 1) ** 2
 print("ref", ref, " diag share", float((torch.diagonal(G1) * torch.diagonal(G2)).sum() / (G1 * G2).sum()))
-m = xb.cross.MCA(n_modes=k, random_state=3, total_squared_covariance=False)
+m = xb.cross.MCA(n_modes=k, random_state=3, use_pca=False, total_squared_covariance=False)
 m.fit(xb.DataArray(X, DIMS), xb.DataArray(Y, DIMS), dim="time")
 for name in ("tf32x1r", "tf32x3", "tf32x1", "simt"):
     m.ops.sum_algo = _lib.ALGO_NAMES[name]

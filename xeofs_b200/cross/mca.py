@@ -21,21 +21,27 @@ def _pair(v):
 
 
 class MCA:
-    """Same parameters as the reference (cross/mca.py:88-123).  ``use_pca`` defaults to False here: the
-    reference's default PCA pre-projection (rank-0.3*T randomized SVD of each field, unseeded —
-    cross/base_model_cross_set.py:165-179) is outside this build's scope and ``use_pca=True`` raises."""
+    """Same parameters and defaults as the reference (cross/mca.py:88-123).
 
-    def __init__(self, n_modes=2, standardize=False, use_coslat=False, check_nans=True, use_pca=False,
+    ``use_pca=False``: the cross-covariance of the two preprocessed fields is decomposed directly, applied implicitly
+    as two streaming passes per product (BASELINE config 3).
+    ``use_pca=True`` (the reference's default, cross/base_model_cross_set.py:165-179, preprocessing/pca.py:94-131):
+    each field is first projected on its leading principal components — int(pca_init_rank_reduction * rank) modes,
+    cut at the ``n_pca_modes`` fraction of variance (linalg/_numpy/_svd.py:214-241) — and MCA runs on the two small
+    score matrices.  The reference gets those components from an (unseeded) randomized SVD; here, with n_samples <
+    n_features, they come from the eigen-decomposition of the n x n sample Gram matrix A A^T (streamed in 128-sample
+    blocks through the tensor-core product), i.e. the converged limit of that randomized SVD.  ``use_pca`` must be
+    the same for both fields."""
+
+    def __init__(self, n_modes=2, standardize=False, use_coslat=False, check_nans=True, use_pca=True,
                  n_pca_modes=0.999, pca_init_rank_reduction=0.3, compute=True, sample_name="sample",
                  feature_name="feature", solver="auto", random_state=None, solver_kwargs=None, *,
                  device=None, algo="auto", distributed=False, total_squared_covariance=True, ops=None):
-        if any(_pair(use_pca)):
-            raise NotImplementedError(
-                "xeofs_b200.cross.MCA implements the use_pca=False path (implicit cross-covariance operator); "
-                "the PCA pre-projection of the reference is not built."
-            )
+        if len(set(bool(v) for v in _pair(use_pca))) != 1:
+            raise NotImplementedError("xeofs_b200.cross.MCA needs the same use_pca setting for both fields")
         self._params = dict(n_modes=n_modes, standardize=standardize, use_coslat=use_coslat, check_nans=check_nans,
-                            use_pca=use_pca, compute=compute, sample_name=sample_name, feature_name=feature_name,
+                            use_pca=use_pca, n_pca_modes=n_pca_modes, pca_init_rank_reduction=pca_init_rank_reduction,
+                            compute=compute, sample_name=sample_name, feature_name=feature_name,
                             solver=solver, random_state=random_state, solver_kwargs=dict(solver_kwargs or {}))
         self.attrs = {"model": "Maximum Covariance Analysis", "backend": "xeofs_b200"}
         self.ops = ops if ops is not None else CudaOps(device=device, algo=algo)
@@ -52,7 +58,136 @@ class MCA:
             L.validate_input_type(a)
         f1 = self.preprocessor1.fit_transform(X, dim, weights_X)
         f2 = self.preprocessor2.fit_transform(Y, dim, weights_Y)
-        self._fit_algorithm(f1, f2)
+        if bool(_pair(self._params["use_pca"])[0]):
+            self._fit_algorithm_pca(f1, f2)
+        else:
+            self._fit_algorithm(f1, f2)
+        return self
+
+    # ------------------------------------------------------------------ PCA stage (preprocessing/pca.py:94-131)
+    def _gram_block_columns(self, ff, algo):
+        """Block columns G[t0:, t0:t1] (t1 - t0 <= 128) of the sample Gram matrix A A^T of a fitted field, as
+        ((t0, t1), (T - t0) x (t1 - t0) fp32 device block).  The matrix is symmetric: only the samples t >= t0 are
+        streamed for the block starting at t0."""
+        from .._cuda_ops import Field
+        ops, comm = self.ops, self.comm
+        f = ff.field
+        for t0 in range(0, ff.T, 128):
+            t1 = min(ff.T, t0 + 128)
+            w = t1 - t0
+            rv = None if f.row_valid is None else f.row_valid[t0:]
+            tail = Field(f.X[t0:], f.pivot, f.dscale, f.ccorr, f.valid, f.mean, f.std, rv)
+            blk = ops.scaled_rows(f, t0, t1)
+            gi = ops.project_T(tail, blk, w, algo=algo)
+            comm.sum_(gi)
+            yield (t0, t1), gi[:, :w]
+
+    def _pca_stage(self, ff, n_pca_modes, init_rank_reduction):
+        """Principal components of one preprocessed field through its sample Gram matrix: A = U S V^T with
+        A A^T = U S^2 U^T.  Returns (U (T x r) fp64, s (r) fp64) with the reference's truncation
+        (linalg/_numpy/_svd.py:89-106, 214-241) and sign convention (sign rule on the columns of V, :205-210).
+        The projection A V the reference hands on (pca.py:121-131) is U * s."""
+        import warnings
+        ops, comm = self.ops, self.comm
+        T, n = ff.T, ff.n_samples
+        if n > ff.n_features:
+            raise NotImplementedError("the PCA stage is built for n_samples <= n_features (sample Gram route)")
+        G = torch.zeros((T, T), dtype=torch.float64, device=ops.device)
+        for (t0, t1), blk in self._gram_block_columns(ff, ops.accurate_algo):
+            b = blk.double()
+            G[t0:, t0:t1] = b
+            G[t0:t1, t0:] = b.t()
+        evals, evecs = torch.linalg.eigh(G)
+        del G
+        evals, evecs = evals.flip(0), evecs.flip(1)
+        rank = min(n, ff.n_features)
+        by_variance = isinstance(n_pca_modes, float)
+        if by_variance:
+            m0 = int(rank * init_rank_reduction)
+            if m0 < 1:
+                warnings.warn(f"`init_rank_reduction={init_rank_reduction}` is too low resulting in zero components. "
+                              "One component will be computed instead.")
+                m0 = 1
+        elif n_pca_modes == "all":
+            m0 = rank
+        elif isinstance(n_pca_modes, (int, np.integer)):
+            if n_pca_modes > rank:
+                raise ValueError(f"n_modes must be less than or equal to the rank of the dataset (rank = {rank}).")
+            m0 = int(n_pca_modes)
+        else:
+            raise ValueError("`n_modes` must be an integer, float or 'all'")
+        s = torch.sqrt(torch.clamp(evals[:m0], min=0.0))
+        r = m0
+        if by_variance:
+            cum = torch.cumsum(s**2 / (n - 1) / ff.total_variance, 0)
+            r = m0 - int((cum >= n_pca_modes).sum().item()) + 1
+            if r > m0:
+                warnings.warn(f"Dataset has {m0} components, explaining {float(cum[-1]):.2%} of the variance. However, "
+                              f"{n_pca_modes:.2%} explained variance was requested. Please consider increasing "
+                              "`init_rank_reduction`.")
+                r = m0
+        U, s = evecs[:, :r].contiguous(), s[:r].contiguous()
+        del evecs
+        # sign of every principal component from the extrema of its pattern V[:, j] = A^T u_j / s_j, 128 at a time
+        inv_s = torch.where(s > 0, 1.0 / s, torch.zeros_like(s))
+        signs = []
+        for j0 in range(0, r, 128):
+            w = min(128, r - j0)
+            W = ops.zeros((T, lpad(w)))
+            W[:, :w] = (U[:, j0:j0 + w] * inv_s[j0:j0 + w]).to(torch.float32)
+            Vt = ops.project_S(ff.field, W, w, algo=ops.accurate_algo)
+            signs.append(E.sign_flip(ops, Vt, w, ff.S, comm).double())
+        U = U * torch.cat(signs)[None, :]
+        return U, s
+
+    def _fit_algorithm_pca(self, f1, f2):
+        """cross/base_model_cross_set.py:307-321 + cross/cpcca.py:168-225 on the PCA scores of both fields."""
+        ops, p = self.ops, self._params
+        if f1.n_samples != f2.n_samples or f1.T != f2.T:
+            raise ValueError(
+                f"Both data matrices must have the same number of samples but found {f1.n_samples} in the "
+                f"first and {f2.n_samples} in the second."
+            )
+        npm, irr = _pair(p["n_pca_modes"]), _pair(p["pca_init_rank_reduction"])
+        U1, s1 = self._pca_stage(f1, npm[0], irr[0])
+        U2, s2 = self._pca_stage(f2, npm[1], irr[1])
+        n, k = f1.n_samples, p["n_modes"]
+        if not isinstance(k, (int, np.integer)):
+            raise NotImplementedError("variance-based n_modes is not supported for MCA in this build")
+        X1, X2 = U1 * s1, U2 * s2                                   # pca.py:121-131: A V = U S
+        C = X1.t() @ X2 / (n - 1)                                   # cpcca.py:1008-1015, r1 x r2
+        rank = min(C.shape)
+        if k > rank:
+            raise ValueError(f"n_modes must be less than or equal to the rank of the dataset (rank = {rank}).")
+        if p["solver"] not in ("auto", "full", "randomized"):
+            raise ValueError(f"Unrecognized solver '{p['solver']}'. Valid options are 'auto', 'full', and 'randomized'.")
+        # the small dense decomposition (decomposer.py:112-146) in fp64: the exact SVD, which the reference's
+        # randomized solver (n_iter = 7 for k < 0.1 rank) reproduces far inside the parity tolerance
+        Uc, sc, Vh = torch.linalg.svd(C, full_matrices=False)
+        Q1, s, Q2 = Uc[:, :k], sc[:k], Vh[:k].t()
+        # decomposer.py:219-222: the sign rule reads Q2 in the space it was computed in, the PCA space
+        sign = torch.where(Q2.max(0).values.abs() >= Q2.min(0).values.abs(), 1.0, -1.0).to(torch.float64)
+        Q1, Q2 = Q1 * sign, Q2 * sign
+        kp = lpad(k)
+        sc1, sc2 = ops.zeros((f1.T, kp)), ops.zeros((f2.T, kp))
+        sc1[:, :k] = (X1 @ Q1).to(torch.float32)                    # cpcca.py:204-205
+        sc2[:, :k] = (X2 @ Q2).to(torch.float32)
+        # components in physical space (pca.py:161-171): V Q = A^T (U S^-1 Q), one streaming pass per field
+        comps = []
+        for ff, U, sv, Q in ((f1, U1, s1, Q1), (f2, U2, s2, Q2)):
+            W = ops.zeros((ff.T, kp))
+            W[:, :k] = ((U * torch.where(sv > 0, 1.0 / sv, torch.zeros_like(sv))) @ Q).to(torch.float32)
+            comps.append(ops.project_S(ff.field, W, k, algo=ops.accurate_algo))
+        self.k = k
+        self._Q1t, self._Q2t, self._sc1, self._sc2, self._s = comps[0], comps[1], sc1, sc2, s
+        self._f1, self._f2 = f1, f2
+        self.n_pca_modes_ = (int(s1.numel()), int(s2.numel()))
+        self.data = {
+            "singular_values": s, "squared_covariance": s**2,
+            "norm1": torch.linalg.norm(X1 @ Q1, dim=0), "norm2": torch.linalg.norm(X2 @ Q2, dim=0),
+            "idx_modes_sorted": torch.argsort(s, descending=True),
+            "total_squared_covariance": float((C**2).sum().item()),   # cpcca.py:991-1000, in the PCA space
+        }
         return self
 
     def _shard_offset(self, S):
@@ -114,29 +249,16 @@ class MCA:
         """cpcca.py:991-1000: sum |C|^2 = <X X^T, Y Y^T>_F / (n-1)^2, from the two T x T Gram matrices built 128
         columns at a time with the streaming product.  The Gram matrices are symmetric: for the column block starting
         at sample t0 only the samples t >= t0 are streamed, the strictly lower part counts twice."""
-        from .._cuda_ops import Field
-        ops, comm = self.ops, self.comm
-        T = self._f1.T
+        ops = self.ops
         acc = torch.zeros((), dtype=torch.float64, device=ops.device)
         # each Gram entry is a sum over all features: with >= 2^16 of them the rounding noise of a single TF32 product
         # (operands rounded to nearest, 2e-4 per term) averages out below 1e-6; smaller fields take the 3xTF32 product
         S_all = min(self._f1.S_global, self._f2.S_global)
         algo = getattr(ops, "sum_algo", ops.accurate_algo) if S_all >= 65536 else ops.accurate_algo
-
-        def tail(f, t0):  # the field from sample t0 on (same Scaler vectors)
-            rv = None if f.row_valid is None else f.row_valid[t0:]
-            return Field(f.X[t0:], f.pivot, f.dscale, f.ccorr, f.valid, f.mean, f.std, rv)
-
-        for t0 in range(0, T, 128):
-            t1 = min(T, t0 + 128)
+        for ((t0, t1), g1), (_, g2) in zip(self._gram_block_columns(self._f1, algo),
+                                           self._gram_block_columns(self._f2, algo)):
             w = t1 - t0
-            g = []
-            for ff in (self._f1, self._f2):
-                blk = ops.scaled_rows(ff.field, t0, t1)
-                gi = ops.project_T(tail(ff.field, t0), blk, w, algo=algo)
-                comm.sum_(gi)
-                g.append(gi[:, :w].double())
-            prod = g[0] * g[1]
+            prod = g1.double() * g2.double()
             acc += prod[:w].sum() + 2.0 * prod[w:].sum()
         return float(acc.item()) / float(self._f1.n_samples - 1) ** 2
 
