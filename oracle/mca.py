@@ -36,7 +36,7 @@ def mca_fit(
     n_modes=2, standardize=False, use_coslat=False, check_nans=True,
     weights_x=None, weights_y=None,
     random_state=None, solver="auto", solver_kwargs=None,
-    use_pca=False, n_pca_modes=0.999, pca_init_rank_reduction=0.3, pca_random_state=None,
+    use_pca=False, n_pca_modes=0.999, pca_init_rank_reduction=0.3, pca_random_state=None, alpha=1.0,
 ):
     """use_pca=False path (the configuration BASELINE.json config 3 is built on; the default
     use_pca=True path is unseeded in the reference, cross/base_model_cross_set.py:165-179)."""
@@ -58,13 +58,38 @@ def mca_fit(
         _, _, V2 = decompose(A2, n_modes=n_pca_modes, init_rank_reduction=pca_init_rank_reduction,
                              random_state=pca_random_state)
         A1, A2 = A1 @ V1, A2 @ V2
+    # fractional whitening (preprocessing/whitener.py:111-133; linalg/_numpy/_utils.py:6-33): T = C^((alpha-1)/2) with
+    # C = X^T X / n_samples through the SVD of C, singular values <= eps cut; identity for alpha = 1
+    al = _pair(alpha)
+    Tinv = [None, None]
+    mats = [A1, A2]
+    for i in range(2):
+        if float(al[i]) == 1.0:
+            continue
+        Xi = mats[i]
+        Ci = Xi.conj().T @ Xi / Xi.shape[0]
+        _, sv, Vh = np.linalg.svd(Ci)
+        keep = sv > np.finfo(sv.dtype).eps
+        Vk, sk = Vh[keep].conj().T, sv[keep]
+        T = (Vk * sk ** ((float(al[i]) - 1.0) / 2.0)) @ Vk.conj().T
+        try:
+            Tinv[i] = np.linalg.inv(T)
+        except np.linalg.LinAlgError:
+            Tinv[i] = np.linalg.pinv(T)
+        mats[i] = Xi @ T
+    A1, A2 = mats
     C = cross_covariance(A1, A2)
     Q1, s, Q2 = decompose(C, n_modes=n_modes, solver=solver, random_state=random_state,
                           solver_kwargs=solver_kwargs)
     tsc = (np.abs(C) ** 2).sum()
     scores1 = A1 @ Q1
     scores2 = A2 @ Q2
-    if use_pca:  # the accessors return the patterns in physical space (pca.py:161-171)
+    # the accessors return the patterns un-whitened (whitener.py:201-213) and in physical space (pca.py:161-171)
+    if Tinv[0] is not None:
+        Q1 = Tinv[0].conj().T @ Q1
+    if Tinv[1] is not None:
+        Q2 = Tinv[1].conj().T @ Q2
+    if use_pca:
         Q1, Q2 = V1 @ Q1, V2 @ Q2
     return {
         "n_pca_modes": None if V1 is None else (V1.shape[1], V2.shape[1]),

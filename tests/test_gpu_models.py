@@ -168,6 +168,33 @@ def test_mca_default_pca_stage_matches_oracle(npm):
         np.testing.assert_allclose(sc.values / scale, osc / scale, atol=2e-3)
 
 
+@pytest.mark.parametrize("cls,alpha", [("CCA", (0.0, 0.0)), ("RDA", (0.0, 1.0)), ("CPCCA", 0.2)])
+def test_cpcca_family_matches_oracle(cls, alpha):
+    """CCA / RDA / CPCCA on the device: fractional whitening of the PCA scores (preprocessing/whitener.py:111-133),
+    un-whitened patterns in physical space, against the numpy restatement."""
+    import xeofs_b200 as xb
+    T, S1, S2, k = 300, 40 * 30, 20 * 36, 3
+    X, Y = _coupled_fields(T, S1, S2, 2 * k, seed=17)
+    X = X.reshape(T, 40, 30)
+    Y = Y.reshape(T, 20, 36)
+    o = omca.mca_fit(X, Y, DIMS, DIMS, "time", n_modes=k, random_state=3, use_pca=True, n_pca_modes=2 * k,
+                     pca_random_state=1, alpha=alpha)
+    kw = dict(n_modes=k, random_state=3, n_pca_modes=2 * k)
+    m = xb.cross.CPCCA(alpha=alpha, **kw) if cls == "CPCCA" else getattr(xb.cross, cls)(**kw)
+    m.fit(xb.DataArray(X, DIMS), xb.DataArray(Y, DIMS), dim="time")
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    c1, c2 = m.components()
+    for c, oc in ((c1, o["components1_2d"]), (c2, o["components2_2d"])):
+        V = c.values.reshape(-1, k)
+        cosang = (V * oc).sum(axis=0) / np.linalg.norm(V, axis=0) / np.linalg.norm(oc, axis=0)
+        assert (cosang > 1 - 1e-4).all(), cosang
+        np.testing.assert_allclose(np.linalg.norm(V, axis=0), np.linalg.norm(oc, axis=0), rtol=1e-3)
+    s1, s2 = m.scores()
+    for sc, osc in ((s1, o["scores1"]), (s2, o["scores2"])):
+        scale = np.abs(osc).max(axis=0)
+        np.testing.assert_allclose(sc.values / scale, osc / scale, atol=2e-3)
+
+
 def test_mca_total_squared_covariance_wide_fields():
     """cpcca.py:991-1000 at a width (S >= 2^16) where the sample Gram matrices take the single rounded TF32 product
     (XEOFS_ALGO_TF32X1R): sum |C|^2 = <A1 A1^T, A2 A2^T> / (n-1)^2 against fp64 torch on the preprocessed fields."""

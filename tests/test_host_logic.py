@@ -172,6 +172,40 @@ def test_mca_pca_stage_host_logic():
             np.testing.assert_allclose(sc.values / scale, osc / scale, atol=1e-3)
 
 
+@pytest.mark.parametrize("cls,alpha", [("CCA", (0.0, 0.0)), ("RDA", (0.0, 1.0)), ("CPCCA", 0.2)])
+def test_cpcca_family_host_logic(cls, alpha):
+    """CCA / RDA / CPCCA (cross/cca.py, rda.py, cpcca.py): MCA on fractionally whitened PCA scores
+    (preprocessing/whitener.py:111-133), patterns un-whitened and mapped back to physical space."""
+    import xeofs_b200 as xb
+    T, k = 150, 3
+    rng = np.random.default_rng(3)
+    U = np.linalg.qr(rng.standard_normal((T, 2 * k)))[0]
+    sig = 100 * 0.7 ** np.arange(2 * k)
+    X = ((U * sig) @ np.linalg.qr(rng.standard_normal((300, 2 * k)))[0].T + 0.05 * rng.standard_normal((T, 300))).astype(np.float32)
+    Y = ((U * sig) @ np.linalg.qr(rng.standard_normal((200, 2 * k)))[0].T + 0.05 * rng.standard_normal((T, 200))).astype(np.float32)
+    o = omca.mca_fit(X, Y, ("time", "x"), ("time", "y"), "time", n_modes=k, random_state=3, use_pca=True,
+                     n_pca_modes=6, pca_random_state=1, alpha=alpha)
+    # (6 = the planted rank: whitening weights every retained principal component alike, and the directions of
+    # noise-level components — nearly degenerate — are not reproducible between two PCA solvers)
+    kw = dict(n_modes=k, random_state=3, n_pca_modes=6, ops=TorchCpuOps())
+    m = xb.cross.CPCCA(alpha=alpha, **kw) if cls == "CPCCA" else getattr(xb.cross, cls)(**kw)
+    m.fit(xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    c1, c2 = m.components()
+    for c, oc in ((c1, o["components1_2d"]), (c2, o["components2_2d"])):
+        V, R = c.values, oc
+        cosang = (V * R).sum(axis=0) / np.linalg.norm(V, axis=0) / np.linalg.norm(R, axis=0)
+        assert (cosang > 1 - 1e-4).all(), cosang
+        np.testing.assert_allclose(np.linalg.norm(V, axis=0), np.linalg.norm(R, axis=0), rtol=1e-3)
+    s1, s2 = m.scores()
+    for sc, osc in ((s1, o["scores1"]), (s2, o["scores2"])):
+        scale = np.abs(osc).max(axis=0)
+        np.testing.assert_allclose(sc.values / scale, osc / scale, atol=1e-3)
+    with pytest.raises(NotImplementedError, match="use_pca"):
+        xb.cross.CCA(n_modes=k, use_pca=False, ops=TorchCpuOps()).fit(
+            xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")
+
+
 def test_mca_rotator_host_logic():
     """cross/cpcca_rotator.py:122-305 (identity whitening, no PCA) against its numpy restatement."""
     import xeofs_b200 as xb

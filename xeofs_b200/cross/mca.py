@@ -51,6 +51,7 @@ class MCA:
                                     check_nans=chk[i], sample_name=sample_name, comm=self.comm)
         self.preprocessor1, self.preprocessor2 = mk(0), mk(1)
         self._want_tsc = total_squared_covariance
+        self._alpha = (1.0, 1.0)  # identity whitening = MCA (cross/mca.py:112-114)
         self.data = {}
 
     def fit(self, X, Y, dim, weights_X=None, weights_Y=None):
@@ -60,6 +61,12 @@ class MCA:
         f2 = self.preprocessor2.fit_transform(Y, dim, weights_Y)
         if bool(_pair(self._params["use_pca"])[0]):
             self._fit_algorithm_pca(f1, f2)
+        elif self._alpha != (1.0, 1.0):
+            raise NotImplementedError(
+                "fractional whitening (alpha < 1) is built on the PCA scores: use_pca=True is required (the reference "
+                "itself warns that whitening the full feature space with n_samples < n_features is ill-conditioned, "
+                "preprocessing/whitener.py:101-105)"
+            )
         else:
             self._fit_algorithm(f1, f2)
         return self
@@ -155,6 +162,14 @@ class MCA:
         if not isinstance(k, (int, np.integer)):
             raise NotImplementedError("variance-based n_modes is not supported for MCA in this build")
         X1, X2 = U1 * s1, U2 * s2                                   # pca.py:121-131: A V = U S
+        # fractional whitening (preprocessing/whitener.py:111-133): T = C^((alpha-1)/2) with C = X^T X / n, which in
+        # the PCA space is diagonal, s^2 / n; alpha = 1 is the identity (MCA), 0 full whitening (CCA)
+        tw = []
+        for sv, a in ((s1, self._alpha[0]), (s2, self._alpha[1])):
+            lam = sv**2 / n
+            t = torch.where(lam > torch.finfo(torch.float64).eps, lam ** ((a - 1.0) / 2.0), torch.zeros_like(lam))
+            tw.append(torch.ones_like(lam) if a == 1.0 else t)
+        X1, X2 = X1 * tw[0], X2 * tw[1]
         C = X1.t() @ X2 / (n - 1)                                   # cpcca.py:1008-1015, r1 x r2
         rank = min(C.shape)
         if k > rank:
@@ -174,9 +189,11 @@ class MCA:
         sc2[:, :k] = (X2 @ Q2).to(torch.float32)
         # components in physical space (pca.py:161-171): V Q = A^T (U S^-1 Q), one streaming pass per field
         comps = []
-        for ff, U, sv, Q in ((f1, U1, s1, Q1), (f2, U2, s2, Q2)):
+        for ff, U, sv, t, Q in ((f1, U1, s1, tw[0], Q1), (f2, U2, s2, tw[1], Q2)):
+            # un-whiten (Tinv^T Q, whitener.py:201-213), then back from the PCA space
+            d = sv * t
             W = ops.zeros((ff.T, kp))
-            W[:, :k] = ((U * torch.where(sv > 0, 1.0 / sv, torch.zeros_like(sv))) @ Q).to(torch.float32)
+            W[:, :k] = ((U * torch.where(d > 0, 1.0 / d, torch.zeros_like(d))) @ Q).to(torch.float32)
             comps.append(ops.project_S(ff.field, W, k, algo=ops.accurate_algo))
         self.k = k
         self._Q1t, self._Q2t, self._sc1, self._sc2, self._s = comps[0], comps[1], sc1, sc2, s
@@ -299,3 +316,50 @@ class MCA:
 
     def get_params(self):
         return dict(self._params)
+
+
+class CPCCA(MCA):
+    """Continuum Power CCA (cross/cpcca.py:25-160): MCA on fractionally whitened fields, alpha = 1 MCA, 0 CCA,
+    (0, 1) RDA.  Built on the PCA scores (``use_pca=True``, the default)."""
+
+    def __init__(self, n_modes=2, alpha=0.2, standardize=False, use_coslat=False, use_pca=True, n_pca_modes=0.999,
+                 pca_init_rank_reduction=0.3, check_nans=True, compute=True, sample_name="sample",
+                 feature_name="feature", solver="auto", random_state=None, solver_kwargs=None, **kw):
+        super().__init__(n_modes=n_modes, standardize=standardize, use_coslat=use_coslat, check_nans=check_nans,
+                         use_pca=use_pca, n_pca_modes=n_pca_modes, pca_init_rank_reduction=pca_init_rank_reduction,
+                         compute=compute, sample_name=sample_name, feature_name=feature_name, solver=solver,
+                         random_state=random_state, solver_kwargs=solver_kwargs, **kw)
+        a = tuple(float(v) for v in _pair(alpha))
+        if any(v < 0.0 or v > 1.0 for v in a):
+            raise ValueError("alpha must be in the range [0, 1]")  # whitener.py:41-42
+        self._alpha = a
+        self._params["alpha"] = alpha
+        self.attrs["model"] = "Continuum Power CCA"
+
+
+class CCA(CPCCA):
+    """Canonical Correlation Analysis (cross/cca.py:8-117): CPCCA with alpha = (0, 0)."""
+
+    def __init__(self, n_modes=2, standardize=False, use_coslat=False, check_nans=True, use_pca=True,
+                 n_pca_modes=0.999, pca_init_rank_reduction=0.3, compute=True, sample_name="sample",
+                 feature_name="feature", solver="auto", random_state=None, solver_kwargs=None, **kw):
+        super().__init__(n_modes=n_modes, alpha=[0.0, 0.0], standardize=standardize, use_coslat=use_coslat,
+                         use_pca=use_pca, n_pca_modes=n_pca_modes, pca_init_rank_reduction=pca_init_rank_reduction,
+                         check_nans=check_nans, compute=compute, sample_name=sample_name, feature_name=feature_name,
+                         solver=solver, random_state=random_state, solver_kwargs=solver_kwargs, **kw)
+        self._params.pop("alpha")
+        self.attrs["model"] = "Canonical Correlation Analysis"
+
+
+class RDA(CPCCA):
+    """Redundancy Analysis (cross/rda.py:8-120): CPCCA with alpha = (0, 1)."""
+
+    def __init__(self, n_modes=2, standardize=False, use_coslat=False, check_nans=True, use_pca=True,
+                 n_pca_modes=0.999, pca_init_rank_reduction=0.3, compute=True, sample_name="sample",
+                 feature_name="feature", solver="auto", random_state=None, solver_kwargs=None, **kw):
+        super().__init__(n_modes=n_modes, alpha=[0.0, 1.0], standardize=standardize, use_coslat=use_coslat,
+                         use_pca=use_pca, n_pca_modes=n_pca_modes, pca_init_rank_reduction=pca_init_rank_reduction,
+                         check_nans=check_nans, compute=compute, sample_name=sample_name, feature_name=feature_name,
+                         solver=solver, random_state=random_state, solver_kwargs=solver_kwargs, **kw)
+        self._params.pop("alpha")
+        self.attrs["model"] = "Redundancy Analysis"

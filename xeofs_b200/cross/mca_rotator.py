@@ -1,6 +1,6 @@
 """Varimax / Promax rotation of an MCA solution on B200 — drop-in for ``xeofs.cross.MCARotator``
-(cross/mca_rotator.py:5 -> cross/cpcca_rotator.py:57-469) for models fitted with ``use_pca=False`` (identity
-whitening, no PCA stage).
+(cross/mca_rotator.py:5 -> cross/cpcca_rotator.py:57-469) for MCA models (identity whitening; with or without
+the PCA stage — the rotation works on the physical-space singular vectors either way).
 
 The singular vectors of both fields, weighted with sqrt(singular value), are rotated as ONE (S1 + S2) x m loadings
 matrix (cpcca_rotator.py:154-180): the same one-pass-per-iteration varimax sweep as ``EOFRotator`` runs on the
