@@ -321,10 +321,12 @@ def randomized_svd(ops, op, k, n_oversamples=10, n_iter="auto", random_state=Non
     if n_iter == "auto":
         n_iter = 7 if k < 0.1 * min(n_r, n_c) else 4
     infos = []
-    if Omega is None:
-        Q = sketch_matrix(ops, op, l, random_state, comm, predrawn)
-    else:
+    if Omega is not None:
         Q = Omega
+    elif first_product is not None and int(n_iter) >= 1:
+        Q = None  # M @ Omega is in hand already (fused statistics pass): the sketch itself is not needed again
+    else:
+        Q = sketch_matrix(ops, op, l, random_state, comm, predrawn)
     lp = lpad(l)
 
     def _shape2d(dim):  # (rows, cols) of a k-column block on this side

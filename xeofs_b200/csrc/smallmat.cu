@@ -444,9 +444,28 @@ __global__ void __launch_bounds__(256)
 row_minmax_kernel(const float* __restrict__ Vt, int64_t n, int64_t ld, float* __restrict__ vmax, float* __restrict__ vmin) {
   const float* row = Vt + (int64_t)blockIdx.y * ld;
   float mx = -INFINITY, mn = INFINITY;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float v = row[i];
+  auto take = [&](float v) {
     if (v == v) { mx = fmaxf(mx, v); mn = fminf(mn, v); }
+  };
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((((uintptr_t)row) & 15) == 0) {
+    // 16-byte loads, four in flight per thread
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const int64_t n4 = n >> 2;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+      const float4 a = __ldg(row4 + i), b = __ldg(row4 + i + stride), c = __ldg(row4 + i + 2 * stride),
+                   d = __ldg(row4 + i + 3 * stride);
+      take(a.x); take(a.y); take(a.z); take(a.w); take(b.x); take(b.y); take(b.z); take(b.w);
+      take(c.x); take(c.y); take(c.z); take(c.w); take(d.x); take(d.y); take(d.z); take(d.w);
+    }
+    for (; i < n4; i += stride) {
+      const float4 a = __ldg(row4 + i);
+      take(a.x); take(a.y); take(a.z); take(a.w);
+    }
+    for (int64_t j = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) take(row[j]);
+  } else {
+    for (; i < n; i += stride) take(row[i]);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -554,7 +573,7 @@ extern "C" int xeofs_b200_row_minmax(const float* Vt, int64_t k, int64_t n, int6
   XB_CHECK_ARG(Vt && vmax && vmin && k > 0 && k <= 65535 && n > 0, "row_minmax: bad arguments");
   minmax_init_kernel<<<(unsigned)ceil_div(k, 128), 128, 0, stream>>>(vmax, vmin, (int)k);
   XB_LAUNCH_CHECK();
-  const int bx = (int)imin(ceil_div(n, 256 * 8), 4 * (int64_t)num_sms());
+  const int bx = (int)imin(ceil_div(n, 256 * 16), 2 * (int64_t)num_sms());
   row_minmax_kernel<<<dim3(bx > 0 ? bx : 1, (unsigned)k), 256, 0, stream>>>(Vt, n, ld, vmax, vmin);
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
