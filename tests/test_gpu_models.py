@@ -168,6 +168,33 @@ def test_mca_default_pca_stage_matches_oracle(npm):
         np.testing.assert_allclose(sc.values / scale, osc / scale, atol=2e-3)
 
 
+def test_mca_pca_stage_subspace_route():
+    """Enough samples (int(0.3 n) >= 512) for the PCA stage to take the blocked subspace iteration on the sample Gram
+    matrix instead of the dense eigen-decomposition: same oracle (the reference's randomized-SVD PCA), same bars."""
+    import xeofs_b200 as xb
+    from xeofs_b200.cross import mca as mca_mod
+    T, S1, S2, k = 2000, 64 * 64, 48 * 64, 5
+    X, Y = _coupled_fields(T, S1, S2, 2 * k, seed=19)
+    X = X.reshape(T, 64, 64)
+    Y = Y.reshape(T, 48, 64)
+    o = omca.mca_fit(X, Y, DIMS, DIMS, "time", n_modes=k, random_state=3, use_pca=True, pca_random_state=1)
+    calls = []
+    orig = torch.linalg.qr
+    m = xb.cross.MCA(n_modes=k, random_state=3)
+    try:
+        torch.linalg.qr = lambda *a, **kw: (calls.append(1), orig(*a, **kw))[1]
+        m.fit(xb.DataArray(X, DIMS), xb.DataArray(Y, DIMS), dim="time")
+    finally:
+        torch.linalg.qr = orig
+    assert calls, "the subspace route was not taken"
+    assert all(abs(a - b) <= 2 for a, b in zip(m.n_pca_modes_, o["n_pca_modes"])), (m.n_pca_modes_, o["n_pca_modes"])
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    c1, c2 = m.components()
+    for c, oc in ((c1, o["components1_2d"]), (c2, o["components2_2d"])):
+        dots = (c.values.reshape(-1, k) * oc).sum(axis=0)
+        assert (dots >= 1 - 1e-4).all(), dots
+
+
 @pytest.mark.parametrize("cls,alpha", [("CCA", (0.0, 0.0)), ("RDA", (0.0, 1.0)), ("CPCCA", 0.2)])
 def test_cpcca_family_matches_oracle(cls, alpha):
     """CCA / RDA / CPCCA on the device: fractional whitening of the PCA scores (preprocessing/whitener.py:111-133),
