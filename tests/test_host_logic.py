@@ -339,9 +339,18 @@ m = xb.single.EOF(n_modes=k, use_coslat=True, standardize=True, random_state=7, 
                   distributed=True, ops=TorchCpuOps())
 m.fit(xb.DataArray(X[:, rows], ("time", "lat", "lon"), coords), dim="time")
 r = xb.single.EOFRotator(n_modes=4).fit(m)
+# MCA of two sharded fields: implicit cross-covariance and the default PCA stage
+Y = planted(T, nlat * nlon, 2 * k, seed=2)[:, ::-1].copy().reshape(T, nlat, nlon) * 2.0 + 5.0
+dax = xb.DataArray(np.nan_to_num(X[:, rows], nan=1.0), ("time", "lat", "lon"), coords)
+day = xb.DataArray(Y[:, rows], ("time", "lat", "lon"), coords)
+c0 = m.comm.collectives
+mi = xb.cross.MCA(n_modes=3, use_pca=False, random_state=7, distributed=True, ops=TorchCpuOps()).fit(dax, day, dim="time")
+mp = xb.cross.MCA(n_modes=3, n_pca_modes=8, random_state=7, distributed=True, ops=TorchCpuOps()).fit(dax, day, dim="time")
 np.savez(os.path.join(sys.argv[2], f"rank{rank}.npz"), s=m.singular_values().values, comps=m.components().values,
-         scores=m.scores().values, evr=m.explained_variance_ratio().values, collectives=m.comm.collectives,
-         rot_ev=r.explained_variance().values, rot_comps=r.components().values)
+         scores=m.scores().values, evr=m.explained_variance_ratio().values, collectives=c0,
+         rot_ev=r.explained_variance().values, rot_comps=r.components().values,
+         mca_s=mi.singular_values().values, mca_tsc=mi.total_squared_covariance(), mca_c1=mi.components()[0].values,
+         pca_s=mp.singular_values().values, pca_tsc=mp.total_squared_covariance(), pca_c2=mp.components()[1].values)
 dist.destroy_process_group()
 '''
 
@@ -376,3 +385,16 @@ def test_feature_sharded_fit_over_gloo(tmp_path):
     np.testing.assert_allclose(comps, ref.components().values, atol=2e-5, equal_nan=True)
     rot = np.concatenate([r0["rot_comps"], r1["rot_comps"]], axis=0)
     np.testing.assert_allclose(rot, rref.components().values, atol=5e-5, equal_nan=True)
+    # MCA, both routes, against the single-process fits
+    Y = planted(T, nlat * nlon, 2 * k, seed=2)[:, ::-1].copy().reshape(T, nlat, nlon) * 2.0 + 5.0
+    dax = xb.DataArray(np.nan_to_num(X, nan=1.0), DIMS, coords)
+    day = xb.DataArray(Y, DIMS, coords)
+    mi = xb.cross.MCA(n_modes=3, use_pca=False, random_state=7, ops=TorchCpuOps()).fit(dax, day, dim="time")
+    mp = xb.cross.MCA(n_modes=3, n_pca_modes=8, random_state=7, ops=TorchCpuOps()).fit(dax, day, dim="time")
+    for r in (r0, r1):
+        np.testing.assert_allclose(r["mca_s"], mi.singular_values().values, rtol=1e-5)
+        np.testing.assert_allclose(r["mca_tsc"], mi.total_squared_covariance(), rtol=1e-5)
+        np.testing.assert_allclose(r["pca_s"], mp.singular_values().values, rtol=1e-5)
+        np.testing.assert_allclose(r["pca_tsc"], mp.total_squared_covariance(), rtol=1e-5)
+    np.testing.assert_allclose(np.concatenate([r0["mca_c1"], r1["mca_c1"]], axis=0), mi.components()[0].values, atol=5e-5)
+    np.testing.assert_allclose(np.concatenate([r0["pca_c2"], r1["pca_c2"]], axis=0), mp.components()[1].values, atol=5e-5)
