@@ -110,6 +110,35 @@ def test_eof_list_input_matches_oracle(shapes):
     assert (np.abs(dots) > 1 - 1e-4).all(), dots
 
 
+def test_eof_api_corners_match_oracle():
+    """float n_modes, user weights + coslat, two sample dimensions, T-mode — on the device (see the host-logic twin)."""
+    import xeofs_b200 as xb
+    T, nlat, nlon = 240, 12, 20
+    X = planted(T, nlat * nlon, 10, seed=21).reshape(T, nlat, nlon)
+    coords = {"lat": np.linspace(50, -50, nlat), "lon": np.arange(nlon) * 10.0}
+    da = xb.DataArray(X, DIMS, coords)
+    o = oeof.eof_fit(X, DIMS, "time", coords=coords, n_modes=0.9, random_state=3)
+    m = xb.single.EOF(n_modes=0.9, random_state=3).fit(da, dim="time")
+    assert m.singular_values().values.shape == o["singular_values"].shape
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    w = np.linspace(0.5, 2.0, nlon)
+    o = oeof.eof_fit(X, DIMS, "time", coords=coords, n_modes=4, use_coslat=True, random_state=3,
+                     weights=np.broadcast_to(w, (nlat, nlon)))
+    m = xb.single.EOF(n_modes=4, use_coslat=True, random_state=3).fit(da, dim="time", weights=xb.DataArray(w, ("lon",)))
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    assert ((m.components().values.reshape(-1, 4) * o["components_2d"]).sum(axis=0) > 1 - 1e-4).all()
+    X4 = X.reshape(20, 12, nlat, nlon)
+    dims4 = ("year", "month", "lat", "lon")
+    o = oeof.eof_fit(X4, dims4, ("year", "month"), coords=coords, n_modes=4, random_state=3)
+    m = xb.single.EOF(n_modes=4, random_state=3).fit(xb.DataArray(X4, dims4, coords), dim=("year", "month"))
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    assert m.scores().values.shape == (20, 12, 4)
+    o = oeof.eof_fit(X, DIMS, ("lat", "lon"), coords=coords, n_modes=4, random_state=3)
+    m = xb.single.EOF(n_modes=4, random_state=3).fit(da, dim=("lat", "lon"))
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    np.testing.assert_allclose(np.abs((m.components().values * o["components_2d"]).sum(axis=0)), 1.0, atol=1e-4)
+
+
 def test_bootstrapper_matches_oracle():
     """EOFBootstrapper (validation/bootstrapper.py:56-135) on the device: resampled fits + projection of the original
     samples against the numpy restatement, members seeded on both sides."""

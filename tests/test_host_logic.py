@@ -257,6 +257,46 @@ def test_rotator_host_logic():
                                        rtol=1e-5)
 
 
+def test_eof_variance_based_n_modes_weights_and_tmode():
+    """Less-travelled corners of the fit API against the oracle: float n_modes (decomposer.py:88-94, 188-216), user
+    weights broadcast over the feature dims (scaler.py:100-126), two sample dimensions, and T-mode analysis
+    (dim = the spatial dims, docs .../plot_eof-tmode.py:22-23)."""
+    import xeofs_b200 as xb
+    T, nlat, nlon = 120, 6, 10
+    X = planted(T, nlat * nlon, 10, seed=21).reshape(T, nlat, nlon)
+    coords = {"lat": np.linspace(50, -50, nlat), "lon": np.arange(nlon) * 10.0}
+    # (1) n_modes as a fraction of variance
+    o = oeof.eof_fit(X, DIMS, "time", coords=coords, n_modes=0.9, random_state=3)
+    m = xb.single.EOF(n_modes=0.9, random_state=3, ops=TorchCpuOps()).fit(xb.DataArray(X, DIMS, coords), dim="time")
+    assert m.singular_values().values.shape == o["singular_values"].shape
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    # (2) weights along one feature dim, together with coslat weights
+    w = np.linspace(0.5, 2.0, nlon)
+    o = oeof.eof_fit(X, DIMS, "time", coords=coords, n_modes=4, use_coslat=True, random_state=3,
+                     weights=np.broadcast_to(w, (nlat, nlon)))
+    m = xb.single.EOF(n_modes=4, use_coslat=True, random_state=3, ops=TorchCpuOps())
+    m.fit(xb.DataArray(X, DIMS, coords), dim="time", weights=xb.DataArray(w, ("lon",)))
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    V = m.components().values.reshape(-1, 4)
+    assert ((V * o["components_2d"]).sum(axis=0) > 1 - 1e-5).all()
+    with pytest.raises(ValueError, match="not feature dimensions"):
+        xb.single.EOF(n_modes=2, ops=TorchCpuOps()).fit(xb.DataArray(X, DIMS, coords), dim="time",
+                                                        weights=xb.DataArray(np.ones(T), ("time",)))
+    # (3) two sample dimensions
+    X4 = X.reshape(10, 12, nlat, nlon)
+    dims4 = ("year", "month", "lat", "lon")
+    o = oeof.eof_fit(X4, dims4, ("year", "month"), coords=coords, n_modes=4, random_state=3)
+    m = xb.single.EOF(n_modes=4, random_state=3, ops=TorchCpuOps()).fit(xb.DataArray(X4, dims4, coords), dim=("year", "month"))
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    assert m.scores().values.shape == (10, 12, 4) and m.components().values.shape == (nlat, nlon, 4)
+    # (4) T-mode: the spatial dims are the samples, time is the feature axis
+    o = oeof.eof_fit(X, DIMS, ("lat", "lon"), coords=coords, n_modes=4, random_state=3)
+    m = xb.single.EOF(n_modes=4, random_state=3, ops=TorchCpuOps()).fit(xb.DataArray(X, DIMS, coords), dim=("lat", "lon"))
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    assert m.components().values.shape == (T, 4) and m.scores().values.shape == (nlat, nlon, 4)
+    np.testing.assert_allclose(np.abs((m.components().values * o["components_2d"]).sum(axis=0)), 1.0, atol=1e-5)
+
+
 def test_eof_list_input_host_logic():
     """A list of arrays (two variables on different grids): each scaled on its own, concatenated along the feature
     axis (preprocessing/preprocessor.py:208-228, concatenator.py:58-81); components come back one array per input."""
