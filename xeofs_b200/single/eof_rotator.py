@@ -18,6 +18,7 @@ from .._lib import lpad
 
 
 TC_WINDOW = 8  # iterations the stopping test of the tensor-core phase of the varimax iteration looks back
+TC_SYNC = 4    # tensor-core iterations between two reads of delta on the host
 
 
 class EOFRotator:
@@ -62,7 +63,7 @@ class EOFRotator:
         # test holds, so the iteration ends where the reference's ends.
         tc = getattr(ops, "_varimax_tc_applies", None)
         use_tc = bool(tc and p["rtol"] >= 1e-9 and tc(Ln, S_local, m, False))
-        hist, basis = [], None
+        hist, basis, pending = [], None, []
         d, d_old, converged, it = 0.0, None, False, 0
         self.n_iter_tc_ = 0
         for it in range(1, p["max_iter"] + 1):
@@ -71,14 +72,25 @@ class EOFRotator:
             comm.sum_(W)
             G = G3 - alpha * (XtX @ R) * W[None, :]
             R, dsum, basis = self._polar(ops, G, basis)
-            d_old, d = d, float(dsum.item())
             if use_tc:
-                hist.append(d)
-                w = min(TC_WINDOW, len(hist) - 1)
-                if w >= 1 and abs(d - hist[-1 - w]) / (w * d) < p["rtol"]:
-                    use_tc, d = False, None  # the next fp64 sweep has no fp64 predecessor to compare with
-                    self.n_iter_tc_ = it
+                # delta is read back only every TC_SYNC iterations (one host sync instead of four: the host keeps
+                # enqueueing while the device works); stopping up to TC_SYNC - 1 sweeps late is harmless here, the
+                # fp64 phase decides where the iteration ends
+                pending.append(dsum)
+                if len(pending) < TC_SYNC and it < p["max_iter"]:
+                    continue
+                vals = torch.stack(pending).cpu().tolist()
+                pending = []
+                for v in vals:
+                    hist.append(v)
+                    w = min(TC_WINDOW, len(hist) - 1)
+                    if w >= 1 and abs(v - hist[-1 - w]) / (w * v) < p["rtol"]:
+                        use_tc = False  # the next fp64 sweep has no fp64 predecessor to compare with
+                        self.n_iter_tc_ = it
+                        break
+                d = None if not use_tc else vals[-1]
                 continue
+            d_old, d = d, float(dsum.item())
             if d_old is not None and abs(d - d_old) / d < p["rtol"]:
                 converged = True
                 break
