@@ -1,5 +1,5 @@
 """Developer check of the tcgen05 varimax sweep against fp64 torch, over the descriptor variants the kernel can be
-switched between by environment (XEOFS_VT_FLAGS, XEOFS_VT_STAGES), plus timings."""
+switched between by environment (XEOFS_VT_STAGES), plus timings."""
 import os
 import sys
 
@@ -22,7 +22,7 @@ def case(ops, S, m, seed=0):
 
 
 def run(ops, S, m, env):
-    for k in ("XEOFS_VT_FLAGS", "XEOFS_VT_STAGES"):
+    for k in ("XEOFS_VT_STAGES",):
         os.environ.pop(k, None)
     os.environ.update(env)
     Ln, R, Gref, Wref = case(ops, S, m)
@@ -37,7 +37,7 @@ def run(ops, S, m, env):
 
 
 def timeit(ops, S, m, env, n=10):
-    for k in ("XEOFS_VT_FLAGS", "XEOFS_VT_STAGES"):
+    for k in ("XEOFS_VT_STAGES",):
         os.environ.pop(k, None)
     os.environ.update(env)
     Ln, R, _, _ = case(ops, S, m)
@@ -56,7 +56,7 @@ def timeit(ops, S, m, env, n=10):
 if __name__ == "__main__":
     ops = CudaOps()
     ops.varimax_algo = "tc"
-    variants = [{}, {"XEOFS_VT_FLAGS": "1"}]
+    variants = [{}]
     for env in variants:
         for (S, m) in ((64 * 3, 20), (5000, 20), (100037, 100), (30011, 128), (20000, 50), (4096, 8)):
             print(env, S, m, run(ops, S, m, env), flush=True)

@@ -40,7 +40,6 @@ __host__ __device__ constexpr bool tc_wide(int ns, bool side_t, bool rn) { retur
 constexpr int TC_KC = 32;        // K elements per stage (= one 128-byte swizzle atom of fp32)
 constexpr int TC_XBYTES = TC_TILE * TC_KC * 4;  // 16 KB of X per stage
 constexpr int TC_MAX_STAGES = 6;
-constexpr int TC_D_COLS = 128;   // TMEM columns per accumulator buffer (lp <= 128)
 constexpr int TC_FLUSH = 16;     // 3xTF32: K-chunks accumulated in TMEM before the sum moves to fp32 registers
 
 struct TcParams {
@@ -528,8 +527,6 @@ tile_Y_kernel(const float* __restrict__ Yt, int64_t S, int64_t ldy, int lp, floa
   float* hi = Yhi + (size_t)blockIdx.x * lp * 32;
   float* lo = Ylo ? Ylo + (size_t)blockIdx.x * lp * 32 : nullptr;
   const int kk = threadIdx.x & 31;
-  const float scale = 1.f;
-  (void)scale;
   for (int j = threadIdx.x >> 5; j < lp; j += 8) {
     const float v = (s0 + kk < S) ? Yt[(int64_t)j * ldy + s0 + kk] : 0.f;
     if (lo) {

@@ -43,7 +43,6 @@ struct VtParams {
   int k1;         // K of GEMM1 (m rounded up to 8)
   int stages;
   int ntiles;
-  int flags;      // debug: 1 = SBO of the MN-major descriptor 1024 instead of 512
   const float* rhi;  // [128][128]: rhi[j'][i] = TF32 bits of (float)R[i][j']
   const float* rlo;  // [128][128]: remainder
   double* gpart;     // [grid][128][ng]
@@ -154,7 +153,7 @@ varimax_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
     const uint32_t idesc1 = make_idesc(VT_TS) | (1u << 16);  // B operand MN-major
     const uint32_t idesc2 = make_idesc(nb);
     const uint32_t smem_u = smem_u32(smem);
-    const uint32_t sbo1 = (p.flags & 1) ? 1024 : 512;
+    constexpr uint32_t sbo1 = 512;  // atoms of 4 K rows x 128 B
     mbar_wait(rready, 0);
     tc_fence_after();
     Pipe p1, p2;  // stage / phase of the tile GEMM1 and GEMM2 work on
@@ -350,7 +349,6 @@ int varimax_sweep_tc(const float* L, int64_t S, int64_t m, int64_t ld, const dou
   VtParams p{};
   p.S = S; p.nb = nb; p.ng = ng; p.k1 = k1;
   p.ntiles = (int)ceil_div(S, VT_TS);
-  p.flags = env_int("XEOFS_VT_FLAGS", 0);
   const int stage_bytes = nb * 512;
   const int budget = 227 * 1024 - 1024 /*alignment*/ - 512 /*barriers*/;
   int stages = budget / stage_bytes;
