@@ -8,7 +8,6 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libxeofs_b200.so")

@@ -8,7 +8,6 @@
 #include "common.cuh"
 
 namespace xb {
-int env_int(const char* name, int dflt);  // project_tc.cu
 
 
 // ------------------------------------------------------------------------------------------------

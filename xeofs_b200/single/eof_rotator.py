@@ -14,7 +14,6 @@ import torch
 
 from .. import _engine as E
 from .. import _labels as L
-from .._lib import lpad
 
 
 TC_WINDOW = 8  # iterations the stopping test of the tensor-core phase of the varimax iteration looks back
