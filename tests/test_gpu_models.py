@@ -139,6 +139,24 @@ def test_eof_api_corners_match_oracle():
     np.testing.assert_allclose(np.abs((m.components().values * o["components_2d"]).sum(axis=0)), 1.0, atol=1e-4)
 
 
+def test_eof_more_modes_than_one_kernel_block():
+    """n_modes + oversamples = 160 > 128: products in two column blocks, k-column algebra through the library
+    fallbacks; leading singular values against the oracle, orthonormal components, scores = A V."""
+    import xeofs_b200 as xb
+    T, S, k = 600, 64 * 64, 150
+    X = planted(T, S, 40, seed=33).reshape(T, 64, 64)
+    o = oeof.eof_fit(X, DIMS, "time", n_modes=k, random_state=3)
+    m = xb.single.EOF(n_modes=k, random_state=3).fit(xb.DataArray(X, DIMS), dim="time")
+    np.testing.assert_allclose(m.singular_values().values[:30], o["singular_values"][:30], rtol=1e-4)
+    V = m.components().values.reshape(-1, k)
+    np.testing.assert_allclose(V.T @ V, np.eye(k), atol=2e-4)
+    dots = (V[:, :20] * o["components_2d"][:, :20]).sum(axis=0)
+    assert (dots > 1 - 1e-4).all(), dots
+    A = o["A"]
+    sc = m.scores().values
+    np.testing.assert_allclose(sc[:, :20], A @ V[:, :20], atol=2e-3 * np.abs(sc[:, :20]).max())
+
+
 def test_bootstrapper_matches_oracle():
     """EOFBootstrapper (validation/bootstrapper.py:56-135) on the device: resampled fits + projection of the original
     samples against the numpy restatement, members seeded on both sides."""

@@ -297,6 +297,19 @@ def test_eof_variance_based_n_modes_weights_and_tmode():
     np.testing.assert_allclose(np.abs((m.components().values * o["components_2d"]).sum(axis=0)), 1.0, atol=1e-5)
 
 
+def test_eof_more_modes_than_one_kernel_block():
+    """n_modes + oversamples beyond the 128-column width of the device kernels: the engine runs the same algorithm,
+    the device layer splits the products into column blocks (exercised on the GPU by its twin)."""
+    import xeofs_b200 as xb
+    T, S, k = 300, 400, 130
+    X = planted(T, S, 40, seed=33).reshape(T, 20, 20)
+    o = oeof.eof_fit(X, DIMS, "time", n_modes=k, random_state=3)
+    m = xb.single.EOF(n_modes=k, random_state=3, ops=TorchCpuOps()).fit(xb.DataArray(X, DIMS), dim="time")
+    np.testing.assert_allclose(m.singular_values().values[:30], o["singular_values"][:30], rtol=1e-4)
+    V = m.components().values.reshape(-1, k)
+    np.testing.assert_allclose(V.T @ V, np.eye(k), atol=1e-4)
+
+
 def test_eof_list_input_host_logic():
     """A list of arrays (two variables on different grids): each scaled on its own, concatenated along the feature
     axis (preprocessing/preprocessor.py:208-228, concatenator.py:58-81); components come back one array per input."""

@@ -12,6 +12,9 @@ from . import _lib
 from ._lib import check, lpad, ptr
 
 
+BLOCK_L = 128  # width of the product kernels' accumulators and of the k-column kernels
+
+
 class Field:
     """One preprocessed field resident in HBM: raw X (T x S fp32, row-major) plus the per-feature
     vectors that fold Scaler.transform (preprocessing/scaler.py:146-153) into the operand load:
@@ -167,6 +170,11 @@ class CudaOps:
         algo = self.algo if algo is None else algo
         lp = lpad(l)
         Yt = out if out is not None else self.space_side(lp, f.S)
+        if l > BLOCK_L:  # wider than the kernels' accumulators: one streaming pass per block of 128 columns
+            for j0 in range(0, l, BLOCK_L):
+                w = min(BLOCK_L, l - j0)
+                self.project_S(f, W[:, j0:], w, algo=algo, out=Yt[j0:j0 + lpad(w)], tag=tag)
+            return Yt
         ws = self.workspace(f.T, f.S, l, algo)
         check(self._timed(tag + self._algo_tag(algo), l, lambda: self.lib.xeofs_b200_project_S(
             ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr), ptr(f.row_valid), ptr(W),
@@ -180,6 +188,11 @@ class CudaOps:
         algo = self.algo if algo is None else algo
         lp = lpad(l)
         Z = out if out is not None else self.empty((f.T, lp))
+        if l > BLOCK_L:
+            for j0 in range(0, l, BLOCK_L):
+                w = min(BLOCK_L, l - j0)
+                self.project_T(f, Yt[j0:], w, algo=algo, out=Z[:, j0:j0 + lpad(w)])
+            return Z
         ws = self.workspace(f.T, f.S, l, algo)
         check(self._timed("project_T" + self._algo_tag(algo), l, lambda: self.lib.xeofs_b200_project_T(
             ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr), ptr(f.row_valid), ptr(Yt),
@@ -197,6 +210,12 @@ class CudaOps:
     # ------------------------------------------------------------------ k-column linear algebra
     def gram(self, M, n, l, side, out=None, accumulate=False):
         G = out if out is not None else self.empty((l, l), torch.float64)
+        if l > BLOCK_L:  # beyond the k-column kernels' width: library fp64 products on the (rarely this wide) block
+            A = (M[:n, :l] if side == 0 else M[:l, :n].t()).double()
+            Gn = A.t() @ A
+            G.copy_(G + Gn if accumulate else Gn)
+            self.launches += 2
+            return G
         check(self.lib.xeofs_b200_gram(ptr(M), n, l, int(M.stride(0)), side, ptr(G), int(accumulate), self._stream()),
               "gram")
         self.launches += 2
@@ -206,6 +225,14 @@ class CudaOps:
         l = int(G.shape[0])
         Rinv = self.empty((l, l), torch.float64)
         info = info if info is not None else self.empty(2, torch.int32)
+        if l > BLOCK_L:
+            Lc, err = torch.linalg.cholesky_ex(G)
+            Rinv.copy_(torch.linalg.solve_triangular(Lc.t(), torch.eye(l, dtype=torch.float64, device=G.device),
+                                                     upper=True))
+            info[0] = 0
+            info[1] = ((err != 0) | ~torch.isfinite(G).all()).to(torch.int32)
+            self.launches += 2
+            return Rinv, info
         check(self.lib.xeofs_b200_chol_inv(ptr(G), l, ptr(Rinv), ptr(info), self._stream()), "chol_inv")
         self.launches += 1
         return Rinv, info
@@ -229,9 +256,27 @@ class CudaOps:
             f = Field(In[:l, :n], zero, one, None, None)
             if out is None:
                 out = self.space_side(kp, n)
+            if k > BLOCK_L and out.data_ptr() == In.data_ptr():
+                # in place over several column blocks: a later block would read rows an earlier one has overwritten
+                tmp = self.project_S(f, W, k, algo=_lib.ALGO_TF32X3, out=self.space_side(kp, n), tag="apply_S")
+                out[:kp].copy_(tmp)
+                return out
             return self.project_S(f, W, k, algo=_lib.ALGO_TF32X3, out=out, tag="apply_S")
         if out is None:
             out = self.space_side(kp, n) if side == 1 else self.zeros((n, kp))
+        if l > BLOCK_L or k > BLOCK_L:
+            A = (In[:n, :l] if side == 0 else In[:l, :n].t()).double()
+            B = A @ Mat[:l, :k].double()
+            if colscale is not None:
+                B = B * colscale.double()[None, :k]
+            if side == 0:
+                out[:, :k] = B.float()
+                out[:, k:] = 0
+            else:
+                out[:k] = B.t().float()
+                out[k:] = 0
+            self.launches += 2
+            return out
         check(self.lib.xeofs_b200_apply(ptr(In), n, l, int(In.stride(0)), side, ptr(Mat), int(Mat.stride(0)), k,
                                         ptr(colscale), ptr(out), int(out.stride(0)), self._stream()), "apply")
         self.launches += 1
@@ -239,6 +284,10 @@ class CudaOps:
 
     def sym_eig(self, G):
         l = int(G.shape[0])
+        if l > BLOCK_L:
+            ev, V = torch.linalg.eigh(0.5 * (G + G.t()))
+            self.launches += 1
+            return ev.flip(0).contiguous(), V.flip(1).contiguous()
         evals = self.empty(l, torch.float64)
         evecs = self.empty((l, l), torch.float64)
         work = self.empty((l + 1) * (l + 1), torch.float64)

@@ -17,7 +17,8 @@ import torch
 
 from ._lib import lpad
 
-MAX_L = 128  # widest k-column block the kernels take
+MAX_L = 128         # widest k-column block the kernels take in one go (wider sketches run in blocks of it)
+MAX_L_TOTAL = 1024  # widest sketch accepted at all
 
 
 # ---------------------------------------------------------------------------------------------- comm
@@ -314,9 +315,9 @@ def randomized_svd(ops, op, k, n_oversamples=10, n_iter="auto", random_state=Non
     """
     n_r, n_c = op.shape
     l = min(k + n_oversamples, n_r, n_c)
-    if l > MAX_L:
+    if l > MAX_L_TOTAL:
         raise NotImplementedError(
-            f"n_modes + n_oversamples = {k + n_oversamples} exceeds the kernels' block width {MAX_L}"
+            f"n_modes + n_oversamples = {k + n_oversamples} exceeds the widest sketch of this build ({MAX_L_TOTAL})"
         )
     if n_iter == "auto":
         n_iter = 7 if k < 0.1 * min(n_r, n_c) else 4
