@@ -77,13 +77,16 @@ def mca_fit(
         except np.linalg.LinAlgError:
             Tinv[i] = np.linalg.pinv(T)
         mats[i] = Xi @ T
+    A1u, A2u = A1, A2   # un-whitened (PCA-space or physical) data
     A1, A2 = mats
     C = cross_covariance(A1, A2)
     Q1, s, Q2 = decompose(C, n_modes=n_modes, solver=solver, random_state=random_state,
                           solver_kwargs=solver_kwargs)
-    tsc = (np.abs(C) ** 2).sum()
+    # cpcca.py:991-1000: total squared covariance of the UN-whitened cross-covariance
+    tsc = (np.abs(cross_covariance(A1u, A2u)) ** 2).sum()
     scores1 = A1 @ Q1
     scores2 = A2 @ Q2
+    Q1_w, Q2_w = Q1, Q2   # singular vectors in the (whitened, PCA) space they were computed in
     # the accessors return the patterns un-whitened (whitener.py:201-213) and in physical space (pca.py:161-171)
     if Tinv[0] is not None:
         Q1 = Tinv[0].conj().T @ Q1
@@ -91,7 +94,27 @@ def mca_fit(
         Q2 = Tinv[1].conj().T @ Q2
     if use_pca:
         Q1, Q2 = V1 @ Q1, V2 @ Q2
+    # cpcca.py:418-512 squared covariance fraction; :331-416 correlation coefficients of the scores
+    Q1w, Q2w = Q1_w, Q2_w
+    scf = []
+    for m_ in range(Q1w.shape[1]):
+        X1r = np.outer(scores1[:, m_], Q1w[:, m_].conj())
+        X2r = np.outer(scores2[:, m_], Q2w[:, m_].conj())
+        if Tinv[0] is not None:
+            X1r = X1r @ Tinv[0]
+        if Tinv[1] is not None:
+            X2r = X2r @ Tinv[1]
+        res = np.linalg.norm((A1u - X1r).conj().T @ (A2u - X2r) / (A1u.shape[0] - 1)) ** 2
+        scf.append(max(0.0, 1.0 - res / tsc))
+
+    def _corr(A, B):
+        A = A / A.std(axis=0)
+        B = B / B.std(axis=0)
+        return A.conj().T @ B / (A.shape[0] - 1)
     return {
+        "squared_covariance_fraction": np.array(scf),
+        "cross_correlation_coefficients": np.diag(_corr(scores1, scores2)).real,
+        "correlation_coefficients_X": _corr(scores1, scores1),
         "n_pca_modes": None if V1 is None else (V1.shape[1], V2.shape[1]),
         "A1": A1, "A2": A2, "fitted1": f1, "fitted2": f2, "C": C,
         "components1_2d": Q1, "components2_2d": Q2,

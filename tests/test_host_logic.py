@@ -134,6 +134,9 @@ def test_mca_host_logic():
     m.fit(xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")
     np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-5)
     np.testing.assert_allclose(m.total_squared_covariance(), o["total_squared_covariance"], rtol=1e-5)
+    np.testing.assert_allclose(m.squared_covariance_fraction().values, o["squared_covariance_fraction"], rtol=1e-4)
+    np.testing.assert_allclose(m.cross_correlation_coefficients().values, o["cross_correlation_coefficients"], rtol=1e-4)
+    np.testing.assert_allclose(m.correlation_coefficients_X(), o["correlation_coefficients_X"], atol=1e-4)
     c1, c2 = m.components()
     v1 = c1.values[~np.isnan(c1.values).any(axis=1)]
     dots = np.abs((v1 * o["components1_2d"]).sum(axis=0))
@@ -201,6 +204,12 @@ def test_cpcca_family_host_logic(cls, alpha):
     for sc, osc in ((s1, o["scores1"]), (s2, o["scores2"])):
         scale = np.abs(osc).max(axis=0)
         np.testing.assert_allclose(sc.values / scale, osc / scale, atol=1e-3)
+    # total squared covariance of the un-whitened cross-covariance, squared covariance fraction, score correlations
+    np.testing.assert_allclose(m.total_squared_covariance(), o["total_squared_covariance"], rtol=1e-4)
+    np.testing.assert_allclose(m.squared_covariance_fraction().values, o["squared_covariance_fraction"], rtol=1e-3,
+                               atol=1e-6)
+    np.testing.assert_allclose(m.cross_correlation_coefficients().values, o["cross_correlation_coefficients"], rtol=1e-4)
+    np.testing.assert_allclose(m.correlation_coefficients_X(), o["correlation_coefficients_X"], atol=1e-4)
     with pytest.raises(NotImplementedError, match="use_pca"):
         xb.cross.CCA(n_modes=k, use_pca=False, ops=TorchCpuOps()).fit(
             xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")

@@ -198,6 +198,7 @@ class MCA:
             lam = sv**2 / n
             t = torch.where(lam > torch.finfo(torch.float64).eps, lam ** ((a - 1.0) / 2.0), torch.zeros_like(lam))
             tw.append(torch.ones_like(lam) if a == 1.0 else t)
+        X1u, X2u = X1, X2
         X1, X2 = X1 * tw[0], X2 * tw[1]
         C = X1.t() @ X2 / (n - 1)                                   # cpcca.py:1008-1015, r1 x r2
         rank = min(C.shape)
@@ -228,11 +229,13 @@ class MCA:
         self._Q1t, self._Q2t, self._sc1, self._sc2, self._s = comps[0], comps[1], sc1, sc2, s
         self._f1, self._f2 = f1, f2
         self.n_pca_modes_ = (int(s1.numel()), int(s2.numel()))
+        self._pca_ctx = dict(X1u=X1u, X2u=X2u, Q1=Q1, Q2=Q2, t1=tw[0], t2=tw[1], R1=X1 @ Q1, R2=X2 @ Q2, n=n)
         self.data = {
             "singular_values": s, "squared_covariance": s**2,
             "norm1": torch.linalg.norm(X1 @ Q1, dim=0), "norm2": torch.linalg.norm(X2 @ Q2, dim=0),
             "idx_modes_sorted": torch.argsort(s, descending=True),
-            "total_squared_covariance": float((C**2).sum().item()),   # cpcca.py:991-1000, in the PCA space
+            # cpcca.py:991-1000: of the UN-whitened cross-covariance (in the PCA space)
+            "total_squared_covariance": float(((X1u.t() @ X2u / (n - 1)) ** 2).sum().item()),
         }
         return self
 
@@ -339,9 +342,51 @@ class MCA:
         return self.data["total_squared_covariance"]
 
     def squared_covariance_fraction(self):
-        """cross/mca.py: SCF_i = s_i^2 / sum |C|^2."""
-        return self._mode_array(self.data["squared_covariance"] / self.total_squared_covariance(),
-                                "squared_covariance_fraction")
+        """cpcca.py:418-512: 1 - ||(X - X_m)^T (Y - Y_m)||_F^2 / (n-1)^2 / sum |C|^2 with X_m, Y_m the un-whitened
+        rank-one reconstructions of mode m, negative values set to zero.  For MCA (alpha = 1) that is s_m^2 / sum |C|^2,
+        which is what the implicit (use_pca=False) path returns."""
+        ctx = getattr(self, "_pca_ctx", None)
+        tsc = self.total_squared_covariance()
+        if ctx is None or self._alpha == (1.0, 1.0):
+            return self._mode_array(self.data["squared_covariance"] / tsc, "squared_covariance_fraction")
+        inv1 = torch.where(ctx["t1"] > 0, 1.0 / ctx["t1"], torch.zeros_like(ctx["t1"]))
+        inv2 = torch.where(ctx["t2"] > 0, 1.0 / ctx["t2"], torch.zeros_like(ctx["t2"]))
+        out = []
+        for m in range(self.k):
+            X1r = torch.outer(ctx["R1"][:, m], ctx["Q1"][:, m] * inv1)   # whitener.py:176-188 on the reconstruction
+            X2r = torch.outer(ctx["R2"][:, m], ctx["Q2"][:, m] * inv2)
+            res = torch.linalg.norm((ctx["X1u"] - X1r).t() @ (ctx["X2u"] - X2r) / (ctx["n"] - 1)) ** 2
+            out.append(1.0 - res / tsc)
+        scf = torch.clamp(torch.stack(out), min=0.0)
+        return self._mode_array(scf, "squared_covariance_fraction")
+
+    # ------------------------------------------------------------------ score statistics (cpcca.py:331-416)
+    def _valid_scores(self):
+        vs = self._f1.valid_sample if self._f1.n_samples < self._f1.T else None
+        r1, r2 = self._sc1[:, : self.k].double(), self._sc2[:, : self.k].double()
+        return (r1, r2) if vs is None else (r1[vs], r2[vs])
+
+    @staticmethod
+    def _corr(A, B, diagonal=False):
+        """cpcca.py:910-985 with method="correlation": columns divided by their (population) standard deviation,
+        then A^T B / (n - 1); centred data assumed."""
+        A = A / A.std(0, unbiased=False)
+        B = B / B.std(0, unbiased=False)
+        if diagonal:
+            return (A * B).sum(0) / (A.shape[0] - 1)
+        return A.t() @ B / (A.shape[0] - 1)
+
+    def cross_correlation_coefficients(self):
+        r1, r2 = self._valid_scores()
+        return self._mode_array(self._corr(r1, r2, diagonal=True), "cross_correlation_coefficients")
+
+    def correlation_coefficients_X(self):
+        r1, _ = self._valid_scores()
+        return self._corr(r1, r1).cpu().numpy()
+
+    def correlation_coefficients_Y(self):
+        _, r2 = self._valid_scores()
+        return self._corr(r2, r2).cpu().numpy()
 
     def get_params(self):
         return dict(self._params)
