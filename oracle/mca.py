@@ -111,7 +111,23 @@ def mca_fit(
         A = A / A.std(axis=0)
         B = B / B.std(axis=0)
         return A.conj().T @ B / (A.shape[0] - 1)
+    # homogeneous / heterogeneous patterns (cpcca.py:726-898; utils/optional/statistics.py:51-106): Pearson
+    # correlation of the (back-transformed) input data with the scores, two-sided p-values from the beta distribution
+    import scipy.stats
+    P1 = A1u @ V1.conj().T if use_pca else A1u
+    P2 = A2u @ V2.conj().T if use_pca else A2u
+
+    def _pearson(X, Y):
+        r = (X / X.std(axis=0)).conj().T @ (Y / Y.std(axis=0)) / X.shape[0]
+        a = X.shape[0] / 2 - 1
+        return r, 2 * scipy.stats.beta(a, a, loc=-1, scale=2).cdf(-np.abs(r))
+    hom1, phom1 = _pearson(P1, scores1)
+    hom2, phom2 = _pearson(P2, scores2)
+    het1, _ = _pearson(P1, scores2)
+    het2, _ = _pearson(P2, scores1)
     return {
+        "homogeneous_patterns": (hom1, hom2), "pvalues_homogeneous": (phom1, phom2),
+        "heterogeneous_patterns": (het1, het2),
         "squared_covariance_fraction": np.array(scf),
         "cross_correlation_coefficients": np.diag(_corr(scores1, scores2)).real,
         "correlation_coefficients_X": _corr(scores1, scores1),

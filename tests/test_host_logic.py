@@ -120,6 +120,22 @@ def test_transform_inverse_transform_host_logic():
 
 
 # ---------------------------------------------------------------- MCA / rotator host logic vs oracle
+def _check_patterns(m, o, valid1=None):
+    """homogeneous / heterogeneous patterns and p-values (cpcca.py:726-898) against the oracle."""
+    (h1, h2), (p1, p2) = m.homogeneous_patterns()
+    (g1, g2), _ = m.heterogeneous_patterns()
+    for got, ref, valid in ((h1, o["homogeneous_patterns"][0], valid1), (h2, o["homogeneous_patterns"][1], None),
+                            (g1, o["heterogeneous_patterns"][0], valid1), (g2, o["heterogeneous_patterns"][1], None),
+                            (p1, o["pvalues_homogeneous"][0], valid1), (p2, o["pvalues_homogeneous"][1], None)):
+        v = got.values.reshape(-1, got.values.shape[-1])
+        if valid is not None:
+            assert np.isnan(v[~valid]).all()
+            v = v[valid]
+        np.testing.assert_allclose(v, ref, atol=2e-4)
+    with pytest.raises(NotImplementedError, match="statsmodels"):
+        m.homogeneous_patterns(correction="fdr_bh")
+
+
 def test_mca_host_logic():
     import xeofs_b200 as xb
     T, k = 150, 5
@@ -137,6 +153,7 @@ def test_mca_host_logic():
     np.testing.assert_allclose(m.squared_covariance_fraction().values, o["squared_covariance_fraction"], rtol=1e-4)
     np.testing.assert_allclose(m.cross_correlation_coefficients().values, o["cross_correlation_coefficients"], rtol=1e-4)
     np.testing.assert_allclose(m.correlation_coefficients_X(), o["correlation_coefficients_X"], atol=1e-4)
+    _check_patterns(m, o, valid1=~np.isnan(X[0]))
     c1, c2 = m.components()
     v1 = c1.values[~np.isnan(c1.values).any(axis=1)]
     dots = np.abs((v1 * o["components1_2d"]).sum(axis=0))
@@ -173,6 +190,8 @@ def test_mca_pca_stage_host_logic():
         for sc, osc in ((s1, o["scores1"]), (s2, o["scores2"])):
             scale = np.abs(osc).max(axis=0)
             np.testing.assert_allclose(sc.values / scale, osc / scale, atol=1e-3)
+        if npm == 12:
+            _check_patterns(m, o, valid1=~np.isnan(X[0]))
 
 
 @pytest.mark.parametrize("cls,alpha", [("CCA", (0.0, 0.0)), ("RDA", (0.0, 1.0)), ("CPCCA", 0.2)])
@@ -210,6 +229,7 @@ def test_cpcca_family_host_logic(cls, alpha):
                                atol=1e-6)
     np.testing.assert_allclose(m.cross_correlation_coefficients().values, o["cross_correlation_coefficients"], rtol=1e-4)
     np.testing.assert_allclose(m.correlation_coefficients_X(), o["correlation_coefficients_X"], atol=1e-4)
+    _check_patterns(m, o)
     with pytest.raises(NotImplementedError, match="use_pca"):
         xb.cross.CCA(n_modes=k, use_pca=False, ops=TorchCpuOps()).fit(
             xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")

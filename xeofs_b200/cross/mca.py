@@ -229,7 +229,8 @@ class MCA:
         self._Q1t, self._Q2t, self._sc1, self._sc2, self._s = comps[0], comps[1], sc1, sc2, s
         self._f1, self._f2 = f1, f2
         self.n_pca_modes_ = (int(s1.numel()), int(s2.numel()))
-        self._pca_ctx = dict(X1u=X1u, X2u=X2u, Q1=Q1, Q2=Q2, t1=tw[0], t2=tw[1], R1=X1 @ Q1, R2=X2 @ Q2, n=n)
+        self._pca_ctx = dict(X1u=X1u, X2u=X2u, Q1=Q1, Q2=Q2, t1=tw[0], t2=tw[1], R1=X1 @ Q1, R2=X2 @ Q2, n=n,
+                             U1=U1, U2=U2)
         self.data = {
             "singular_values": s, "squared_covariance": s**2,
             "norm1": torch.linalg.norm(X1 @ Q1, dim=0), "norm2": torch.linalg.norm(X2 @ Q2, dim=0),
@@ -375,6 +376,72 @@ class MCA:
         if diagonal:
             return (A * B).sum(0) / (A.shape[0] - 1)
         return A.t() @ B / (A.shape[0] - 1)
+
+    # ------------------------------------------------------------------ homogeneous / heterogeneous patterns
+    def _data_score_correlation(self, i, R):
+        """Pearson correlation (utils/optional/statistics.py:51-76) between every feature of field i — in physical
+        space; with the PCA stage that is the rank-r reconstruction the reference back-transforms (cpcca.py:768-775) —
+        and the k score series R (n x k fp64, valid samples).  Returns (k x S) on the device."""
+        ops, comm, k = self.ops, self.comm, self.k
+        ff = (self._f1, self._f2)[i]
+        n = ff.n_samples
+        vs = ff.valid_sample if n < ff.T else None
+        Rn = R / R.std(0, unbiased=False)
+        W = ops.zeros((ff.T, lpad(k)))
+        ctx = getattr(self, "_pca_ctx", None)
+        if ctx is None:
+            # A^T R / (n std(A)): one streaming pass; std(A_s) = raw std * |dscale| (the field is centred)
+            if vs is None:
+                W[:, :k] = Rn.to(torch.float32)
+            else:
+                W[vs, :k] = Rn.to(torch.float32)
+            num = ops.project_S(ff.field, W, k, algo=ops.accurate_algo)
+            std = (ff.std * ff.field.dscale.abs()).double()
+        else:
+            # the reconstruction is U S V^T with V S = A^T U:  A_r^T R = A^T U (U^T R),  sum_t A_r[t,s]^2 = |(A^T U)_s|^2
+            U = ctx["U1" if i == 0 else "U2"]
+            Uv = U if vs is None else U[vs]
+            W[:, :k] = (U @ (Uv.t() @ Rn)).to(torch.float32)
+            num = ops.project_S(ff.field, W, k, algo=ops.accurate_algo)
+            ss = torch.zeros(ff.S, dtype=torch.float64, device=ops.device)
+            for j0 in range(0, int(U.shape[1]), 128):
+                w = min(128, int(U.shape[1]) - j0)
+                Wb = ops.zeros((ff.T, lpad(w)))
+                Wb[:, :w] = U[:, j0:j0 + w].to(torch.float32)
+                Yt = ops.project_S(ff.field, Wb, w, algo=ops.accurate_algo)
+                ss += (Yt[:w].double() ** 2).sum(0)
+            std = torch.sqrt(ss / n)
+        return num[:k].double() / (n * std)[None, :]
+
+    def _patterns(self, R1, R2, names, correction, alpha):
+        if correction is not None:
+            raise NotImplementedError("multiple-test correction of the p-values needs statsmodels, which this build "
+                                      "does not carry; pass correction=None")
+        import scipy.stats
+
+        n = self._f1.n_samples
+        dist = scipy.stats.beta(n / 2 - 1, n / 2 - 1, loc=-1, scale=2)  # statistics.py:92-106
+        pats, pvals = [], []
+        for i, (R, pp, name) in enumerate(zip((R1, R2), (self.preprocessor1, self.preprocessor2), names)):
+            corr = self._data_score_correlation(i, R)
+            buf = self.ops.space_side(lpad(self.k), int(corr.shape[1]), zero=True)
+            buf[: self.k] = corr.to(torch.float32)
+            pats.append(pp.components_to_nd(buf, self.k, name))
+            pv = 2.0 * dist.cdf(-np.abs(corr.cpu().numpy()))
+            buf[: self.k] = torch.as_tensor(pv, dtype=torch.float32, device=buf.device)
+            pvals.append(pp.components_to_nd(buf, self.k, "pvalues_of_" + name))
+        return tuple(pats), tuple(pvals)
+
+    def homogeneous_patterns(self, correction=None, alpha=0.05):
+        """cpcca.py:726-811: correlation of each field with its OWN scores, and two-sided p-values."""
+        r1, r2 = self._valid_scores()
+        return self._patterns(r1, r2, ("left_homogeneous_patterns", "right_homogeneous_patterns"), correction, alpha)
+
+    def heterogeneous_patterns(self, correction=None, alpha=0.05):
+        """cpcca.py:813-898: correlation of each field with the scores of the OTHER field."""
+        r1, r2 = self._valid_scores()
+        return self._patterns(r2, r1, ("left_heterogeneous_patterns", "right_heterogeneous_patterns"), correction,
+                              alpha)
 
     def cross_correlation_coefficients(self):
         r1, r2 = self._valid_scores()
