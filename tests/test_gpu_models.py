@@ -269,6 +269,34 @@ def test_cpcca_family_matches_oracle(cls, alpha):
         np.testing.assert_allclose(sc.values / scale, osc / scale, atol=2e-3)
 
 
+@pytest.mark.parametrize("use_pca", [False, True])
+def test_mca_patterns_and_score_statistics(use_pca):
+    """homogeneous / heterogeneous patterns with p-values, squared covariance fraction and score correlations
+    (cpcca.py:331-512, 726-898) on the device against the numpy restatement."""
+    import xeofs_b200 as xb
+    T, S1, S2, k = 300, 40 * 30, 20 * 36, 4
+    X, Y = _coupled_fields(T, S1, S2, 2 * k, seed=23)
+    X = X.reshape(T, 40, 30)
+    Y = Y.reshape(T, 20, 36)
+    X[:, 3, 5] = np.nan
+    kw = dict(n_modes=k, random_state=3, use_pca=use_pca, n_pca_modes=2 * k)
+    o = omca.mca_fit(X, Y, DIMS, DIMS, "time", pca_random_state=1, **kw)
+    m = xb.cross.MCA(**kw).fit(xb.DataArray(X, DIMS), xb.DataArray(Y, DIMS), dim="time")
+    np.testing.assert_allclose(m.squared_covariance_fraction().values, o["squared_covariance_fraction"], rtol=1e-3)
+    np.testing.assert_allclose(m.cross_correlation_coefficients().values, o["cross_correlation_coefficients"], rtol=1e-4)
+    (h1, h2), (p1, p2) = m.homogeneous_patterns()
+    (g1, g2), _ = m.heterogeneous_patterns()
+    valid1 = o["fitted1"]["is_valid_feature"]
+    for got, ref, valid in ((h1, o["homogeneous_patterns"][0], valid1), (h2, o["homogeneous_patterns"][1], None),
+                            (g1, o["heterogeneous_patterns"][0], valid1), (g2, o["heterogeneous_patterns"][1], None),
+                            (p1, o["pvalues_homogeneous"][0], valid1), (p2, o["pvalues_homogeneous"][1], None)):
+        v = got.values.reshape(-1, k)
+        if valid is not None:
+            assert np.isnan(v[~valid]).all()
+            v = v[valid]
+        np.testing.assert_allclose(v, ref, atol=5e-4)
+
+
 def test_mca_total_squared_covariance_wide_fields():
     """cpcca.py:991-1000 at a width (S >= 2^16) where the sample Gram matrices take the single rounded TF32 product
     (XEOFS_ALGO_TF32X1R): sum |C|^2 = <A1 A1^T, A2 A2^T> / (n-1)^2 against fp64 torch on the preprocessed fields."""
