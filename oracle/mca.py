@@ -30,6 +30,34 @@ def cross_covariance(X, Y):
     return X.conj().T @ Y / (X.shape[0] - 1)
 
 
+def whitener_transform(X, alpha):
+    """preprocessing/whitener.py:111-133 with linalg/_numpy/_utils.py:6-33: T = C^((alpha-1)/2) for C = X^H X / n
+    through the SVD of C (singular values <= eps cut), Tinv = inv(T) (pinv when singular)."""
+    C = X.conj().T @ X / X.shape[0]
+    _, sv, Vh = np.linalg.svd(C)
+    keep = sv > np.finfo(sv.dtype).eps
+    Vk, sk = Vh[keep].conj().T, sv[keep]
+    T = (Vk * sk ** ((alpha - 1.0) / 2.0)) @ Vk.conj().T
+    T = T if np.iscomplexobj(C) else T.real
+    try:
+        Tinv = np.linalg.inv(T)
+    except np.linalg.LinAlgError:
+        Tinv = np.linalg.pinv(T)
+    return T, Tinv
+
+
+def residual_squared_covariance(X, Y, Xrec, Yrec):
+    """cross/cpcca.py:436-443: squared Frobenius norm of the cross-covariance of the residuals."""
+    dX, dY = X - Xrec, Y - Yrec
+    return np.linalg.norm(dX.conj().T @ dY / (dX.shape[0] - 1)) ** 2
+
+
+def pearson_correlation(X, Y):
+    """utils/optional/statistics.py:51-55: columns scaled by their population standard deviation, X^H Y / n
+    (centred data assumed)."""
+    return (X / X.std(0)).conj().T @ (Y / Y.std(0)) / X.shape[0]
+
+
 def mca_fit(
     X, Y, dims_x, dims_y, sample_dims,
     coords_x=None, coords_y=None,
@@ -66,17 +94,8 @@ def mca_fit(
     for i in range(2):
         if float(al[i]) == 1.0:
             continue
-        Xi = mats[i]
-        Ci = Xi.conj().T @ Xi / Xi.shape[0]
-        _, sv, Vh = np.linalg.svd(Ci)
-        keep = sv > np.finfo(sv.dtype).eps
-        Vk, sk = Vh[keep].conj().T, sv[keep]
-        T = (Vk * sk ** ((float(al[i]) - 1.0) / 2.0)) @ Vk.conj().T
-        try:
-            Tinv[i] = np.linalg.inv(T)
-        except np.linalg.LinAlgError:
-            Tinv[i] = np.linalg.pinv(T)
-        mats[i] = Xi @ T
+        T, Tinv[i] = whitener_transform(mats[i], float(al[i]))
+        mats[i] = mats[i] @ T
     A1u, A2u = A1, A2   # un-whitened (PCA-space or physical) data
     A1, A2 = mats
     C = cross_covariance(A1, A2)
@@ -104,7 +123,7 @@ def mca_fit(
             X1r = X1r @ Tinv[0]
         if Tinv[1] is not None:
             X2r = X2r @ Tinv[1]
-        res = np.linalg.norm((A1u - X1r).conj().T @ (A2u - X2r) / (A1u.shape[0] - 1)) ** 2
+        res = residual_squared_covariance(A1u, A2u, X1r, X2r)
         scf.append(max(0.0, 1.0 - res / tsc))
 
     def _corr(A, B):
@@ -118,7 +137,7 @@ def mca_fit(
     P2 = A2u @ V2.conj().T if use_pca else A2u
 
     def _pearson(X, Y):
-        r = (X / X.std(axis=0)).conj().T @ (Y / Y.std(axis=0)) / X.shape[0]
+        r = pearson_correlation(X, Y)
         a = X.shape[0] / 2 - 1
         return r, 2 * scipy.stats.beta(a, a, loc=-1, scale=2).cdf(-np.abs(r))
     hom1, phom1 = _pearson(P1, scores1)

@@ -10,6 +10,9 @@ have no xarray dependency and are executed verbatim from /root/reference:
   * xeofs/linalg/_numpy/_rotation.py _varimax, _promax
   * xeofs/cross/cpcca.py:1008-1015   CPCCA._compute_cross_covariance_numpy  (function body lifted via ast)
   * xeofs/utils/xarray_utils.py:256-270 _np_sqrt_cos_lat_weights             (function body lifted via ast)
+  * xeofs/linalg/_numpy/_utils.py     _fractional_matrix_power (the Whitener's transform, whitener.py:111-133)
+  * xeofs/cross/cpcca.py:418-443      _compute_residual_variance_numpy      (nested function, lifted via ast)
+  * xeofs/utils/optional/statistics.py:51-55 _correlation_coefficients_numpy (nested function, lifted via ast)
 `dask` is stubbed: those files import it only for isinstance checks / the dask branch.
 Inputs are the reference's own test fixtures re-created with numpy (tests/conftest.py:225-240 mock_data_array,
 seed 7; tests/models/cross/test_cpcca_rotator.py:9-22 generate_random_data) plus a planted-spectrum field.
@@ -130,6 +133,29 @@ def main():
     # ---- coslat
     lat = np.array([-95.0, -90.0, -60.0, -33.3, 0.0, 20.0, 45.0, 89.9, 90.0, 91.0])
     out.update(coslat_lat=lat, coslat_w=coslat(lat))
+
+    # ---- fractional whitening (preprocessing/whitener.py:111-133 calls _fractional_matrix_power with solver="full")
+    utl_mod = _load("xeofs.linalg._numpy._utils", f"{REF}/xeofs/linalg/_numpy/_utils.py")
+    rw = np.random.default_rng(17)
+    Xw = rw.standard_normal((120, 7)) * np.array([9.0, 6.0, 4.0, 2.5, 1.5, 1.0, 0.6])
+    Xw = Xw @ np.linalg.qr(rw.standard_normal((7, 7)))[0]
+    Xw = Xw - Xw.mean(axis=0)
+    Cw = Xw.conj().T @ Xw / Xw.shape[0]                      # whitener.py:124-125
+    out.update(whit_X=Xw)
+    for alpha in (0.0, 0.2, 0.7):
+        out[f"whit_T_alpha{alpha}"] = utl_mod._fractional_matrix_power(Cw, (alpha - 1) / 2, random_state=3,
+                                                                        solver="full")
+
+    # ---- residual squared covariance of one mode (cpcca.py:418-443) and the Pearson correlation of
+    #      utils/optional/statistics.py:51-55 (nested functions, lifted unmodified)
+    resid = _lift(f"{REF}/xeofs/cross/cpcca.py", "_compute_residual_variance_numpy")
+    pear = _lift(f"{REF}/xeofs/utils/optional/statistics.py", "_correlation_coefficients_numpy")
+    Yw = rw.standard_normal((120, 5))
+    Yw = Yw - Yw.mean(axis=0)
+    Xrec = np.outer(Xw @ rw.standard_normal(7), rw.standard_normal(7))
+    Yrec = np.outer(Yw @ rw.standard_normal(5), rw.standard_normal(5))
+    out.update(resid_Y=Yw, resid_Xrec=Xrec, resid_Yrec=Yrec, resid_value=np.array(resid(Xw, Yw, Xrec, Yrec)),
+               pearson_XY=pear(Xw, Yw))
 
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), {k: v.shape for k, v in out.items()})

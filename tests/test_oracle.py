@@ -1,5 +1,7 @@
 """CPU: pin the oracle against (a) golden vectors produced by executing the reference's own numpy source
 (tests/golden/make_golden.py) and (b) the invariants the reference's test-suite asserts for this path."""
+import os
+
 import numpy as np
 import pytest
 
@@ -178,3 +180,19 @@ def test_mca_total_squared_covariance():
     s_exact = np.linalg.svd(cov, compute_uv=False)[:5]
     np.testing.assert_allclose(m["singular_values"], s_exact, rtol=1e-8)
     np.testing.assert_allclose(m["norm1"], np.linalg.norm(m["scores1"], axis=0))
+
+
+def test_whitener_residual_and_pearson_against_reference_vectors():
+    """Fractional whitening (preprocessing/whitener.py:111-133 -> linalg/_numpy/_utils.py:6-33), the residual squared
+    covariance of cpcca.py:436-443 and the Pearson correlation of utils/optional/statistics.py:51-55 were executed
+    from the reference's source (tests/golden/make_golden.py); the oracle's restatements must reproduce them."""
+    from oracle import mca as omca
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+    X = g["whit_X"]
+    for alpha in (0.0, 0.2, 0.7):
+        T, Tinv = omca.whitener_transform(X, alpha)
+        np.testing.assert_allclose(T, g[f"whit_T_alpha{alpha}"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(T @ Tinv, np.eye(X.shape[1]), atol=1e-9)
+    np.testing.assert_allclose(omca.residual_squared_covariance(X, g["resid_Y"], g["resid_Xrec"], g["resid_Yrec"]),
+                               float(g["resid_value"]), rtol=1e-12)
+    np.testing.assert_allclose(omca.pearson_correlation(X, g["resid_Y"]), g["pearson_XY"], rtol=1e-12, atol=1e-15)
