@@ -144,7 +144,21 @@ def mca_fit(
     hom2, phom2 = _pearson(P2, scores2)
     het1, _ = _pearson(P1, scores2)
     het2, _ = _pearson(P2, scores1)
+    # transform / predict / inverse_transform (cpcca.py:227-306; base_model_cross_set.py:323-463)
+    G_pred = scores1.conj().T @ scores2 / np.linalg.norm(scores1, axis=0) ** 2
+
+    def _to_model_space(A, V, T):
+        A = A @ V if V is not None else A
+        return A @ T if T is not None else A
+    T1 = None if Tinv[0] is None else np.linalg.inv(Tinv[0])
+    T2 = None if Tinv[1] is None else np.linalg.inv(Tinv[1])
+    helpers = {
+        "transform1": lambda A: _to_model_space(A, V1 if use_pca else None, T1) @ Q1_w,
+        "transform2": lambda A: _to_model_space(A, V2 if use_pca else None, T2) @ Q2_w,
+        "predict": lambda A: _to_model_space(A, V1 if use_pca else None, T1) @ Q1_w @ G_pred,
+    }
     return {
+        "helpers": helpers,
         "homogeneous_patterns": (hom1, hom2), "pvalues_homogeneous": (phom1, phom2),
         "heterogeneous_patterns": (het1, het2),
         "squared_covariance_fraction": np.array(scf),

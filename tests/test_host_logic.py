@@ -235,6 +235,55 @@ def test_cpcca_family_host_logic(cls, alpha):
             xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")
 
 
+@pytest.mark.parametrize("mode", ["implicit", "pca", "cca"])
+def test_cross_transform_predict_inverse_host_logic(mode):
+    """transform / predict / inverse_transform of the cross models (cpcca.py:227-306 behind the back-transforms of
+    base_model_cross_set.py:323-463) against the oracle, on unseen samples."""
+    import xeofs_b200 as xb
+    from oracle import preprocess as opp
+    T, k = 150, 3
+    rng = np.random.default_rng(5)
+    U = np.linalg.qr(rng.standard_normal((T, 2 * k)))[0]
+    sig = 100 * 0.7 ** np.arange(2 * k)
+    X = ((U * sig) @ np.linalg.qr(rng.standard_normal((300, 2 * k)))[0].T + 0.05 * rng.standard_normal((T, 300)) + 7).astype(np.float32)
+    Y = ((U * sig) @ np.linalg.qr(rng.standard_normal((200, 2 * k)))[0].T + 0.05 * rng.standard_normal((T, 200)) - 3).astype(np.float32)
+    X[:, 5] = np.nan
+    dx, dy = ("time", "x"), ("time", "y")
+    kw = dict(n_modes=k, random_state=3, standardize=True)
+    okw = dict(kw)
+    if mode == "implicit":
+        cls, kw2, okw2 = xb.cross.MCA, dict(use_pca=False), dict(use_pca=False)
+    elif mode == "pca":
+        cls, kw2, okw2 = xb.cross.MCA, dict(n_pca_modes=6), dict(use_pca=True, n_pca_modes=6, pca_random_state=1)
+    else:
+        cls, kw2, okw2 = xb.cross.CCA, dict(n_pca_modes=6), dict(use_pca=True, n_pca_modes=6, pca_random_state=1, alpha=0.0)
+    o = omca.mca_fit(X, Y, dx, dy, "time", **okw, **okw2)
+    m = cls(ops=TorchCpuOps(), **kw, **kw2).fit(xb.DataArray(X, dx), xb.DataArray(Y, dy), dim="time")
+    # training data reproduce the scores
+    s1, s2 = m.scores()
+    t1, t2 = m.transform(X=xb.DataArray(X, dx), Y=xb.DataArray(Y, dy))
+    np.testing.assert_allclose(t1.values, s1.values, atol=2e-3 * np.abs(s1.values).max())
+    np.testing.assert_allclose(t2.values, s2.values, atol=2e-3 * np.abs(s2.values).max())
+    # unseen samples
+    Xn = X[:40] + (0.3 * rng.standard_normal((40, 300))).astype(np.float32)
+    An = opp.transform_new(Xn, dx, o["fitted1"], True, True, False)
+    ref = o["helpers"]["transform1"](An)
+    got = m.transform(X=xb.DataArray(Xn, dx)).values
+    np.testing.assert_allclose(got, ref, atol=2e-3 * np.abs(ref).max())
+    refp = o["helpers"]["predict"](An)
+    gotp = m.predict(xb.DataArray(Xn, dx)).values
+    np.testing.assert_allclose(gotp, refp, atol=2e-3 * np.abs(refp).max())
+    # reconstruction from the scores: scores . components^H, un-scaled (NaN at the dropped feature)
+    rec = m.inverse_transform(X=s1).values
+    ref_rec = opp.inverse_scale(o["scores1"] @ o["components1_2d"].T, o["fitted1"], True, True, False)
+    assert np.isnan(rec[:, 5]).all()
+    keep = ~np.isnan(X[0])
+    np.testing.assert_allclose(rec[:, keep], ref_rec[:, keep] if ref_rec.shape[1] == X.shape[1] else ref_rec,
+                               atol=2e-3 * np.abs(ref_rec[np.isfinite(ref_rec)]).max())
+    with pytest.raises(ValueError, match="Either X or Y"):
+        m.transform()
+
+
 def test_mca_rotator_host_logic():
     """cross/cpcca_rotator.py:122-305 (identity whitening, no PCA) against its numpy restatement."""
     import xeofs_b200 as xb

@@ -377,6 +377,82 @@ class MCA:
             return (A * B).sum(0) / (A.shape[0] - 1)
         return A.t() @ B / (A.shape[0] - 1)
 
+    # ------------------------------------------------------------------ transform / predict / inverse_transform
+    def _projection_patterns(self, i):
+        """Space-side (kp x S) patterns P with scores = A P: the singular vectors themselves for the implicit MCA;
+        with the PCA stage V diag(t) Q (PCA projection, whitening, singular vectors — pca.py:121-131,
+        whitener.py:135-145, cpcca.py:233-252) = A^T U diag(t / s) Q, built with one streaming pass and cached."""
+        ctx = getattr(self, "_pca_ctx", None)
+        if ctx is None:
+            return (self._Q1t, self._Q2t)[i]
+        cache = self.__dict__.setdefault("_proj_cache", {})
+        if i not in cache:
+            ff = (self._f1, self._f2)[i]
+            U, t, Q = ctx["U1" if i == 0 else "U2"], ctx["t1" if i == 0 else "t2"], ctx["Q1" if i == 0 else "Q2"]
+            sv = torch.linalg.norm(ctx["X1u" if i == 0 else "X2u"], dim=0)   # columns of U S have norm s
+            W = self.ops.zeros((ff.T, lpad(self.k)))
+            W[:, : self.k] = ((U * torch.where(sv > 0, t / sv, torch.zeros_like(sv))) @ Q).to(torch.float32)
+            cache[i] = self.ops.project_S(ff.field, W, self.k, algo=self.ops.accurate_algo)
+        return cache[i]
+
+    def _transform_one(self, i, data, normalized):
+        pp = (self.preprocessor1, self.preprocessor2)[i]
+        new, sample_shape, sample_coords, valid_sample = pp.transform(data)
+        Z = self.ops.project_T(new, self._projection_patterns(i), self.k, algo=self.ops.accurate_algo)
+        self.comm.sum_(Z)
+        if normalized:
+            Z[:, : self.k] /= self.data["norm1" if i == 0 else "norm2"].to(torch.float32)[None, :]
+        return Z, (pp, sample_shape, sample_coords, valid_sample)
+
+    def transform(self, X=None, Y=None, normalized=False):
+        """cross/base_model_cross_set.py:323-392 + cpcca.py:227-252: scores of new data of either field."""
+        if X is None and Y is None:
+            raise ValueError("Either X or Y must be given.")
+        out = []
+        for i, d in enumerate((X, Y)):
+            if d is None:
+                continue
+            L.validate_input_type(d)
+            Z, (pp, shp, crd, vs) = self._transform_one(i, d, normalized)
+            out.append(pp.scores_to_nd(Z, self.k, "scores1" if i == 0 else "scores2", shp, crd, vs))
+        return out[0] if len(out) == 1 else tuple(out)
+
+    def predict(self, X):
+        """cpcca.py:281-306: pseudo scores of Y from new X: (X P_x) G with G = R_x^H R_y / |R_x|^2."""
+        L.validate_input_type(X)
+        Z, (pp, shp, crd, vs) = self._transform_one(0, X, False)
+        r1, r2 = self._valid_scores()
+        G = (r1.t() @ r2) / (torch.linalg.norm(r1, dim=0) ** 2)[:, None]
+        Zp = self.ops.zeros(tuple(Z.shape))
+        Zp[:, : self.k] = (Z[:, : self.k].double() @ G).to(torch.float32)
+        return pp.scores_to_nd(Zp, self.k, "pseudo_scores_Y", shp, crd, vs)
+
+    def inverse_transform(self, X=None, Y=None):
+        """cpcca.py:254-279 + the back-transforms of base_model_cross_set.py:394-463: scores . components^H (the
+        un-whitened physical-space components), then un-scaled; ``X`` / ``Y`` are score arrays with a 'mode'
+        dimension whose coordinate selects the modes."""
+        if X is None and Y is None:
+            raise ValueError("Either X or Y must be given.")
+        out = []
+        for i, scores in enumerate((X, Y)):
+            if scores is None:
+                continue
+            data, dims, coords, _ = L.unpack(scores)
+            sc = torch.as_tensor(np.asarray(data) if not isinstance(data, torch.Tensor) else data)
+            sc = sc.to(self.ops.device, torch.float32)
+            if "mode" not in dims:
+                sc, dims = sc.unsqueeze(-1), tuple(dims) + ("mode",)
+            sc = sc.movedim(dims.index("mode"), -1)
+            sample_dims = tuple(d for d in dims if d != "mode")
+            sample_shape = tuple(sc.shape[:-1])
+            modes = np.asarray(coords.get("mode", np.arange(1, sc.shape[-1] + 1))).astype(int) - 1
+            pp = (self.preprocessor1, self.preprocessor2)[i]
+            if sample_dims != pp.sample_dims:
+                raise ValueError(f"scores have sample dimensions {sample_dims}, the model was fitted with {pp.sample_dims}")
+            rec = self.ops.reconstruct(pp.fitted.field, sc.reshape(-1, sc.shape[-1]), (self._Q1t, self._Q2t)[i], modes)
+            out.append(pp.data_to_nd(rec, sample_shape, {d: coords[d] for d in sample_dims if d in coords}))
+        return out[0] if len(out) == 1 else tuple(out)
+
     # ------------------------------------------------------------------ homogeneous / heterogeneous patterns
     def _data_score_correlation(self, i, R):
         """Pearson correlation (utils/optional/statistics.py:51-76) between every feature of field i — in physical
