@@ -330,6 +330,11 @@ def test_rotator_host_logic():
         V = r.components().values.reshape(-1, 5)
         dots = (V * ro["components_2d"]).sum(axis=0)
         assert (dots > 1 - 1e-5).all(), dots
+        if power == 1:  # an orthogonal rotation reconstructs what the un-rotated modes reconstruct
+            rec_r = r.inverse_transform(r.scores()).values
+            sc = m.scores()
+            rec_m = m.inverse_transform(xb.DataArray(sc.values[:, :5], ("time", "mode"), {"mode": np.arange(1, 6)})).values
+            np.testing.assert_allclose(rec_r, rec_m, rtol=1e-4, atol=1e-4 * np.abs(rec_m).max())
         if power == 1:  # rotation conserves the variance (tests/models/single/test_eof_rotator.py:98-137)
             np.testing.assert_allclose(r.explained_variance().values.sum(), m.explained_variance().values[:5].sum(),
                                        rtol=1e-5)

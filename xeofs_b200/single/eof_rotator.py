@@ -185,6 +185,15 @@ class EOFRotator:
     def phi_matrix(self):
         return self.data["phi_matrix"].cpu().numpy()
 
+    def inverse_transform(self, scores, normalized=False):
+        """Inherited from EOF in the reference (single/eof.py:134-156 with the rotated components): scores .
+        components^H, un-scaled.  For an orthogonal rotation the m rotated modes span what the first m EOFs span."""
+        from .eof import EOF
+        return EOF.inverse_transform(self, scores, normalized)
+
+    def get_params(self):
+        return dict(self._params)
+
     def transform(self, data, normalized=False):
         """eof_rotator.py:227-263: project on the un-rotated components, rotate, reorder, scale, sign."""
         model, p = self.model, self._params
