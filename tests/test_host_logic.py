@@ -311,6 +311,11 @@ def test_mca_rotator_host_logic():
         for sc, osc in ((s1, ro["scores1"]), (s2, ro["scores2"])):
             scale = np.abs(osc).max(axis=0)
             np.testing.assert_allclose(sc.values / scale, osc / scale, atol=1e-3)
+        # transform of the training data reproduces the rotated scores (cpcca_rotator.py:322-427)
+        dax, day = xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y"))
+        t1, t2 = r.transform(X=dax, Y=day)
+        np.testing.assert_allclose(t1.values, s1.values, atol=2e-3 * np.abs(s1.values).max())
+        np.testing.assert_allclose(t2.values, s2.values, atol=2e-3 * np.abs(s2.values).max())
     with pytest.raises(ValueError, match="exceeds"):
         xb.cross.MCARotator(n_modes=k + 1).fit(m)
 

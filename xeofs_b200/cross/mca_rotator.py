@@ -104,6 +104,30 @@ class MCARotator:
         return (self.preprocessor1.scores_to_nd(s1, self.k, "scores1"),
                 self.preprocessor2.scores_to_nd(s2, self.k, "scores2"))
 
+    def transform(self, X=None, Y=None, normalized=False):
+        """cpcca_rotator.py:322-427: project on the UN-rotated singular vectors, divide by sqrt(s), rotate (R^-T),
+        reorder, sign, scale with the rotated norms."""
+        if X is None and Y is None:
+            raise ValueError("No data provided. Please provide X and/or Y.")
+        model, p, m = self.model, self._params, self.k
+        Rt = self.data["rotation_matrix"]
+        RinvT = Rt if p["power"] == 1 else torch.linalg.inv(Rt).t()
+        idx = self.data["idx_modes_sorted"]
+        scaling = torch.sqrt(model._s[:m])
+        Mat = (RinvT[:, idx] / scaling[:, None]).contiguous()
+        out = []
+        for i, d in enumerate((X, Y)):
+            if d is None:
+                continue
+            L.validate_input_type(d)
+            Z, (pp, shp, crd, vs) = model._transform_one(i, d, False)
+            scale = self.data["modes_sign"].double()
+            if not normalized:
+                scale = scale * self.data["norm1" if i == 0 else "norm2"]
+            Zr = self.ops.apply(Z, int(Z.shape[0]), m, 0, Mat, m, colscale=scale)
+            out.append(pp.scores_to_nd(Zr, m, "scores1" if i == 0 else "scores2", shp, crd, vs))
+        return out[0] if len(out) == 1 else out
+
     def _mode_array(self, t, name):
         return L.wrap(t.cpu().numpy(), ("mode",), {"mode": np.arange(1, self.k + 1)}, name,
                       self.preprocessor1.as_xarray)
