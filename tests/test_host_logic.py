@@ -154,6 +154,9 @@ def test_mca_host_logic():
     np.testing.assert_allclose(m.cross_correlation_coefficients().values, o["cross_correlation_coefficients"], rtol=1e-4)
     np.testing.assert_allclose(m.correlation_coefficients_X(), o["correlation_coefficients_X"], atol=1e-4)
     _check_patterns(m, o, valid1=~np.isnan(X[0]))
+    with pytest.warns(UserWarning, match="sensitive to the number of modes"):
+        cf = m.covariance_fraction_CD95().values
+    np.testing.assert_allclose(cf, o["singular_values"] / o["singular_values"].sum(), rtol=1e-5)
     c1, c2 = m.components()
     v1 = c1.values[~np.isnan(c1.values).any(axis=1)]
     dots = np.abs((v1 * o["components1_2d"]).sum(axis=0))

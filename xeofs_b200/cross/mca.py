@@ -361,6 +361,17 @@ class MCA:
         scf = torch.clamp(torch.stack(out), min=0.0)
         return self._mode_array(scf, "squared_covariance_fraction")
 
+    def covariance_fraction_CD95(self):
+        """cross/mca.py:125-215 (Cheng & Dunkerton 1995): sigma_i / sum_i sigma_i over the retained modes, with the
+        reference's warning when the estimate still moves with the number of modes."""
+        import warnings
+        cov = torch.sqrt(self.data["squared_covariance"])
+        cf = cov[0] / torch.cumsum(cov, 0)
+        if cf.numel() > 1 and float(cf[-2] - cf[-1]) > 0.001:
+            warnings.warn("The curent estimate of CF is sensitive to the number of modes retained. Please increase "
+                          "`n_modes` for a better estimate.")
+        return self._mode_array(cov / cov.sum(), "covariance_fraction")
+
     # ------------------------------------------------------------------ score statistics (cpcca.py:331-416)
     def _valid_scores(self):
         vs = self._f1.valid_sample if self._f1.n_samples < self._f1.T else None
