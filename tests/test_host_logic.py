@@ -401,6 +401,30 @@ def test_eof_more_modes_than_one_kernel_block():
     np.testing.assert_allclose(V.T @ V, np.eye(k), atol=1e-4)
 
 
+def test_one_normalisation_per_power_iteration_matches_sklearn_schedule():
+    """From the second power iteration on only the short side is normalised (_engine.randomized_svd); on a steep
+    spectrum (sigma_j = 0.3^j, ratio 2e-5 over the first ten modes) the result equals the reference's schedule —
+    a normalisation after every half-step — and the oracle, down to the modes the fp32 input resolves."""
+    import xeofs_b200 as xb
+    from xeofs_b200 import _engine as E
+    rng = np.random.default_rng(0)
+    T, S, r, k = 400, 3000, 30, 12
+    U = np.linalg.qr(rng.standard_normal((T, r)))[0]
+    V = np.linalg.qr(rng.standard_normal((S, r)))[0]
+    X = (280 + (U * (1e4 * 0.3 ** np.arange(r))) @ V.T + 1e-9 * rng.standard_normal((T, S))).astype(np.float32)
+    o = oeof.eof_fit(X, ("time", "x"), "time", n_modes=k, random_state=3, solver_kwargs={"n_iter": 4})
+    res = {}
+    try:
+        for both in (False, True):
+            E.NORMALIZE_BOTH_HALF_STEPS = both
+            m = xb.single.EOF(n_modes=k, random_state=3, solver_kwargs={"n_iter": 4}, ops=TorchCpuOps())
+            res[both] = m.fit(xb.DataArray(X, ("time", "x")), dim="time").singular_values().values
+    finally:
+        E.NORMALIZE_BOTH_HALF_STEPS = False
+    np.testing.assert_allclose(res[False][:10], res[True][:10], rtol=1e-6)
+    np.testing.assert_allclose(res[False][:10], o["singular_values"][:10], rtol=1e-4)
+
+
 def test_eof_list_input_host_logic():
     """A list of arrays (two variables on different grids): each scaled on its own, concatenated along the feature
     axis (preprocessing/preprocessor.py:208-228, concatenator.py:58-81); components come back one array per input."""

@@ -19,6 +19,7 @@ from ._lib import lpad
 
 MAX_L = 128         # widest k-column block the kernels take in one go (wider sketches run in blocks of it)
 MAX_L_TOTAL = 1024  # widest sketch accepted at all
+NORMALIZE_BOTH_HALF_STEPS = False  # True: sklearn's schedule (a normalisation after every half-step of a power iteration)
 
 
 # ---------------------------------------------------------------------------------------------- comm
@@ -339,7 +340,7 @@ def randomized_svd(ops, op, k, n_oversamples=10, n_iter="auto", random_state=Non
         # sklearn normalises after both half-steps.  From the second iteration on the columns of Q are graded (column j
         # is dominated by the j-th singular direction), M^T (M Q) keeps them graded, and one normalisation per full
         # iteration (on M's column side) holds the same span to fp32 accuracy: the row-side one is left out.
-        if it == 0:
+        if it == 0 or NORMALIZE_BOTH_HALF_STEPS:
             Y = orthonormalize(ops, Y, op.r, l, comm, 1, infos)
         Q = orthonormalize(ops, op.mul_t(Y, l), op.c, l, comm, 1, infos)
     # The last two passes decide the singular values and run at fp32 accuracy.  For the first of them the small
