@@ -233,6 +233,8 @@ def test_cpcca_family_host_logic(cls, alpha):
     np.testing.assert_allclose(m.cross_correlation_coefficients().values, o["cross_correlation_coefficients"], rtol=1e-4)
     np.testing.assert_allclose(m.correlation_coefficients_X(), o["correlation_coefficients_X"], atol=1e-4)
     _check_patterns(m, o)
+    with pytest.raises(NotImplementedError, match="identity whitening"):
+        xb.cross.MCARotator(n_modes=2).fit(m)
     with pytest.raises(NotImplementedError, match="use_pca"):
         xb.cross.CCA(n_modes=k, use_pca=False, ops=TorchCpuOps()).fit(
             xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")

@@ -33,6 +33,9 @@ class MCARotator:
         m = int(p["n_modes"])
         if m > model.k:
             raise ValueError(f"n_modes={m} exceeds the {model.k} modes of the MCA model")
+        if getattr(model, "_alpha", (1.0, 1.0)) != (1.0, 1.0):
+            raise NotImplementedError("MCARotator rotates MCA solutions (identity whitening); the rotators of whitened "
+                                      "models (CCA / RDA / CPCCA, cross/cpcca_rotator.py) are not built")
         f1, f2 = model._f1, model._f2
         S1, S2, T = f1.S, f2.S, f1.T
         s = model._s[:m]
