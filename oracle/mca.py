@@ -158,7 +158,7 @@ def mca_fit(
         "predict": lambda A: _to_model_space(A, V1 if use_pca else None, T1) @ Q1_w @ G_pred,
     }
     return {
-        "helpers": helpers,
+        "helpers": helpers, "components_model": (Q1_w, Q2_w),
         "homogeneous_patterns": (hom1, hom2), "pvalues_homogeneous": (phom1, phom2),
         "heterogeneous_patterns": (het1, het2),
         "squared_covariance_fraction": np.array(scf),

@@ -103,7 +103,7 @@ def eof_rotator_fit(components_2d, explained_variance, scores, norms, n_samples,
 
 
 def mca_rotator_fit(components1_2d, components2_2d, singular_values, scores1, scores2,
-                    n_modes=2, power=1, max_iter=None, rtol=1e-8):
+                    n_modes=2, power=1, max_iter=None, rtol=1e-8, model_components=None):
     """MCARotator / CPCCARotator with identity whitening and no PCA stage (cross/cpcca_rotator.py:122-305;
     cross/mca_rotator.py:5): varimax/promax of the concatenated, sqrt(s)-weighted singular vectors.
     components*_2d (S', k) valid features only, scores* (n, k) = X Q."""
@@ -115,8 +115,14 @@ def mca_rotator_fit(components1_2d, components2_2d, singular_values, scores1, sc
     loadings = np.concatenate([components1_2d[:, :m], components2_2d[:, :m]], axis=0) * scaling   # :171
     Lrot, R, phi = promax(loadings, power=power, max_iter=max_iter, rtol=rtol)   # :175-180
     Q1r, Q2r = Lrot[:S1], Lrot[S1:]                                          # :193-198
-    n1 = np.linalg.norm(Q1r, axis=0)                                         # :211-232
-    n2 = np.linalg.norm(Q2r, axis=0)
+    if model_components is None:
+        n1 = np.linalg.norm(Q1r, axis=0)                                     # :211-232
+        n2 = np.linalg.norm(Q2r, axis=0)
+    else:
+        # whitened / PCA models: the rotated vectors go back into the whitened PCA space first (:203-208), where they
+        # are (Q_model sqrt(s)) R
+        n1 = np.linalg.norm((model_components[0][:, :m] * scaling) @ R, axis=0)
+        n2 = np.linalg.norm((model_components[1][:, :m] * scaling) @ R, axis=0)
     Q1r, Q2r = Q1r / n1, Q2r / n2                                            # :235-236
     sqcov = (n1 * n2) ** 2                                                   # :239-240
     idx = np.argsort(sqcov)[::-1]                                            # :243

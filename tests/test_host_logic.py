@@ -233,8 +233,17 @@ def test_cpcca_family_host_logic(cls, alpha):
     np.testing.assert_allclose(m.cross_correlation_coefficients().values, o["cross_correlation_coefficients"], rtol=1e-4)
     np.testing.assert_allclose(m.correlation_coefficients_X(), o["correlation_coefficients_X"], atol=1e-4)
     _check_patterns(m, o)
-    with pytest.raises(NotImplementedError, match="identity whitening"):
-        xb.cross.MCARotator(n_modes=2).fit(m)
+    # rotation of the whitened model (cross/cpcca_rotator.py:122-305): norms in the whitened PCA space
+    for power in (1, 2):
+        r = xb.cross.CPCCARotator(n_modes=2, power=power).fit(m)
+        ro = orot.mca_rotator_fit(o["components1_2d"], o["components2_2d"], o["singular_values"], o["scores1"],
+                                  o["scores2"], n_modes=2, power=power, model_components=o["components_model"])
+        np.testing.assert_allclose(r.squared_covariance().values, ro["squared_covariance"], rtol=1e-4)
+        rc1, rc2 = r.components()
+        for c, oc in ((rc1, ro["components1_2d"]), (rc2, ro["components2_2d"])):
+            np.testing.assert_allclose(c.values, oc, atol=2e-4 * np.abs(oc).max())
+        rs1, _ = r.scores()
+        np.testing.assert_allclose(rs1.values, ro["scores1"], atol=2e-3 * np.abs(ro["scores1"]).max())
     with pytest.raises(NotImplementedError, match="use_pca"):
         xb.cross.CCA(n_modes=k, use_pca=False, ops=TorchCpuOps()).fit(
             xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")

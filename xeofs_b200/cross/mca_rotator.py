@@ -1,6 +1,6 @@
-"""Varimax / Promax rotation of an MCA solution on B200 — drop-in for ``xeofs.cross.MCARotator``
-(cross/mca_rotator.py:5 -> cross/cpcca_rotator.py:57-469) for MCA models (identity whitening; with or without
-the PCA stage — the rotation works on the physical-space singular vectors either way).
+"""Varimax / Promax rotation of an MCA / CCA / RDA / CPCCA solution on B200 — drop-in for
+``xeofs.cross.CPCCARotator`` and ``xeofs.cross.MCARotator`` (cross/cpcca_rotator.py:57-469, cross/mca_rotator.py:5),
+with or without the PCA stage — the rotation works on the un-whitened physical-space singular vectors either way.
 
 The singular vectors of both fields, weighted with sqrt(singular value), are rotated as ONE (S1 + S2) x m loadings
 matrix (cpcca_rotator.py:154-180): the same one-pass-per-iteration varimax sweep as ``EOFRotator`` runs on the
@@ -16,7 +16,7 @@ from .._lib import lpad
 from ..single.eof_rotator import EOFRotator
 
 
-class MCARotator:
+class CPCCARotator:
     def __init__(self, n_modes=10, power=1, max_iter=None, rtol=1e-8, compute=True):
         if max_iter is None:
             max_iter = 1000 if compute else 100  # cpcca_rotator.py:86-87
@@ -33,9 +33,6 @@ class MCARotator:
         m = int(p["n_modes"])
         if m > model.k:
             raise ValueError(f"n_modes={m} exceeds the {model.k} modes of the MCA model")
-        if getattr(model, "_alpha", (1.0, 1.0)) != (1.0, 1.0):
-            raise NotImplementedError("MCARotator rotates MCA solutions (identity whitening); the rotators of whitened "
-                                      "models (CCA / RDA / CPCCA, cross/cpcca_rotator.py) are not built")
         f1, f2 = model._f1, model._f2
         S1, S2, T = f1.S, f2.S, f1.T
         s = model._s[:m]
@@ -54,9 +51,15 @@ class MCARotator:
         Rt, phi = rot._rotate(ops, comm, L0, S1p + S2, f1.n_features + f2.n_features, m)   # :175-180
         self.n_iter_, self.n_iter_tc_ = rot.n_iter_, getattr(rot, "n_iter_tc_", 0)
         # norms of the rotated, loaded vectors of each field: diag(Rt^T (L^T L) Rt)   (:211-232)
-        G1, G2 = ops.gram(L1, S1, m, 1), ops.gram(L2, S2, m, 1)
-        comm.sum_(G1)
-        comm.sum_(G2)
+        if getattr(model, "_alpha", (1.0, 1.0)) != (1.0, 1.0):
+            # whitened models (CCA / RDA / CPCCA): the reference takes the norms after transforming the rotated vectors
+            # back into the whitened PCA space (cpcca_rotator.py:203-232), where they are Q sqrt(s) R with orthonormal
+            # Q: the Gram matrix of the loadings there is diag(s) for both fields
+            G1 = G2 = torch.diag(s.double())
+        else:
+            G1, G2 = ops.gram(L1, S1, m, 1), ops.gram(L2, S2, m, 1)
+            comm.sum_(G1)
+            comm.sum_(G2)
         n1 = torch.sqrt(torch.diagonal(Rt.t() @ G1 @ Rt)).clone()
         n2 = torch.sqrt(torch.diagonal(Rt.t() @ G2 @ Rt)).clone()
         sqcov = (n1 * n2) ** 2                                                     # :239-240
@@ -155,3 +158,7 @@ class MCARotator:
 
     def get_params(self):
         return dict(self._params)
+
+
+class MCARotator(CPCCARotator):
+    """cross/mca_rotator.py:5: the rotator of MCA models (same algorithm)."""
