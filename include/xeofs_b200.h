@@ -135,7 +135,8 @@ int xeofs_b200_apply(const float* In, int64_t n, int64_t l, int64_t ld_in, int s
 /* ---- D2/D3: the small SVD and the sign rule ------------------------------------------------------
  * sym_eig: cyclic Jacobi on the l x l Gram (replaces scipy.linalg.svd(B) inside randomized_svd via
  *          B B^T = U diag(s^2) U^T).  evals[l] descending, evecs l x l row-major with eigenvector i in
- *          COLUMN i.  work: l*l doubles.
+ *          COLUMN i.  l <= 128.  work: le*le doubles with le = l rounded up to even (the eigenvector accumulator when
+ *          it does not fit shared memory next to the matrix, l > 118; (l+1)*(l+1) doubles always suffice).
  * row_minmax: per row of a (k x n) matrix the max and the min (utils/xarray_utils.py:273-301 needs both).
  * finish_components: Vt[m,s] = valid[s] ? sign[m] * Vt[m,s] : NaN   (decomposer.py:219-222 and
  *          sanitizer.py:128-153's reindex).                                                          */
@@ -182,6 +183,22 @@ int xeofs_b200_reconstruct(const float* scores, int64_t T, int64_t lds, const fl
 int xeofs_b200_scaled_rows(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
                            const float* dscale, const float* ccorr, const uint8_t* row_valid, int64_t t0,
                            int64_t nrows, int64_t rows_out, float* out, int64_t ldo, void* stream);
+
+/* ---- D2 beyond one 128-column block, and the small dense matrices of the cross models' PCA stage ----------------
+ * (what the reference gets from LAPACK / BLAS through scipy.linalg.lu / qr / svd inside randomized_svd, call site
+ * linalg/decomposer.py:141-146, and numpy in preprocessing/pca.py:94-131, whitener.py:111-133.)
+ * dgemm:         C (m x n) = alpha op(A) op(B) + beta C, all fp64 row-major, op = transpose when trans_* != 0.
+ * gram_wide:     G (l x l fp64 row-major) = M^T M for a k-column matrix with l up to 4096 columns (side as in gram),
+ *                fp64 accumulation, one pair of 128-column blocks per launch.
+ * sym_eig_wide:  eigen-decomposition of a symmetric positive semi-definite n x n matrix (n <= 4096) by multi-CTA
+ *                one-sided Jacobi; evals descending, eigenvector i in COLUMN i of evecs (n x n row-major);
+ *                info[0] = sweeps run (at most max_sweeps; <= 0: 16).  Workspace size from the query function.     */
+int xeofs_b200_dgemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                     int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, void* stream);
+int xeofs_b200_gram_wide(const float* M, int64_t n, int64_t l, int64_t ld, int side, double* G, void* stream);
+int64_t xeofs_b200_sym_eig_wide_workspace_bytes(int64_t n);
+int xeofs_b200_sym_eig_wide(const double* G, int64_t n, double* evals, double* evecs, void* workspace,
+                            int64_t workspace_bytes, int32_t* info, int max_sweeps, void* stream);
 
 #ifdef __cplusplus
 }

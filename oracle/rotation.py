@@ -132,7 +132,16 @@ def mca_rotator_fit(components1_2d, components2_2d, singular_values, scores1, sc
     sc1 = (scores1[:, :m] / scaling) @ RinvT * n1                            # :254-268
     sc2 = (scores2[:, :m] / scaling) @ RinvT * n2
     sgn = sign_multiplier(Lrot.T)                                            # :271 (rule on the combined loadings)
+
+    def _transform(A, comps, nrm):
+        """cpcca_rotator.py:322-427: preprocessed data A projected on the UN-rotated components — un-whitened and back
+        in physical space (:359-366), which is what ``components*_2d`` holds — / sqrt(s), rotated, reordered, signed,
+        scaled with the rotated norms."""
+        return (((A @ comps[:, :m]) / scaling) @ RinvT)[:, idx] * sgn[idx] * nrm[idx]
+
     return {
+        "transform1": lambda A: _transform(A, components1_2d, n1),
+        "transform2": lambda A: _transform(A, components2_2d, n2),
         "components1_2d": (Q1r * sgn)[:, idx], "components2_2d": (Q2r * sgn)[:, idx],
         "scores1": (sc1 * sgn)[:, idx], "scores2": (sc2 * sgn)[:, idx],
         "squared_covariance": sqcov[idx], "norm1": n1[idx], "norm2": n2[idx],

@@ -153,6 +153,13 @@ class TorchCpuOps:
         ev, V = torch.linalg.eigh(0.5 * (G + G.t()))
         return ev.flip(0).contiguous(), V.flip(1).contiguous()
 
+    def dgemm(self, A, B, trans_a=False, trans_b=False, alpha=1.0, out=None, beta=0.0):
+        C = alpha * ((A.t() if trans_a else A).double() @ (B.t() if trans_b else B).double())
+        if out is not None:
+            out.copy_(C + beta * out if beta != 0.0 else C)
+            return out
+        return C
+
     def row_minmax(self, Vt, k, n):
         return Vt[:k, :n].max(dim=1).values.clone(), Vt[:k, :n].min(dim=1).values.clone()
 

@@ -1,0 +1,19 @@
+#!/bin/bash
+# One gpurun call = several measurements; every step logs under gpurun_out/ and no step aborts the others.
+# usage: tools/gpu_session.sh <tag> <step> [<step> ...]     steps: tests bench bench_c3 bench_c5 parity profile
+tag=$1; shift
+mkdir -p gpurun_out
+for step in "$@"; do
+  case $step in
+    tests)    timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_pytest.log ;;
+    bench)    timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_bench.log ;;
+    benchq)   timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-strong-c4 --no-e2e > gpurun_out/${tag}_benchq.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_benchq.log ;;
+    bench_c3) timeout 600 python bench.py --workload c3 --steps 5 --warmup 3 > gpurun_out/${tag}_bench_c3.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_bench_c3.log ;;
+    bench_c5) timeout 600 python bench.py --workload c5 --steps 4 --warmup 3 > gpurun_out/${tag}_bench_c5.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_bench_c5.log ;;
+    parity)   timeout 1800 python tools/parity_full.py c2 c3 c5 c4n1 > gpurun_out/${tag}_parity.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_parity.log ;;
+    profile)  timeout 600 python tools/profile_fit.py c2 > gpurun_out/${tag}_profile.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_profile.log ;;
+    smoke)    timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_smoke.log ;;
+    *) echo "unknown step $step" ;;
+  esac
+done
+tail -n 3 gpurun_out/${tag}_*.log | cut -c1-600

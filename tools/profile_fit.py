@@ -15,7 +15,7 @@ import xeofs_b200 as xb  # noqa: E402
 def main():
     wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
     T, n_lat, n_lon, k, n_iter, kw = bench.WORKLOADS[wl]
-    X = bench.planted_field_device(T, n_lat * n_lon, 2 * k, 1, torch.device("cuda")).reshape(T, n_lat, n_lon)
+    X = bench.planted_field_device(T, n_lat, n_lon, 0, n_lat, 2 * k, 1, torch.device("cuda"))
     import numpy as np
     coords = {"lat": np.linspace(90, -90, n_lat), "lon": np.arange(n_lon) * (360.0 / n_lon)}
 

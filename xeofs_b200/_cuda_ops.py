@@ -210,11 +210,14 @@ class CudaOps:
     # ------------------------------------------------------------------ k-column linear algebra
     def gram(self, M, n, l, side, out=None, accumulate=False):
         G = out if out is not None else self.empty((l, l), torch.float64)
-        if l > BLOCK_L:  # beyond the k-column kernels' width: library fp64 products on the (rarely this wide) block
-            A = (M[:n, :l] if side == 0 else M[:l, :n].t()).double()
-            Gn = A.t() @ A
-            G.copy_(G + Gn if accumulate else Gn)
-            self.launches += 2
+        if l > BLOCK_L:  # beyond one block of the k-column kernels: one launch per pair of 128-column blocks
+            Gn = G if not accumulate else self.empty((l, l), torch.float64)
+            check(self.lib.xeofs_b200_gram_wide(ptr(M), n, l, int(M.stride(0)), side, ptr(Gn), self._stream()),
+                  "gram_wide")
+            if accumulate:
+                G += Gn
+            nb = (l + BLOCK_L - 1) // BLOCK_L
+            self.launches += 1 + nb * (nb + 1) // 2
             return G
         check(self.lib.xeofs_b200_gram(ptr(M), n, l, int(M.stride(0)), side, ptr(G), int(accumulate), self._stream()),
               "gram")
@@ -226,12 +229,16 @@ class CudaOps:
         Rinv = self.empty((l, l), torch.float64)
         info = info if info is not None else self.empty(2, torch.int32)
         if l > BLOCK_L:
-            Lc, err = torch.linalg.cholesky_ex(G)
-            Rinv.copy_(torch.linalg.solve_triangular(Lc.t(), torch.eye(l, dtype=torch.float64, device=G.device),
-                                                     upper=True))
-            info[0] = 0
-            info[1] = ((err != 0) | ~torch.isfinite(G).all()).to(torch.int32)
-            self.launches += 2
+            # wider than the one-block Cholesky kernel: the orthonormalising factor comes from the eigen-decomposition
+            # G = V diag(ev) V^T instead, M V diag(ev^-1/2) — any orthonormal basis of the same span serves the range
+            # finder (sklearn's own normalizers, LU and QR, produce different ones).  Directions below the fp32 noise
+            # floor of G are dropped like the Cholesky kernel drops them.
+            ev, V = self.sym_eig(G)
+            ok = ev > 5.7e-14 * ev[0].clamp(min=0.0)
+            scale = torch.where(ok, 1.0 / torch.sqrt(torch.where(ok, ev, torch.ones_like(ev))), torch.zeros_like(ev))
+            Rinv.copy_(V * scale[None, :])
+            info[0] = (~ok).sum().to(torch.int32)
+            info[1] = (~torch.isfinite(ev).all()).to(torch.int32)
             return Rinv, info
         check(self.lib.xeofs_b200_chol_inv(ptr(G), l, ptr(Rinv), ptr(info), self._stream()), "chol_inv")
         self.launches += 1
@@ -265,17 +272,18 @@ class CudaOps:
         if out is None:
             out = self.space_side(kp, n) if side == 1 else self.zeros((n, kp))
         if l > BLOCK_L or k > BLOCK_L:
-            A = (In[:n, :l] if side == 0 else In[:l, :n].t()).double()
-            B = A @ Mat[:l, :k].double()
+            # (space-side blocks this wide only get here without the tensor-core path: unaligned views)
+            A = (In[:n, :l] if side == 0 else In[:l, :n].t()).double().contiguous()
+            Ms = Mat[:l, :k].double()
             if colscale is not None:
-                B = B * colscale.double()[None, :k]
+                Ms = Ms * colscale.double()[None, :k]
+            B = self.dgemm(A, Ms.contiguous())
             if side == 0:
                 out[:, :k] = B.float()
                 out[:, k:] = 0
             else:
                 out[:k] = B.t().float()
                 out[k:] = 0
-            self.launches += 2
             return out
         check(self.lib.xeofs_b200_apply(ptr(In), n, l, int(In.stride(0)), side, ptr(Mat), int(Mat.stride(0)), k,
                                         ptr(colscale), ptr(out), int(out.stride(0)), self._stream()), "apply")
@@ -285,9 +293,7 @@ class CudaOps:
     def sym_eig(self, G):
         l = int(G.shape[0])
         if l > BLOCK_L:
-            ev, V = torch.linalg.eigh(0.5 * (G + G.t()))
-            self.launches += 1
-            return ev.flip(0).contiguous(), V.flip(1).contiguous()
+            return self.sym_eig_wide(G)
         evals = self.empty(l, torch.float64)
         evecs = self.empty((l, l), torch.float64)
         work = self.empty((l + 1) * (l + 1), torch.float64)
@@ -296,6 +302,37 @@ class CudaOps:
               "sym_eig")
         self.launches += 1
         return evals, evecs
+
+    def sym_eig_wide(self, G, max_sweeps=16):
+        """Eigen-decomposition (descending) of a symmetric positive semi-definite matrix wider than one block:
+        multi-CTA one-sided Jacobi (csrc/dense64.cu)."""
+        n = int(G.shape[0])
+        G = G.contiguous()
+        evals = self.empty(n, torch.float64)
+        evecs = self.empty((n, n), torch.float64)
+        need = int(self.lib.xeofs_b200_sym_eig_wide_workspace_bytes(n))
+        work = torch.empty(need, dtype=torch.uint8, device=self.device)
+        info = self.empty(1, torch.int32)
+        check(self.lib.xeofs_b200_sym_eig_wide(ptr(G), n, ptr(evals), ptr(evecs), ptr(work), need, ptr(info),
+                                               int(max_sweeps), self._stream()), "sym_eig_wide")
+        self.launches += 3 + max_sweeps * (n | 1)
+        return evals, evecs
+
+    def dgemm(self, A, B, trans_a=False, trans_b=False, alpha=1.0, out=None, beta=0.0):
+        """op(A) op(B) in fp64 (row-major device matrices) on the library's own kernel: the small dense products of
+        the k-column algebra (PCA scores, cross-covariance of score matrices, m x m rotation algebra)."""
+        A = A if A.stride(-1) == 1 else A.contiguous()
+        B = B if B.stride(-1) == 1 else B.contiguous()
+        m, ka = (A.shape[1], A.shape[0]) if trans_a else (A.shape[0], A.shape[1])
+        kb, n = (B.shape[1], B.shape[0]) if trans_b else (B.shape[0], B.shape[1])
+        if ka != kb or A.dtype != torch.float64 or B.dtype != torch.float64:
+            raise ValueError(f"dgemm: shapes {tuple(A.shape)} x {tuple(B.shape)} (trans {trans_a}, {trans_b}) / dtypes")
+        C = out if out is not None else self.empty((int(m), int(n)), torch.float64)
+        check(self.lib.xeofs_b200_dgemm(int(trans_a), int(trans_b), int(m), int(n), int(ka), float(alpha), ptr(A),
+                                        int(A.stride(0)), ptr(B), int(B.stride(0)), float(beta), ptr(C),
+                                        int(C.stride(0)), self._stream()), "dgemm")
+        self.launches += 1
+        return C
 
     def row_minmax(self, Vt, k, n):
         vmax, vmin = self.empty(k), self.empty(k)

@@ -104,3 +104,16 @@ def sqrt_cos_lat_weights(feature_dims, feature_shape, coords):
     shape = [1] * len(feature_dims)
     shape[feature_dims.index(lat_dim)] = lat.size
     return np.broadcast_to(w.reshape(shape), feature_shape)
+
+
+def mode_indices(coords, n, k):
+    """Row indices (0-based) of the modes a score array names with its 'mode' coordinate (1-based, default 1..n).
+    The reference selects them with ``.sel(mode=...)`` (single/eof.py:150-152), which raises KeyError for a mode
+    the model does not hold; the device kernel indexes the components buffer with them, so they are checked here."""
+    modes = np.asarray(coords.get("mode", np.arange(1, n + 1))).astype(int) - 1
+    if modes.shape != (n,):
+        raise ValueError(f"the 'mode' coordinate has {modes.size} entries, the scores have {n} modes")
+    bad = modes[(modes < 0) | (modes >= k)]
+    if bad.size:
+        raise KeyError(f"modes {sorted(set((bad + 1).tolist()))} are not in the model (modes 1..{k})")
+    return modes

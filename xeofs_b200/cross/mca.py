@@ -20,34 +20,6 @@ def _pair(v):
     return tuple(v) if isinstance(v, (list, tuple)) else (v, v)
 
 
-def _leading_eigenpairs(G, m0, frac, trace):
-    """The m0 leading eigenpairs (descending) of the symmetric PSD matrix G (n x n fp64, device) — or, when ``frac``
-    is given, at least as many of them as it takes to reach that fraction of ``trace`` plus a margin.
-
-    The reference asks a randomized SVD for int(0.3 rank) modes and then keeps the few that carry 99.9 % of the
-    variance (linalg/_numpy/_svd.py:89-106, 214-241).  A dense eigen-decomposition of an 8760 x 8760 matrix costs
-    ~0.5 s; blocked subspace iteration on G (block 128, doubled until the kept modes sit well inside the block)
-    finds the same leading pairs in a few dozen n x n x l products.  Small problems take the dense route."""
-    n = int(G.shape[0])
-    l = 128
-    while frac is not None and 4 * l <= min(m0, n):
-        gen = torch.Generator(device=G.device).manual_seed(1234)
-        Q = torch.randn((n, l), dtype=torch.float64, device=G.device, generator=gen)
-        for _ in range(8):  # G = A A^T: every product is a full power iteration of A
-            Q = torch.linalg.qr(G @ Q).Q
-        GQ = G @ Q
-        ev, W = torch.linalg.eigh(Q.t() @ GQ)
-        ev, W = ev.flip(0), W.flip(1)
-        cum = torch.cumsum(ev / trace, 0)
-        reached = int((cum < frac).sum().item())  # modes needed - 1
-        if reached + 1 <= l - 32:  # the cut sits at least 32 modes inside the block: those pairs have converged
-            keep = reached + 1 + 16
-            return ev[:keep], (Q @ W[:, :keep])
-        l *= 2
-    evals, evecs = torch.linalg.eigh(G)
-    return evals.flip(0)[:m0], evecs.flip(1)[:, :m0]
-
-
 class MCA:
     """Same parameters and defaults as the reference (cross/mca.py:88-123).
 
@@ -85,6 +57,9 @@ class MCA:
     def fit(self, X, Y, dim, weights_X=None, weights_Y=None):
         for a in (X, Y):
             L.validate_input_type(a)
+        self.data, self._tsc_cache = {}, None
+        self.__dict__.pop("_pca_ctx", None)
+        self.__dict__.pop("_proj_cache", None)
         f1 = self.preprocessor1.fit_transform(X, dim, weights_X)
         f2 = self.preprocessor2.fit_transform(Y, dim, weights_Y)
         if bool(_pair(self._params["use_pca"])[0]):
@@ -118,20 +93,19 @@ class MCA:
             yield (t0, t1), gi[:, :w]
 
     def _pca_stage(self, ff, n_pca_modes, init_rank_reduction):
-        """Principal components of one preprocessed field through its sample Gram matrix: A = U S V^T with
-        A A^T = U S^2 U^T.  Returns (U (T x r) fp64, s (r) fp64) with the reference's truncation
-        (linalg/_numpy/_svd.py:89-106, 214-241) and sign convention (sign rule on the columns of V, :205-210).
-        The projection A V the reference hands on (pca.py:121-131) is U * s."""
+        """Principal components of one preprocessed field (preprocessing/pca.py:94-131 -> linalg/_numpy/_svd.py:108-243):
+        A = U S V^T by the same randomized range finder as EOF.fit, straight on the field through the streaming products
+        (either orientation: n_samples < n_features or not), with the reference's truncation (:214-241) and sign rule
+        (:205-210).  Returns (U (T x r) fp64, s (r) fp64, Vt (space-side, >= r rows, unit rows) fp32); the projection
+        A V the reference hands on (pca.py:121-131) is U * s.
+
+        The reference asks its (unseeded) randomized SVD for int(init_rank_reduction * rank) modes and then keeps the
+        few that carry ``n_pca_modes`` of the variance.  Here the sketch starts one kernel block wide (118 modes + 10)
+        and is widened only if the cut does not fall well inside it: the kept modes are the converged leading ones
+        either way."""
         import warnings
         ops, comm = self.ops, self.comm
-        T, n = ff.T, ff.n_samples
-        if n > ff.n_features:
-            raise NotImplementedError("the PCA stage is built for n_samples <= n_features (sample Gram route)")
-        G = torch.zeros((T, T), dtype=torch.float64, device=ops.device)
-        for (t0, t1), blk in self._gram_block_columns(ff, ops.accurate_algo):
-            b = blk.double()
-            G[t0:, t0:t1] = b
-            G[t0:t1, t0:] = b.t()
+        n = ff.n_samples
         rank = min(n, ff.n_features)
         by_variance = isinstance(n_pca_modes, float)
         if by_variance:
@@ -148,36 +122,72 @@ class MCA:
             m0 = int(n_pca_modes)
         else:
             raise ValueError("`n_modes` must be an integer, float or 'all'")
-        evals, evecs = _leading_eigenpairs(G, m0, n_pca_modes if by_variance else None,
-                                           ff.total_variance * (n - 1))
-        del G
-        m0 = min(m0, int(evals.numel())) if by_variance else m0
-        s = torch.sqrt(torch.clamp(evals[:m0], min=0.0))
-        r = m0
-        if by_variance:
+        op = E.FieldOperator(ops, ff, comm, algo=None)
+        seed = self._params["random_state"]
+        seed = 0 if seed is None else seed       # the reference leaves its PCA unseeded; a fixed draw here
+        k_try = min(m0, E.MAX_L - 10) if by_variance else m0
+        while True:
+            n_over = min(10, rank - k_try)
+            Ur, s, Vc, infos = E.randomized_svd(ops, op, k_try, n_oversamples=n_over, n_iter="auto",
+                                                random_state=seed, comm=comm)
+            E.check_infos(infos)
+            r = k_try
+            if not by_variance:
+                break
             cum = torch.cumsum(s**2 / (n - 1) / ff.total_variance, 0)
-            r = m0 - int((cum >= n_pca_modes).sum().item()) + 1
-            if r > m0:
-                warnings.warn(f"Dataset has {m0} components, explaining {float(cum[-1]):.2%} of the variance. However, "
-                              f"{n_pca_modes:.2%} explained variance was requested. Please consider increasing "
-                              "`init_rank_reduction`.")
-                r = m0
-        U, s = evecs[:, :r].contiguous(), s[:r].contiguous()
-        del evecs
-        # sign of every principal component from the extrema of its pattern V[:, j] = A^T u_j / s_j, 128 at a time
-        inv_s = torch.where(s > 0, 1.0 / s, torch.zeros_like(s))
-        signs = []
-        for j0 in range(0, r, 128):
-            w = min(128, r - j0)
-            W = ops.zeros((T, lpad(w)))
-            W[:, :w] = (U[:, j0:j0 + w] * inv_s[j0:j0 + w]).to(torch.float32)
-            Vt = ops.project_S(ff.field, W, w, algo=ops.accurate_algo)
-            signs.append(E.sign_flip(ops, Vt, w, ff.S, comm).double())
-        U = U * torch.cat(signs)[None, :]
-        return U, s
+            r = k_try - int((cum >= n_pca_modes).sum().item()) + 1       # _svd.py:223-227
+            if r <= k_try - 8 or k_try == m0:
+                if r > k_try:
+                    warnings.warn(f"Dataset has {m0} components, explaining {float(cum[-1]):.2%} of the variance. "
+                                  f"However, {n_pca_modes:.2%} explained variance was requested. Please consider "
+                                  "increasing `init_rank_reduction`.")
+                    r = k_try
+                break
+            k_try = min(m0, 2 * k_try + 10, E.MAX_L_TOTAL - 10)           # the cut is too close to the sketch's edge
+            if 2 * r > k_try and k_try < min(m0, E.MAX_L_TOTAL - 10):
+                k_try = min(m0, 4 * r, E.MAX_L_TOTAL - 10)
+        Vt, Ut = (Ur, Vc) if op.transposed else (Vc, Ur)
+        sign = E.sign_flip(ops, Vt, r, ff.S, comm)                      # _svd.py:205-210
+        ops.finish_components(Vt, r, ff.S, sign, None)
+        U = Ut[:, :r].double() * sign.double()[None, :]
+        return U, s[:r].contiguous(), Vt
+
+    def _decompose_small(self, C, k):
+        """SVD of a small dense fp64 matrix (the cross-covariance of two PCA score matrices, decomposer.py:112-146)
+        through the eigen-decomposition of its smaller Gram matrix, all on the library's own kernels.  The
+        reference's randomized solver (n_iter = 7 for k < 0.1 rank) reproduces the exact SVD far inside the parity
+        tolerance.  Returns (Q1 (r1 x k), s (k), Q2 (r2 x k))."""
+        ops = self.ops
+        r1, r2 = int(C.shape[0]), int(C.shape[1])
+        if r2 <= r1:
+            ev, V = ops.sym_eig(ops.dgemm(C, C, trans_a=True))          # C^T C = Q2 s^2 Q2^T
+            s = torch.sqrt(torch.clamp(ev[:k], min=0.0))
+            Q2 = V[:, :k].contiguous()
+            Q1 = ops.dgemm(C, Q2) * torch.where(s > 0, 1.0 / s, torch.zeros_like(s))[None, :]
+        else:
+            ev, V = ops.sym_eig(ops.dgemm(C, C, trans_b=True))          # C C^T = Q1 s^2 Q1^T
+            s = torch.sqrt(torch.clamp(ev[:k], min=0.0))
+            Q1 = V[:, :k].contiguous()
+            Q2 = ops.dgemm(C, Q1, trans_a=True) * torch.where(s > 0, 1.0 / s, torch.zeros_like(s))[None, :]
+        return Q1, s, Q2
+
+    @staticmethod
+    def _modes_for_variance(s, frac, k0, total_variance, n_rows):
+        """decomposer.py:188-216 for a float ``n_modes``: of the k0 precomputed modes keep the first that reach the
+        requested fraction of the matrix' total variance (column variances over its rows, ddof = 1)."""
+        import warnings
+        cum = torch.cumsum(s[:k0] ** 2 / (n_rows - 1) / total_variance, 0)
+        n_req = k0 - int((cum >= frac).sum().item()) + 1
+        if n_req > k0:
+            warnings.warn(f"Dataset has {k0} components, explaining {float(cum[-1]):.2%} of the variance. However, "
+                          f"{frac:.2%} explained variance was requested. Please consider increasing "
+                          "`init_rank_reduction`.")
+            n_req = k0
+        return n_req
 
     def _fit_algorithm_pca(self, f1, f2):
         """cross/base_model_cross_set.py:307-321 + cross/cpcca.py:168-225 on the PCA scores of both fields."""
+        import warnings
         ops, p = self.ops, self._params
         if f1.n_samples != f2.n_samples or f1.T != f2.T:
             raise ValueError(
@@ -185,11 +195,9 @@ class MCA:
                 f"first and {f2.n_samples} in the second."
             )
         npm, irr = _pair(p["n_pca_modes"]), _pair(p["pca_init_rank_reduction"])
-        U1, s1 = self._pca_stage(f1, npm[0], irr[0])
-        U2, s2 = self._pca_stage(f2, npm[1], irr[1])
+        U1, s1, V1t = self._pca_stage(f1, npm[0], irr[0])
+        U2, s2, V2t = self._pca_stage(f2, npm[1], irr[1])
         n, k = f1.n_samples, p["n_modes"]
-        if not isinstance(k, (int, np.integer)):
-            raise NotImplementedError("variance-based n_modes is not supported for MCA in this build")
         X1, X2 = U1 * s1, U2 * s2                                   # pca.py:121-131: A V = U S
         # fractional whitening (preprocessing/whitener.py:111-133): T = C^((alpha-1)/2) with C = X^T X / n, which in
         # the PCA space is diagonal, s^2 / n; alpha = 1 is the identity (MCA), 0 full whitening (CCA)
@@ -200,43 +208,53 @@ class MCA:
             tw.append(torch.ones_like(lam) if a == 1.0 else t)
         X1u, X2u = X1, X2
         X1, X2 = X1 * tw[0], X2 * tw[1]
-        C = X1.t() @ X2 / (n - 1)                                   # cpcca.py:1008-1015, r1 x r2
+        C = ops.dgemm(X1, X2, trans_a=True) / (n - 1)               # cpcca.py:1008-1015, r1 x r2
         rank = min(C.shape)
+        by_variance = isinstance(k, float)
+        frac = k
+        if by_variance:                                            # decomposer.py:88-94
+            k = int(rank * 0.3)
+            if k < 1:
+                warnings.warn("`init_rank_reduction=0.3` is too low resulting in zero components. One component "
+                              "will be computed instead.")
+                k = 1
         if k > rank:
             raise ValueError(f"n_modes must be less than or equal to the rank of the dataset (rank = {rank}).")
         if p["solver"] not in ("auto", "full", "randomized"):
             raise ValueError(f"Unrecognized solver '{p['solver']}'. Valid options are 'auto', 'full', and 'randomized'.")
-        # the small dense decomposition (decomposer.py:112-146) in fp64: the exact SVD, which the reference's
-        # randomized solver (n_iter = 7 for k < 0.1 rank) reproduces far inside the parity tolerance
-        Uc, sc, Vh = torch.linalg.svd(C, full_matrices=False)
-        Q1, s, Q2 = Uc[:, :k], sc[:k], Vh[:k].t()
+        Q1, s, Q2 = self._decompose_small(C, k)
+        if by_variance:
+            tv = C.var(dim=0, unbiased=True).sum()
+            k = self._modes_for_variance(s, frac, k, tv, int(C.shape[0]))
+            Q1, s, Q2 = Q1[:, :k].contiguous(), s[:k].contiguous(), Q2[:, :k].contiguous()
         # decomposer.py:219-222: the sign rule reads Q2 in the space it was computed in, the PCA space
         sign = torch.where(Q2.max(0).values.abs() >= Q2.min(0).values.abs(), 1.0, -1.0).to(torch.float64)
-        Q1, Q2 = Q1 * sign, Q2 * sign
+        Q1, Q2 = (Q1 * sign).contiguous(), (Q2 * sign).contiguous()
         kp = lpad(k)
+        R1, R2 = ops.dgemm(X1, Q1), ops.dgemm(X2, Q2)               # cpcca.py:204-205
         sc1, sc2 = ops.zeros((f1.T, kp)), ops.zeros((f2.T, kp))
-        sc1[:, :k] = (X1 @ Q1).to(torch.float32)                    # cpcca.py:204-205
-        sc2[:, :k] = (X2 @ Q2).to(torch.float32)
-        # components in physical space (pca.py:161-171): V Q = A^T (U S^-1 Q), one streaming pass per field
+        sc1[:, :k] = R1.to(torch.float32)
+        sc2[:, :k] = R2.to(torch.float32)
+        # components in physical space: un-whiten (Tinv^T Q, whitener.py:201-213), then back from the PCA space
+        # (pca.py:161-171): V (Q / t), one k-column product on the space-side block of principal patterns per field
         comps = []
-        for ff, U, sv, t, Q in ((f1, U1, s1, tw[0], Q1), (f2, U2, s2, tw[1], Q2)):
-            # un-whiten (Tinv^T Q, whitener.py:201-213), then back from the PCA space
-            d = sv * t
-            W = ops.zeros((ff.T, kp))
-            W[:, :k] = ((U * torch.where(d > 0, 1.0 / d, torch.zeros_like(d))) @ Q).to(torch.float32)
-            comps.append(ops.project_S(ff.field, W, k, algo=ops.accurate_algo))
+        for ff, Vt, t, Q in ((f1, V1t, tw[0], Q1), (f2, V2t, tw[1], Q2)):
+            Mat = (Q * torch.where(t > 0, 1.0 / t, torch.zeros_like(t))[:, None]).contiguous()
+            comps.append(ops.apply(Vt, ff.S, int(Q.shape[0]), 1, Mat, k))
         self.k = k
         self._Q1t, self._Q2t, self._sc1, self._sc2, self._s = comps[0], comps[1], sc1, sc2, s
         self._f1, self._f2 = f1, f2
         self.n_pca_modes_ = (int(s1.numel()), int(s2.numel()))
-        self._pca_ctx = dict(X1u=X1u, X2u=X2u, Q1=Q1, Q2=Q2, t1=tw[0], t2=tw[1], R1=X1 @ Q1, R2=X2 @ Q2, n=n,
-                             U1=U1, U2=U2)
+        self._pca_ctx = dict(X1u=X1u, X2u=X2u, Q1=Q1, Q2=Q2, t1=tw[0], t2=tw[1], R1=R1, R2=R2, n=n,
+                             U1=U1, U2=U2, V1t=V1t, V2t=V2t, s1=s1, s2=s2)
+        self.__dict__.pop("_proj_cache", None)
+        Cu = C if self._alpha == (1.0, 1.0) else ops.dgemm(X1u, X2u, trans_a=True) / (n - 1)
         self.data = {
             "singular_values": s, "squared_covariance": s**2,
-            "norm1": torch.linalg.norm(X1 @ Q1, dim=0), "norm2": torch.linalg.norm(X2 @ Q2, dim=0),
+            "norm1": torch.linalg.norm(R1, dim=0), "norm2": torch.linalg.norm(R2, dim=0),
             "idx_modes_sorted": torch.argsort(s, descending=True),
             # cpcca.py:991-1000: of the UN-whitened cross-covariance (in the PCA space)
-            "total_squared_covariance": float(((X1u.t() @ X2u / (n - 1)) ** 2).sum().item()),
+            "total_squared_covariance": float((Cu ** 2).sum().item()),
         }
         return self
 
@@ -253,8 +271,14 @@ class MCA:
         op = E.CrossOperator(ops, f1, f2, comm)
         k = p["n_modes"]
         rank = min(op.shape)
-        if not isinstance(k, (int, np.integer)):
-            raise NotImplementedError("variance-based n_modes is not supported for MCA in this build")
+        by_variance, frac = isinstance(k, float), k
+        if by_variance:                                            # decomposer.py:88-94
+            import warnings
+            k = int(rank * 0.3)
+            if k < 1:
+                warnings.warn("`init_rank_reduction=0.3` is too low resulting in zero components. One component "
+                              "will be computed instead.")
+                k = 1
         if k > rank:
             raise ValueError(f"n_modes must be less than or equal to the rank of the dataset (rank = {rank}).")
         solver, kw = p["solver"], dict(p["solver_kwargs"])
@@ -274,6 +298,10 @@ class MCA:
         E.check_infos(infos)
         # C = Q1 s Q2^T;  M = C^T when transposed
         Q1t, Q2t = (Vc, Ur) if op.transposed else (Ur, Vc)
+        self._f1, self._f2 = f1, f2
+        if by_variance:                                            # decomposer.py:188-216 on the implicit C
+            k = self._modes_for_variance(s, frac, k, self._cross_matrix_variance(), f1.n_features)
+            s = s[:k].contiguous()
         sign = E.sign_flip(ops, Q2t, k, f2.S, comm)  # decomposer.py:219-222: rule on V_ = Q2, applied to both
         ops.finish_components(Q2t, k, f2.S, sign, None)
         ops.finish_components(Q1t, k, f1.S, sign, None)
@@ -295,7 +323,29 @@ class MCA:
             self.data["total_squared_covariance"] = self._total_squared_covariance()
         return self
 
+    def _cross_matrix_variance(self):
+        """What decomposer.py:203 evaluates on the cross-covariance matrix, C.var(feature1, ddof=1).sum(feature2) =
+        (sum |C|^2 - S1 sum_j mean_i(C[i,j])^2) / (S1 - 1), without forming C: the column means are
+        1^T C / S1 = (A1 1)^T A2 / ((n-1) S1), two one-column streaming passes."""
+        ops, comm, f1, f2 = self.ops, self.comm, self._f1, self._f2
+        ones = ops.space_side(lpad(1), f1.S, zero=True)
+        ones[0] = 1.0
+        w = ops.project_T(f1.field, ones, 1, algo=ops.accurate_algo)            # A1 1  (T x 1)
+        comm.sum_(w)
+        mu = ops.project_S(f2.field, w, 1, algo=ops.accurate_algo)[0].double()  # (A1 1)^T A2  (S2)
+        mu = mu / float(f1.n_samples - 1) / float(f1.n_features)
+        msq = (mu ** 2).sum()
+        comm.sum_(msq)
+        tsc = self.data.get("total_squared_covariance") if self.data else None
+        if tsc is None:
+            tsc = self._total_squared_covariance()
+            self._tsc_cache = tsc
+        S1 = float(f1.n_features)
+        return (tsc - S1 * float(msq.item())) / (S1 - 1.0)
+
     def _total_squared_covariance(self):
+        if getattr(self, "_tsc_cache", None) is not None:
+            return self._tsc_cache
         """cpcca.py:991-1000: sum |C|^2 = <X X^T, Y Y^T>_F / (n-1)^2, from the two T x T Gram matrices built 128
         columns at a time with the streaming product.  The Gram matrices are symmetric: for the column block starting
         at sample t0 only the samples t >= t0 are streamed, the strictly lower part counts twice."""
@@ -310,12 +360,19 @@ class MCA:
             w = t1 - t0
             prod = g1.double() * g2.double()
             acc += prod[:w].sum() + 2.0 * prod[w:].sum()
-        return float(acc.item()) / float(self._f1.n_samples - 1) ** 2
+        self._tsc_cache = float(acc.item()) / float(self._f1.n_samples - 1) ** 2
+        return self._tsc_cache
 
     # ------------------------------------------------------------------ accessors
     def components(self, normalized=True):
-        c1 = self.preprocessor1.components_to_nd(self._Q1t, self.k, "components1")
-        c2 = self.preprocessor2.components_to_nd(self._Q2t, self.k, "components2")
+        """cpcca.py:308-316 behind base_model_cross_set.py:465-493: normalized=False scales every mode by norm1 /
+        norm2 (the scaling commutes with the linear un-whitening and PCA back-projection)."""
+        Q1t, Q2t = self._Q1t, self._Q2t
+        if not normalized:
+            Q1t = Q1t[: self.k] * self.data["norm1"].to(torch.float32)[:, None]
+            Q2t = Q2t[: self.k] * self.data["norm2"].to(torch.float32)[:, None]
+        c1 = self.preprocessor1.components_to_nd(Q1t, self.k, "components1")
+        c2 = self.preprocessor2.components_to_nd(Q2t, self.k, "components2")
         return c1, c2
 
     def scores(self, normalized=False):
@@ -399,11 +456,8 @@ class MCA:
         cache = self.__dict__.setdefault("_proj_cache", {})
         if i not in cache:
             ff = (self._f1, self._f2)[i]
-            U, t, Q = ctx["U1" if i == 0 else "U2"], ctx["t1" if i == 0 else "t2"], ctx["Q1" if i == 0 else "Q2"]
-            sv = torch.linalg.norm(ctx["X1u" if i == 0 else "X2u"], dim=0)   # columns of U S have norm s
-            W = self.ops.zeros((ff.T, lpad(self.k)))
-            W[:, : self.k] = ((U * torch.where(sv > 0, t / sv, torch.zeros_like(sv))) @ Q).to(torch.float32)
-            cache[i] = self.ops.project_S(ff.field, W, self.k, algo=self.ops.accurate_algo)
+            Vt, t, Q = ctx["V1t" if i == 0 else "V2t"], ctx["t1" if i == 0 else "t2"], ctx["Q1" if i == 0 else "Q2"]
+            cache[i] = self.ops.apply(Vt, ff.S, int(Q.shape[0]), 1, (Q * t[:, None]).contiguous(), self.k)
         return cache[i]
 
     def _transform_one(self, i, data, normalized):
@@ -456,7 +510,7 @@ class MCA:
             sc = sc.movedim(dims.index("mode"), -1)
             sample_dims = tuple(d for d in dims if d != "mode")
             sample_shape = tuple(sc.shape[:-1])
-            modes = np.asarray(coords.get("mode", np.arange(1, sc.shape[-1] + 1))).astype(int) - 1
+            modes = L.mode_indices(coords, int(sc.shape[-1]), self.k)
             pp = (self.preprocessor1, self.preprocessor2)[i]
             if sample_dims != pp.sample_dims:
                 raise ValueError(f"scores have sample dimensions {sample_dims}, the model was fitted with {pp.sample_dims}")
@@ -485,18 +539,13 @@ class MCA:
             num = ops.project_S(ff.field, W, k, algo=ops.accurate_algo)
             std = (ff.std * ff.field.dscale.abs()).double()
         else:
-            # the reconstruction is U S V^T with V S = A^T U:  A_r^T R = A^T U (U^T R),  sum_t A_r[t,s]^2 = |(A^T U)_s|^2
-            U = ctx["U1" if i == 0 else "U2"]
+            # the reconstruction is A_r = U S V^T:  A_r^T R = V S (U^T R),  sum_t A_r[t,s]^2 = sum_j (s_j V[s,j])^2
+            U, Vt, sv = ctx["U1" if i == 0 else "U2"], ctx["V1t" if i == 0 else "V2t"], ctx["s1" if i == 0 else "s2"]
             Uv = U if vs is None else U[vs]
-            W[:, :k] = (U @ (Uv.t() @ Rn)).to(torch.float32)
-            num = ops.project_S(ff.field, W, k, algo=ops.accurate_algo)
-            ss = torch.zeros(ff.S, dtype=torch.float64, device=ops.device)
-            for j0 in range(0, int(U.shape[1]), 128):
-                w = min(128, int(U.shape[1]) - j0)
-                Wb = ops.zeros((ff.T, lpad(w)))
-                Wb[:, :w] = U[:, j0:j0 + w].to(torch.float32)
-                Yt = ops.project_S(ff.field, Wb, w, algo=ops.accurate_algo)
-                ss += (Yt[:w].double() ** 2).sum(0)
+            r = int(sv.numel())
+            Mat = (sv[:, None] * ops.dgemm(Uv, Rn.contiguous(), trans_a=True)).contiguous()
+            num = ops.apply(Vt, ff.S, r, 1, Mat, k)
+            ss = ((Vt[:r].double() * sv[:, None]) ** 2).sum(0)
             std = torch.sqrt(ss / n)
         return num[:k].double() / (n * std)[None, :]
 

@@ -98,8 +98,13 @@ class CPCCARotator:
 
     # ------------------------------------------------------------------ accessors
     def components(self, normalized=True):
-        return (self.preprocessor1.components_to_nd(self._Q1t, self.k, "components1"),
-                self.preprocessor2.components_to_nd(self._Q2t, self.k, "components2"))
+        """cpcca.py:308-316 (inherited by the rotator): normalized=False scales every mode by norm1 / norm2."""
+        Q1t, Q2t = self._Q1t, self._Q2t
+        if not normalized:
+            Q1t = Q1t[: self.k] * self.data["norm1"].to(torch.float32)[:, None]
+            Q2t = Q2t[: self.k] * self.data["norm2"].to(torch.float32)[:, None]
+        return (self.preprocessor1.components_to_nd(Q1t, self.k, "components1"),
+                self.preprocessor2.components_to_nd(Q2t, self.k, "components2"))
 
     def scores(self, normalized=False):
         s1, s2 = self._sc1, self._sc2
@@ -111,8 +116,9 @@ class CPCCARotator:
                 self.preprocessor2.scores_to_nd(s2, self.k, "scores2"))
 
     def transform(self, X=None, Y=None, normalized=False):
-        """cpcca_rotator.py:322-427: project on the UN-rotated singular vectors, divide by sqrt(s), rotate (R^-T),
-        reorder, sign, scale with the rotated norms."""
+        """cpcca_rotator.py:322-427: project the preprocessed data on the UN-rotated singular vectors — taken, as the
+        reference takes them (:359-366), un-whitened and back in physical space, i.e. the model's components, not its
+        whitening projection — divide by sqrt(s), rotate (R^-T), reorder, sign, scale with the rotated norms."""
         if X is None and Y is None:
             raise ValueError("No data provided. Please provide X and/or Y.")
         model, p, m = self.model, self._params, self.k
@@ -126,7 +132,10 @@ class CPCCARotator:
             if d is None:
                 continue
             L.validate_input_type(d)
-            Z, (pp, shp, crd, vs) = model._transform_one(i, d, False)
+            pp = (self.preprocessor1, self.preprocessor2)[i]
+            new, shp, crd, vs = pp.transform(d)
+            Z = self.ops.project_T(new, (model._Q1t, model._Q2t)[i], m, algo=self.ops.accurate_algo)
+            self.comm.sum_(Z)
             scale = self.data["modes_sign"].double()
             if not normalized:
                 scale = scale * self.data["norm1" if i == 0 else "norm2"]

@@ -41,6 +41,7 @@ constexpr int TC_KC = 32;        // K elements per stage (= one 128-byte swizzle
 constexpr int TC_XBYTES = TC_TILE * TC_KC * 4;  // 16 KB of X per stage
 constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_FLUSH = 16;     // 3xTF32: K-chunks accumulated in TMEM before the sum moves to fp32 registers
+constexpr int TC_FLUSH_PK = 32;  // the same for the packed mode (one accumulator buffer: the issuer waits for the move)
 
 struct TcParams {
   int64_t T, S;
@@ -81,12 +82,20 @@ struct TcParams {
 // KB: 32-wide K slabs per pipeline stage (project_T reads KB*128 contiguous bytes of every row per TMA box).
 // RN (single TF32 only): round the operands to TF32 (to nearest) instead of letting the tensor core truncate them — the
 // product is then unbiased (XEOFS_ALGO_TF32X1R: sums that are read as numbers, not only as a subspace).
-template <int NS, bool SIDE_T, int KB, bool STATS = false, bool RN = false>
+// PK (3xTF32 only, lp <= 96): the two products that share the big operand's upper part, a_hi b_hi and a_hi b_lo, are
+// ONE instruction of N = 2 lp against the operand image [b_hi rows | b_lo rows]; a_lo b_hi follows with N = lp into
+// the first half of the accumulator.  tcgen05.mma has a floor of ~63 cycles per instruction whatever N is below ~64
+// (profiles/r01_mma_issue_probe.txt): two instructions per K step instead of three.  The accumulator is then 2 lp
+// columns wide, so there is one buffer (not two taking turns): the issuer waits while the epilogue warps move it into
+// registers, every TC_FLUSH_PK slabs.
+template <int NS, bool SIDE_T, int KB, bool STATS = false, bool RN = false, bool PK = false>
 __global__ void __launch_bounds__(tc_threads(tc_wide(NS, SIDE_T, RN)), (NS == 1 && !SIDE_T && !RN) ? 2 : 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBhi,
                   const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
   static_assert(SIDE_T || KB == 1, "project_S stages are 32 rows of t");
   static_assert(!STATS || (NS == 1 && !SIDE_T), "the statistics ride on the first (single TF32) project_S pass");
+  static_assert(!PK || NS == 3, "operand packing is the 3xTF32 mode's");
+  constexpr int NBUF = PK ? 1 : 2;                  // accumulator buffers of the flushing modes
   constexpr int NPART = NS >= 2 ? 2 : 1;            // parts of the big operand kept per value (hi | lo)
   constexpr int BPART = NS == 3 ? 2 : 1;            // parts of the small operand (NS == 2: it is TF32-exact already)
   // FL: two TMEM accumulators that take turns, each moved into fp32 registers (round-to-nearest adds) after TC_FLUSH
@@ -100,7 +109,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   constexpr int XPITCH = SIDE_T ? KB * 128 + 16 : TC_TILE * 4;
   constexpr int XB = SIDE_T ? TC_TILE * XPITCH : TC_XBYTES;  // bytes of X per stage
   constexpr int ACOLS = TC_KC * KB * NPART;         // TMEM columns of one A-operand slot
-  constexpr int FLUSH_STAGES = TC_FLUSH / KB;       // stages per accumulator flush group (NS >= 2)
+  constexpr int FLUSH_STAGES = (PK ? TC_FLUSH_PK : TC_FLUSH) / KB;  // stages per accumulator flush group (NS >= 2)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,7 +147,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t a_col0 = (FL ? 2 : 1) * p.dcols;  // first TMEM column of the A-operand ring
+  const uint32_t a_col0 = (FL ? NBUF : 1) * p.dcols;  // first TMEM column of the A-operand ring
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -160,8 +169,9 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           tma_load_2d(xs + (size_t)st * XB, &mapX, k0, tile0i, &full[st], HINT_EVICT_FIRST);
           bulk_load_1d(pd + st * KB * 256, p.pivot + 2 * k0, KB * 256, &full[st]);
         }
-        tma_load_2d(b, &mapBhi, 0, brow, &full[st], HINT_EVICT_LAST);
-        if (NS == 3) tma_load_2d(b + (size_t)KB * bbytes, &mapBlo, 0, brow, &full[st], HINT_EVICT_LAST);
+        // packed: the image of a slab is [hi rows | lo rows], one box brings both for all KB slabs of the stage
+        tma_load_2d(b, &mapBhi, 0, PK ? 2 * brow : brow, &full[st], HINT_EVICT_LAST);
+        if (NS == 3 && !PK) tma_load_2d(b + (size_t)KB * bbytes, &mapBlo, 0, brow, &full[st], HINT_EVICT_LAST);
       }
       __syncwarp();
     }
@@ -169,6 +179,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     // ===================================================================== MMA issuer
     {
       const uint32_t idesc = make_idesc(lp);
+      const uint32_t idesc2 = make_idesc(2 * lp);  // packed: N = 2 lp
       Pipe pp;
       int g = 0, cg = 0;  // flush group and stage within it (NS == 3)
       for (int c = 0; c < nchunks; ++c, pp.advance(stages)) {
@@ -176,9 +187,9 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         uint32_t d_tmem = tmem_base;
         bool first = c == 0;
         if (FL) {
-          const int buf = g & 1;
+          const int buf = g % NBUF;
           first = cg == 0;
-          if (first) mbar_wait(&dempty[buf], (((uint32_t)g >> 1) & 1) ^ 1);  // registers hold what this buffer had
+          if (first) mbar_wait(&dempty[buf], (((uint32_t)g / NBUF) & 1) ^ 1);  // registers hold what this buffer had
           d_tmem = tmem_base + buf * p.dcols;
         }
         mbar_wait(&full[st], pp.ph);
@@ -190,19 +201,24 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           const uint32_t b0 = smem_u32(bs + (size_t)st * BPART * KB * bbytes);
 #pragma unroll
           for (int kb = 0; kb < KB; ++kb) {
-            const uint64_t dh = make_b_desc(b0 + kb * bbytes);
-            const uint64_t dl = NS == 3 ? make_b_desc(b0 + (KB + kb) * bbytes) : 0;
+            const uint64_t dh = make_b_desc(b0 + kb * (PK ? 2 : 1) * bbytes);
+            const uint64_t dl = (NS == 3 && !PK) ? make_b_desc(b0 + (KB + kb) * bbytes) : 0;
 #pragma unroll
             for (int k = 0; k < TC_KC / 8; ++k) {
               // +32 bytes (8 tf32) along K inside the swizzle atom = +2 in the (address >> 4) field
               const uint32_t a = a_hi + kb * TC_KC + k * 8;
-              mma_tf32_ts(d_tmem, a, dh + 2 * k, idesc, !(first && kb == 0 && k == 0));
-              if (NS == 3) mma_tf32_ts(d_tmem, a, dl + 2 * k, idesc, 1);
-              if (NS >= 2) mma_tf32_ts(d_tmem, a + TC_KC * KB, dh + 2 * k, idesc, 1);
+              if (PK) {
+                mma_tf32_ts(d_tmem, a, dh + 2 * k, idesc2, !(first && kb == 0 && k == 0));  // a_hi [b_hi | b_lo]
+                mma_tf32_ts(d_tmem, a + TC_KC * KB, dh + 2 * k, idesc, 1);                  // a_lo b_hi
+              } else {
+                mma_tf32_ts(d_tmem, a, dh + 2 * k, idesc, !(first && kb == 0 && k == 0));
+                if (NS == 3) mma_tf32_ts(d_tmem, a, dl + 2 * k, idesc, 1);
+                if (NS >= 2) mma_tf32_ts(d_tmem, a + TC_KC * KB, dh + 2 * k, idesc, 1);
+              }
             }
           }
           mma_commit(&empty[st]);
-          if (group_end) mma_commit(&dfull[g & 1]);
+          if (group_end) mma_commit(&dfull[g % NBUF]);
           if (!FL && c == nchunks - 1) mma_commit(&dfull[0]);
         }
         __syncwarp();
@@ -245,8 +261,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     int next_flush = 0;
     // registers += accumulator buffer of flush group g (after the MMA warp committed it), then hand the buffer back
     auto flush = [&](int g) {
-      const int buf = g & 1;
-      mbar_wait(&dfull[buf], ((uint32_t)g >> 1) & 1);
+      const int buf = g % NBUF;
+      mbar_wait(&dfull[buf], ((uint32_t)g / NBUF) & 1);
       tc_fence_after();
 #pragma unroll
       for (int gi = 0; gi < ACCN / 4; ++gi) {
@@ -255,6 +271,11 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           tmem_ld4(tmem_base + lane_addr + buf * p.dcols + part * cw + gi * 4, v);
 #pragma unroll
           for (int e = 0; e < 4; ++e) acc[(FL ? gi * 4 + e : 0)] += v[e];
+          if (PK) {  // the a_hi b_lo half
+            tmem_ld4(tmem_base + lane_addr + lp + part * cw + gi * 4, v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[(FL ? gi * 4 + e : 0)] += v[e];
+          }
         }
       }
       tc_fence_before();
@@ -476,11 +497,13 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 // remainder (3xTF32 only, else the value goes in unsplit).  Zero beyond T.
 __global__ void __launch_bounds__(256)
 prep_W_kernel(const float* __restrict__ W, int64_t T, int64_t ldw, int lp, float* __restrict__ Whi, float* __restrict__ Wlo,
-              int rn = 0) {
-  // one block per slab of 32 t: thread (j, 4 k's)
+              int rn = 0, int slab_floats = 0) {
+  // one block per slab of 32 t: thread (j, 4 k's).  slab_floats: distance between the images of consecutive slabs
+  // (lp * 32, or 2 * lp * 32 when hi and lo rows share one image: Wlo = Whi + lp * 32)
   const int64_t t0 = (int64_t)blockIdx.x * 32;
-  float* hi = Whi + (size_t)blockIdx.x * lp * 32;
-  float* lo = Wlo ? Wlo + (size_t)blockIdx.x * lp * 32 : nullptr;
+  const size_t ss = slab_floats ? (size_t)slab_floats : (size_t)lp * 32;
+  float* hi = Whi + (size_t)blockIdx.x * ss;
+  float* lo = Wlo ? Wlo + (size_t)blockIdx.x * ss : nullptr;
   for (int idx = threadIdx.x; idx < lp * 32; idx += 256) {
     const int kk = idx / lp, j = idx % lp;  // consecutive threads walk a row of W
     const int64_t t = t0 + kk;
@@ -522,10 +545,11 @@ __global__ void chunk_flags_kernel(const uint8_t* __restrict__ row_valid, int64_
 // Yt (lp x ldy, space-side) -> images of its K slabs (K = s), zero beyond S.  One block per slab.
 __global__ void __launch_bounds__(256)
 tile_Y_kernel(const float* __restrict__ Yt, int64_t S, int64_t ldy, int lp, float* __restrict__ Yhi, float* __restrict__ Ylo,
-              int rn = 0) {
+              int rn = 0, int slab_floats = 0) {
   const int64_t s0 = (int64_t)blockIdx.x * 32;
-  float* hi = Yhi + (size_t)blockIdx.x * lp * 32;
-  float* lo = Ylo ? Ylo + (size_t)blockIdx.x * lp * 32 : nullptr;
+  const size_t ss = slab_floats ? (size_t)slab_floats : (size_t)lp * 32;
+  float* hi = Yhi + (size_t)blockIdx.x * ss;
+  float* lo = Ylo ? Ylo + (size_t)blockIdx.x * ss : nullptr;
   const int kk = threadIdx.x & 31;
   for (int j = threadIdx.x >> 5; j < lp; j += 8) {
     const float v = (s0 + kk < S) ? Yt[(int64_t)j * ldy + s0 + kk] : 0.f;
@@ -626,6 +650,8 @@ static inline int64_t align256(int64_t b) { return round_up(b, 256); }
 static inline bool is_x3(int algo) { return algo == XEOFS_ALGO_TF32X3 || algo == XEOFS_ALGO_AUTO; }
 static inline int algo_ns(int algo) { return algo == XEOFS_ALGO_TF32X3 ? 3 : algo == XEOFS_ALGO_TF32X2 ? 2 : 1; }
 static inline bool algo_rn(int algo) { return algo == XEOFS_ALGO_TF32X1R; }
+// 3xTF32 with the two products of the big operand's upper part packed into one N = 2 lp instruction (see the kernel)
+static inline bool use_pack(int ns, int lp) { return ns == 3 && lp <= 96 && env_int("XEOFS_TC_PACK", 1) != 0; }
 
 // project_T: 32-wide K slabs per stage = bytes of a row fetched per bulk copy / 128.  The largest that leaves
 // at least two stages of shared memory and TMEM.
@@ -638,12 +664,13 @@ static Shape pick_shape(int lp, int ns, bool side_t, int kb, bool rn = false) {
   Shape sh;
   const int npart = ns >= 2 ? 2 : 1, bpart = ns == 3 ? 2 : 1;
   const bool two_ctas = !side_t && ns == 1 && !rn;  // project_S x1: two CTAs per SM share the 512 TMEM columns
+  const bool pk = use_pack(ns, lp);
   const int xb = side_t ? TC_TILE * (kb * 128 + 16) : TC_XBYTES;
   const int per_stage = xb + lp * TC_KC * 4 * bpart * kb + (side_t ? kb * 256 : 0);
   sh.kb = kb;
-  sh.dcols = (int)round_up(lp, 32);
+  sh.dcols = (int)round_up(pk ? 2 * lp : lp, 32);
   sh.tmem_cols = two_ctas ? 256 : 512;
-  const int ring = (int)sh.tmem_cols - ((ns >= 2 || rn) ? 2 : 1) * sh.dcols;
+  const int ring = (int)sh.tmem_cols - (pk ? 1 : (ns >= 2 || rn) ? 2 : 1) * sh.dcols;
   const int by_tmem = ring / (TC_KC * kb * npart);
   const int budget = (two_ctas ? 110 : 222) * 1024 - 2048;
   int st = budget / per_stage;
@@ -709,11 +736,11 @@ int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo) {
   return (bs > bt ? bs : bt) + 256;
 }
 
-template <int NS, bool SIDE_T, int KB, bool RN = false>
+template <int NS, bool SIDE_T, int KB, bool RN = false, bool PK = false>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p, dim3 grid,
                      size_t smem, cudaStream_t stream) {
-  XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<NS, SIDE_T, KB, false, RN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  project_tc_kernel<NS, SIDE_T, KB, false, RN><<<grid, tc_threads(tc_wide(NS, SIDE_T, RN)), smem, stream>>>(mx, mh, ml, p);
+  XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<NS, SIDE_T, KB, false, RN, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  project_tc_kernel<NS, SIDE_T, KB, false, RN, PK><<<grid, tc_threads(tc_wide(NS, SIDE_T, RN)), smem, stream>>>(mx, mh, ml, p);
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
 }
@@ -728,8 +755,10 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   uint8_t* ws = (uint8_t*)workspace;
   float* wsum = (float*)ws;
   uint8_t* flags = ws + align256(lp * 4);
+  const bool pk = use_pack(ns, lp);
   float* Whi = (float*)(flags + align256(Tpad / TC_KC));
-  float* Wlo = ns == 3 ? (float*)((uint8_t*)Whi + align256(lp * Tpad * 4)) : nullptr;
+  // packed: one image per slab, [hi rows | lo rows]
+  float* Wlo = ns == 3 ? (pk ? Whi + lp * 32 : (float*)((uint8_t*)Whi + align256(lp * Tpad * 4))) : nullptr;
   int rc = XEOFS_OK;
   if (ccorr) {  // the rank-1 term ccorr[s] * colsum(W)[j] exists only for un-centred fields
     rc = launch_colsum(W, T, ldw, lp, row_valid, wsum, stream);
@@ -739,16 +768,18 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
     chunk_flags_kernel<<<(unsigned)ceil_div(Tpad / TC_KC, 128), 128, 0, stream>>>(row_valid, T, (int)(Tpad / TC_KC), flags);
     XB_LAUNCH_CHECK();
   }
-  prep_W_kernel<<<(unsigned)(Tpad / TC_KC), 256, 0, stream>>>(W, T, ldw, lp, Whi, Wlo, algo_rn(algo) ? 1 : 0);
+  prep_W_kernel<<<(unsigned)(Tpad / TC_KC), 256, 0, stream>>>(W, T, ldw, lp, Whi, Wlo, algo_rn(algo) ? 1 : 0,
+                                                              pk ? 2 * lp * 32 : 0);
   XB_LAUNCH_CHECK();
   CUtensorMap mx, mh, ml;
   rc = make_map2(&mx, X, S, T, ldx, TC_TILE, TC_KC, false);
   if (rc) return rc;
   // the operand images as rows of 1 KB: a stage's image arrives as lp/8 long pieces
-  rc = make_map2(&mh, Whi, 256, (Tpad / TC_KC) * (lp / 8), 256, 256, lp / 8, false);
+  const int bp = pk ? 2 : 1;
+  rc = make_map2(&mh, Whi, 256, (Tpad / TC_KC) * (bp * lp / 8), 256, 256, bp * lp / 8, false);
   if (rc) return rc;
   ml = mh;
-  if (ns == 3) {
+  if (ns == 3 && !pk) {
     rc = make_map2(&ml, Wlo, 256, (Tpad / TC_KC) * (lp / 8), 256, 256, lp / 8, false);
     if (rc) return rc;
   }
@@ -763,7 +794,8 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   p.X = X; p.ldx = ldx; p.bimg_hi = Whi; p.bimg_lo = Wlo;
   p.chunk_flags = row_valid ? flags : nullptr;
   dim3 grid((unsigned)ceil_div(S, TC_TILE));
-  return ns == 3        ? launch_tc<3, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
+  return ns == 3 && pk  ? launch_tc<3, false, 1, false, true>(mx, mh, ml, p, grid, sh.smem, stream)
+         : ns == 3      ? launch_tc<3, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
          : ns == 2      ? launch_tc<2, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
          : algo_rn(algo) ? launch_tc<1, false, 1, true>(mx, mh, ml, p, grid, sh.smem, stream)
                         : launch_tc<1, false, 1>(mx, mh, ml, p, grid, sh.smem, stream);
@@ -845,11 +877,13 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   float* rvec = (float*)ws; ws += align256(lp * 4);
   float* pdpad = (float*)ws; ws += 2 * align256(g.Spad * 4);
   float* part = (float*)ws; ws += align256((int64_t)g.splits * g.rows_pad * lp * 4);
+  const bool pk = use_pack(ns, lp);
   float* Yhi = (float*)ws; ws += align256(lp * g.Spad * 4);
-  float* Ylo = ns == 3 ? (float*)ws : nullptr;
+  float* Ylo = ns == 3 ? (pk ? Yhi + lp * 32 : (float*)ws) : nullptr;
   pad_vectors_kernel<<<(unsigned)ceil_div(g.Spad, 256), 256, 0, stream>>>(pivot, dscale, S, g.Spad, pdpad);
   XB_LAUNCH_CHECK();
-  tile_Y_kernel<<<(unsigned)(g.Spad / TC_KC), 256, 0, stream>>>(Yt, S, ldy, lp, Yhi, Ylo, algo_rn(algo) ? 1 : 0);
+  tile_Y_kernel<<<(unsigned)(g.Spad / TC_KC), 256, 0, stream>>>(Yt, S, ldy, lp, Yhi, Ylo, algo_rn(algo) ? 1 : 0,
+                                                                pk ? 2 * lp * 32 : 0);
   XB_LAUNCH_CHECK();
   int rc;
   if (ccorr) {
@@ -869,15 +903,20 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   // rows of X in pieces of KB*32 + 4 floats (the 4 extra only give the shared-memory rows their odd pitch)
   rc = make_map2(&mx, X, S, T, ldx, kb * TC_KC + 4, TC_TILE, false);
   if (rc) return rc;
-  rc = make_map2(&mh, Yhi, 256, (g.Spad / TC_KC) * (lp / 8), 256, 256, kb * lp / 8, false);
+  const int bp = pk ? 2 : 1;
+  rc = make_map2(&mh, Yhi, 256, (g.Spad / TC_KC) * (bp * lp / 8), 256, 256, kb * bp * lp / 8, false);
   if (rc) return rc;
   ml = mh;
-  if (ns == 3) {
+  if (ns == 3 && !pk) {
     rc = make_map2(&ml, Ylo, 256, (g.Spad / TC_KC) * (lp / 8), 256, 256, kb * lp / 8, false);
     if (rc) return rc;
   }
 #define XB_T_LAUNCH(NSV, KBV) launch_tc<NSV, true, KBV>(mx, mh, ml, p, grid, sh.smem, stream)
-  if (ns == 3) rc = kb == 1 ? XB_T_LAUNCH(3, 1) : kb == 2 ? XB_T_LAUNCH(3, 2) : XB_T_LAUNCH(3, 4);
+  if (ns == 3 && pk)
+    rc = kb == 1   ? launch_tc<3, true, 1, false, true>(mx, mh, ml, p, grid, sh.smem, stream)
+         : kb == 2 ? launch_tc<3, true, 2, false, true>(mx, mh, ml, p, grid, sh.smem, stream)
+                   : launch_tc<3, true, 4, false, true>(mx, mh, ml, p, grid, sh.smem, stream);
+  else if (ns == 3) rc = kb == 1 ? XB_T_LAUNCH(3, 1) : kb == 2 ? XB_T_LAUNCH(3, 2) : XB_T_LAUNCH(3, 4);
   else if (ns == 2) rc = kb == 1 ? XB_T_LAUNCH(2, 1) : kb == 2 ? XB_T_LAUNCH(2, 2) : XB_T_LAUNCH(2, 4);
   else if (algo_rn(algo))
     rc = kb == 1   ? launch_tc<1, true, 1, true>(mx, mh, ml, p, grid, sh.smem, stream)

@@ -181,7 +181,7 @@ class EOF:
         sc = sc.movedim(dims.index("mode"), -1)
         sample_dims = tuple(d for d in dims if d != "mode")
         sample_shape = tuple(sc.shape[:-1])
-        modes = np.asarray(coords.get("mode", np.arange(1, sc.shape[-1] + 1))).astype(int) - 1
+        modes = L.mode_indices(coords, int(sc.shape[-1]), self.k)
         sc2 = sc.reshape(-1, sc.shape[-1])
         if normalized:
             sc2 = sc2 * self._s.to(torch.float32)[torch.as_tensor(modes, device=sc2.device)][None, :]

@@ -90,10 +90,11 @@ class EOFRotator:
                 d = None if not use_tc else vals[-1]
                 continue
             d_old, d = d, float(dsum.item())
-            if d_old is not None and abs(d - d_old) / d < p["rtol"]:
+            if p["compute"] and d_old is not None and abs(d - d_old) / d < p["rtol"]:
                 converged = True
                 break
-        if not converged:
+        # compute=False: the reference runs all max_iter iterations without a test and never raises (_rotation.py:176-180)
+        if p["compute"] and not converged:
             raise RuntimeError("Rotation process did not converge.")  # _rotation.py:179-180
         self.n_iter_ = it
         eye = torch.eye(m, dtype=torch.float64, device=ops.device)
