@@ -25,3 +25,20 @@ def test_cross_transform_predict_inverse(mode):
 
 def test_mca_rotator_and_its_transform():
     H.test_mca_rotator_host_logic()
+
+
+def test_mca_more_samples_than_features_default_pca():
+    H.test_mca_more_samples_than_features_default_pca()
+
+
+@pytest.mark.parametrize("use_pca", [True, False])
+def test_mca_variance_based_n_modes(use_pca):
+    H.test_mca_variance_based_n_modes(use_pca)
+
+
+def test_inverse_transform_rejects_modes_the_model_does_not_hold():
+    H.test_inverse_transform_rejects_modes_the_model_does_not_hold()
+
+
+def test_rotator_compute_false_runs_max_iter_without_raising():
+    H.test_rotator_compute_false_runs_max_iter_without_raising()

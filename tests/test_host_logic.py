@@ -598,3 +598,76 @@ def test_feature_sharded_fit_over_gloo(tmp_path):
         np.testing.assert_allclose(r["pca_tsc"], mp.total_squared_covariance(), rtol=1e-5)
     np.testing.assert_allclose(np.concatenate([r0["mca_c1"], r1["mca_c1"]], axis=0), mi.components()[0].values, atol=5e-5)
     np.testing.assert_allclose(np.concatenate([r0["pca_c2"], r1["pca_c2"]], axis=0), mp.components()[1].values, atol=5e-5)
+
+
+def test_mca_more_samples_than_features_default_pca():
+    """Default arguments (use_pca=True, n_pca_modes=0.999) on fields with n_samples > n_features — station data, small
+    grids with long records: the PCA stage runs the range finder in the other orientation
+    (preprocessing/pca.py:94-131; the round-1 build raised here)."""
+    import xeofs_b200 as xb
+    T, k = 400, 2
+    rng = np.random.default_rng(8)
+    U = np.linalg.qr(rng.standard_normal((T, 4)))[0]
+    sig = 100 * 0.6 ** np.arange(4)
+    X = ((U * sig) @ np.linalg.qr(rng.standard_normal((40, 4)))[0].T + 0.01 * rng.standard_normal((T, 40))).astype(np.float32)
+    Y = ((U * sig) @ np.linalg.qr(rng.standard_normal((30, 4)))[0].T + 0.01 * rng.standard_normal((T, 30))).astype(np.float32)
+    o = omca.mca_fit(X, Y, ("time", "x"), ("time", "y"), "time", n_modes=k, random_state=3, use_pca=True,
+                     pca_random_state=1)
+    m = xb.cross.MCA(n_modes=k, random_state=3, ops=make_ops())
+    m.fit(xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")
+    assert m.n_pca_modes_ == o["n_pca_modes"]
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    c1, c2 = m.components()
+    for c, oc in ((c1, o["components1_2d"]), (c2, o["components2_2d"])):
+        assert ((c.values * oc).sum(axis=0) > 1 - 1e-4).all()
+    s1, _ = m.scores()
+    np.testing.assert_allclose(s1.values, o["scores1"], atol=1e-3 * np.abs(o["scores1"]).max())
+
+
+@pytest.mark.parametrize("use_pca", [True, False])
+def test_mca_variance_based_n_modes(use_pca):
+    """A float ``n_modes`` (linalg/decomposer.py:88-94, 188-216): int(0.3 rank) modes of the cross-covariance matrix are
+    computed and the first that reach the fraction of ITS total variance (column variances over feature1, ddof = 1)
+    are kept."""
+    import xeofs_b200 as xb
+    T = 200
+    rng = np.random.default_rng(2)
+    U = np.linalg.qr(rng.standard_normal((T, 8)))[0]
+    sig = 100 * 0.6 ** np.arange(8)
+    X = ((U * sig) @ np.linalg.qr(rng.standard_normal((60, 8)))[0].T + 0.01 * rng.standard_normal((T, 60))).astype(np.float32)
+    Y = ((U * sig) @ np.linalg.qr(rng.standard_normal((50, 8)))[0].T + 0.01 * rng.standard_normal((T, 50))).astype(np.float32)
+    kw = dict(use_pca=True, n_pca_modes=20, pca_random_state=1) if use_pca else dict(use_pca=False)
+    o = omca.mca_fit(X, Y, ("time", "x"), ("time", "y"), "time", n_modes=0.95, random_state=3, **kw)
+    mk = dict(n_pca_modes=20) if use_pca else dict(use_pca=False)
+    m = xb.cross.MCA(n_modes=0.95, random_state=3, ops=make_ops(), **mk)
+    m.fit(xb.DataArray(X, ("time", "x")), xb.DataArray(Y, ("time", "y")), dim="time")
+    assert m.k == len(o["singular_values"]) and 1 <= m.k < 15
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    c1, _ = m.components()
+    assert c1.values.shape[-1] == m.k
+    assert ((c1.values * o["components1_2d"]).sum(axis=0) > 1 - 1e-4).all()
+
+
+def test_inverse_transform_rejects_modes_the_model_does_not_hold():
+    """The reference's .sel(mode=...) raises KeyError (single/eof.py:150-152); the device kernel indexes with them."""
+    import xeofs_b200 as xb
+    X = mock_data_array().astype(np.float32)
+    m = xb.single.EOF(n_modes=3, ops=make_ops()).fit(xb.DataArray(X, DIMS, {"lat": MOCK_LAT, "lon": MOCK_LON}), dim="time")
+    sc = m.scores()
+    for bad in ([0, 1, 2], [1, 2, 4], [1, 2, 17]):
+        with pytest.raises(KeyError):
+            m.inverse_transform(xb.DataArray(sc.values, ("time", "mode"), {"mode": np.array(bad)}))
+    rec = m.inverse_transform(xb.DataArray(sc.values[:, :2], ("time", "mode"), {"mode": np.array([1, 3])}))
+    assert rec.values.shape == X.shape
+
+
+def test_rotator_compute_false_runs_max_iter_without_raising():
+    """linalg/_numpy/_rotation.py:172-180: with compute=False there is no stopping test and no RuntimeError."""
+    import xeofs_b200 as xb
+    X = planted(200, 300, 12, seed=4).reshape(200, 10, 30)
+    coords = {"lat": np.linspace(60, -60, 10), "lon": np.arange(30) * 12.0}
+    m = xb.single.EOF(n_modes=6, ops=make_ops()).fit(xb.DataArray(X, DIMS, coords), dim="time")
+    r = xb.single.EOFRotator(n_modes=6, max_iter=3, compute=False).fit(m)
+    assert r.n_iter_ == 3
+    with pytest.raises(RuntimeError, match="did not converge"):
+        xb.single.EOFRotator(n_modes=6, max_iter=3, compute=True).fit(m)

@@ -14,6 +14,18 @@ from . import _labels as L
 from ._engine import NO_COMM, fit_field
 
 
+def _align_rows(t2):
+    """The TMA descriptors of the tensor-core kernels need 16-byte aligned rows: a field whose row length is not a
+    multiple of 4 floats (BASELINE configs[0]: 25 x 53 = 1325 features) gets ONE padded-pitch copy here instead of
+    running every pass on the CUDA-core path."""
+    if not t2.is_cuda or (t2.stride(0) % 4 == 0 and t2.data_ptr() % 16 == 0):
+        return t2
+    T, S = int(t2.shape[0]), int(t2.shape[1])
+    buf = torch.empty((T, (S + 31) // 32 * 32), dtype=torch.float32, device=t2.device)
+    buf[:, :S].copy_(t2)
+    return buf[:, :S]
+
+
 def _new_field(ops, comm, ff, X2, check_nans):
     """Unseen data behind the fitted scaling vectors + the Sanitizer's checks on it (sanitizer.py:108-122)."""
     from ._cuda_ops import Field
@@ -77,7 +89,7 @@ class Preprocessor:
         t2 = t.reshape(T, S)  # copies only when the permutation made it non-viewable
         if t2.stride(1) != 1 or (T > 1 and t2.stride(0) < S):
             t2 = t2.contiguous()
-        return t2, sample_shape, feature_shape
+        return _align_rows(t2), sample_shape, feature_shape
 
     # ------------------------------------------------------------------ fit
     def _prepare(self, X, sample_dims, weights=None):
@@ -208,7 +220,7 @@ class MultiPreprocessor:
             raise ValueError(f"All arrays must have the same sample dimensions; found shapes {sorted(shapes)}.")
         sizes = [int(m.shape[1]) for m in mats]
         self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(int)
-        X2 = torch.cat(mats, dim=1)
+        X2 = _align_rows(torch.cat(mats, dim=1))
         del mats
         featw = None
         if any(fw is not None for fw in fws):
@@ -238,7 +250,7 @@ class MultiPreprocessor:
             if feature_shape != p.feature_shape:
                 raise ValueError(f"Feature shape {feature_shape} differs from the fitted one {p.feature_shape}.")
             mats.append(X2)
-        new, valid_sample = _new_field(self.ops, self.comm, self.fitted, torch.cat(mats, dim=1), self.check_nans)
+        new, valid_sample = _new_field(self.ops, self.comm, self.fitted, _align_rows(torch.cat(mats, dim=1)), self.check_nans)
         sample_coords = {d: coords[d] for d in self.parts[0].sample_dims if d in coords}
         return new, sample_shape, sample_coords, valid_sample
 
