@@ -48,6 +48,9 @@ extern "C" {
 #define XEOFS_ALGO_TF32X2 5 /* tcgen05 kind::tf32, field split hi/lo, the small operand (W / Yt) must hold TF32-exact
                                values (xeofs_b200_round_tf32): 2 products, ~fp32 accuracy; SIMT where tcgen05 does
                                not apply                                                                        */
+/* OR-ed into `algo` of project_T: the caller vouches that the field holds no NaN / Inf at all (every feature and every
+ * sample valid, row_valid NULL), so the tensor-core operand stage skips its per-value test.                          */
+#define XEOFS_ALGO_FLAG_NO_NAN 0x100
 #define XEOFS_ALGO_TF32X1R 6 /* TF32X1 with both operands rounded to TF32 to nearest (unbiased sums; else as TF32X1) */
 
 /* flags for xeofs_b200_scaling_finalize */
@@ -165,6 +168,15 @@ int xeofs_b200_varimax_accumulate(const float* L, int64_t S, int64_t m, int64_t 
 int64_t xeofs_b200_varimax_workspace_bytes(int64_t S, int64_t m);
 int xeofs_b200_varimax_sweep(const float* Ln, int64_t S, int64_t m, int64_t ld, const double* R, double* Gout,
                              double* Wout, int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
+/* The m x m step of one varimax iteration (_rotation.py:170-175), on the device: with Gout / Wout of the sweep, XtX =
+ * Ln^T Ln and alpha = gamma / n_rows,  G = Gout - alpha (XtX R) diag(Wout);  R <- U V^T of svd(G) (in place);
+ * *dsum = sum(svals).  `basis` (m x m, in/out; identity before the first iteration) carries the eigenvectors of
+ * G^T G from one iteration to the next — in that basis the matrix is nearly diagonal and the Jacobi solver ends early.
+ * m <= 128; all matrices fp64 row-major.                                                                            */
+int64_t xeofs_b200_varimax_update_workspace_bytes(int64_t m);
+int xeofs_b200_varimax_update(const double* Gout, const double* Wout, const double* XtX, double alpha, int64_t m,
+                              double* R, double* basis, double* dsum, void* workspace, int64_t workspace_bytes,
+                              void* stream);
 /* Kaiser norms (_rotation.py:155-160): h[s] = sqrt(sum_j L[j,s]^2); rownorm[s] = 1/(h+eps);
  * Ln[j,s] = L[j,s] * rownorm[s] (space-side, ldn >= S).  Any of h / rownorm / Ln may be NULL.             */
 int xeofs_b200_col_norms(const float* L, int64_t S, int64_t m, int64_t ld, float* h, float* rownorm, float* Ln,

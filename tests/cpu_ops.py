@@ -192,6 +192,14 @@ class TorchCpuOps:
             Ln[:m] = L[:m, :S] * rn[None, :]
         return h, rn, Ln
 
+    def varimax_update(self, G3, W, XtX, alpha, R, basis, dsum):
+        G = G3 - alpha * (XtX @ R) * W[None, :]
+        U, sv, Vh = torch.linalg.svd(G)
+        R.copy_(U @ Vh)
+        basis.copy_(Vh.t())
+        dsum.fill_(float(sv.sum()))
+        return dsum
+
     def varimax_accumulate(self, L, S, m, R, power=3.0, colscale=None, want_absmax=False, exact=False):
         X = L[:m, :S].double().t()
         B = X @ R

@@ -215,25 +215,29 @@ def test_mca_default_pca_stage_matches_oracle(npm):
         np.testing.assert_allclose(sc.values / scale, osc / scale, atol=2e-3)
 
 
-def test_mca_pca_stage_subspace_route():
-    """Enough samples (int(0.3 n) >= 512) for the PCA stage to take the blocked subspace iteration on the sample Gram
-    matrix instead of the dense eigen-decomposition: same oracle (the reference's randomized-SVD PCA), same bars."""
+def test_mca_pca_stage_wide_sketch_runs_on_own_kernels():
+    """2000 samples, noise-dominated tail: the 99.9 % cut is not reached inside one 128-column sketch, so the PCA stage
+    widens it up to int(0.3 n) = 600 modes (the reference's own width) — the k-column algebra beyond one kernel block
+    (cross-block Gram, multi-CTA Jacobi, eigen-orthonormalisation).  No torch.linalg routine (cuSOLVER / cuBLAS) may run
+    during the fit; same oracle (the reference's randomized-SVD PCA), same bars."""
     import xeofs_b200 as xb
-    from xeofs_b200.cross import mca as mca_mod
     T, S1, S2, k = 2000, 64 * 64, 48 * 64, 5
     X, Y = _coupled_fields(T, S1, S2, 2 * k, seed=19)
     X = X.reshape(T, 64, 64)
     Y = Y.reshape(T, 48, 64)
     o = omca.mca_fit(X, Y, DIMS, DIMS, "time", n_modes=k, random_state=3, use_pca=True, pca_random_state=1)
+    names = ["qr", "eigh", "svd", "cholesky_ex", "cholesky", "solve_triangular", "solve", "inv", "eig", "svdvals"]
+    orig = {n: getattr(torch.linalg, n) for n in names}
     calls = []
-    orig = torch.linalg.qr
     m = xb.cross.MCA(n_modes=k, random_state=3)
     try:
-        torch.linalg.qr = lambda *a, **kw: (calls.append(1), orig(*a, **kw))[1]
+        for n in names:
+            setattr(torch.linalg, n, (lambda nn: lambda *a, **kw: (calls.append(nn), orig[nn](*a, **kw))[1])(n))
         m.fit(xb.DataArray(X, DIMS), xb.DataArray(Y, DIMS), dim="time")
     finally:
-        torch.linalg.qr = orig
-    assert calls, "the subspace route was not taken"
+        for n in names:
+            setattr(torch.linalg, n, orig[n])
+    assert not calls, f"library factorizations on the fit path: {calls}"
     assert all(abs(a - b) <= 2 for a, b in zip(m.n_pca_modes_, o["n_pca_modes"])), (m.n_pca_modes_, o["n_pca_modes"])
     np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
     c1, c2 = m.components()

@@ -20,7 +20,8 @@ class Field:
     vectors that fold Scaler.transform (preprocessing/scaler.py:146-153) into the operand load:
     A[t,s] = (X[t,s] - pivot[s]) * dscale[s] + ccorr[s]."""
 
-    def __init__(self, X, pivot, dscale, ccorr, valid, mean=None, std=None, row_valid=None):
+    def __init__(self, X, pivot, dscale, ccorr, valid, mean=None, std=None, row_valid=None, no_nan=False):
+        self.no_nan = no_nan  # True: no NaN anywhere in X (every feature and every sample valid), known to the caller
         self.X = X
         self.T, self.S = int(X.shape[0]), int(X.shape[1])
         self.ldx = int(X.stride(0))
@@ -194,10 +195,11 @@ class CudaOps:
                 self.project_T(f, Yt[j0:], w, algo=algo, out=Z[:, j0:j0 + lpad(w)])
             return Z
         ws = self.workspace(f.T, f.S, l, algo)
+        flag = _lib.ALGO_FLAG_NO_NAN if (f.no_nan and f.row_valid is None) else 0
         check(self._timed("project_T" + self._algo_tag(algo), l, lambda: self.lib.xeofs_b200_project_T(
             ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr), ptr(f.row_valid), ptr(Yt),
             int(Yt.stride(0)), l,
-            ptr(Z), int(Z.stride(0)), ptr(ws), ws.numel(), algo, self._stream())), "project_T")
+            ptr(Z), int(Z.stride(0)), ptr(ws), ws.numel(), algo | flag, self._stream())), "project_T")
         self.launches += 2 + (2 if f.ccorr is not None else 0)
         return Z
 
@@ -389,6 +391,18 @@ class CudaOps:
                 and int(L.shape[0]) >= lpad(m)):
             return False
         return self.varimax_algo == "tc" or (S >= self.varimax_tc_min_S and m >= 8)
+
+    def varimax_update(self, G3, W, XtX, alpha, R, basis, dsum):
+        """The m x m step of a varimax iteration on the device (xeofs_b200_varimax_update): R and basis are updated in
+        place, the sum of the singular values lands in the one-element fp64 tensor ``dsum``.  No host round trip."""
+        m = int(R.shape[0])
+        need = int(self.lib.xeofs_b200_varimax_update_workspace_bytes(m))
+        if getattr(self, "_uws", None) is None or self._uws.numel() < need:
+            self._uws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        check(self.lib.xeofs_b200_varimax_update(ptr(G3), ptr(W), ptr(XtX), float(alpha), m, ptr(R), ptr(basis),
+                                                 ptr(dsum), ptr(self._uws), need, self._stream()), "varimax_update")
+        self.launches += 12
+        return dsum
 
     def varimax_accumulate(self, L, S, m, R, power=3.0, colscale=None, want_absmax=False, exact=False):
         """One sweep over the normalised loadings (linalg/_numpy/_rotation.py:166-170): Gout = Ln^T f(Ln R), W = colsum

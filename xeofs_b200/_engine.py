@@ -137,7 +137,8 @@ def fit_field(ops, X, featw=None, center=True, standardize=False, check_nans=Tru
     # centred: pivot == mean, the rank-1 term vanishes;  all-NaN samples are named to the kernels only when present
     ccorr = None if center else fin["ccorr"]
     row_valid = valid_sample.to(torch.uint8) if n_samples < T else None
-    ff.field = Field(X, fin["pivot"], fin["dscale"], ccorr, fin["valid"], fin["mean"], fin["std"], row_valid)
+    ff.field = Field(X, fin["pivot"], fin["dscale"], ccorr, fin["valid"], fin["mean"], fin["std"], row_valid,
+                     no_nan=(n_valid == S_global and n_samples == T))
     ff.mean, ff.std, ff.valid, ff.featw = fin["mean"], fin["std"], fin["valid"], featw
     ff.valid_sample, ff.n_samples, ff.n_features = valid_sample, n_samples, n_valid
     ff.total_variance = total_variance

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libxeofs_b200.so")
 
 ALGO_AUTO, ALGO_SIMT, ALGO_TF32X1, ALGO_TF32X3, ALGO_AUTO_FAST, ALGO_TF32X2, ALGO_TF32X1R = 0, 1, 2, 3, 4, 5, 6
 ALGO_NAMES = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tf32x1": ALGO_TF32X1, "tf32x3": ALGO_TF32X3, "tf32x2": ALGO_TF32X2, "tf32x1r": ALGO_TF32X1R}
+ALGO_FLAG_NO_NAN = 0x100
 F_CENTER, F_STANDARDIZE = 1, 2
 E_INVALID, E_CUDA, E_WORKSPACE, E_UNSUPPORTED = -1, -2, -3, -4
 
@@ -43,6 +44,8 @@ SIGNATURES = {
     "xeofs_b200_varimax_accumulate": (_int, [_p, _i64, _i64, _i64, _p, _p, C.c_double, _p, _p, _p, _p, _int, _p]),
     "xeofs_b200_varimax_workspace_bytes": (_i64, [_i64, _i64]),
     "xeofs_b200_varimax_sweep": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _int, _p, _i64, _p]),
+    "xeofs_b200_varimax_update_workspace_bytes": (_i64, [_i64]),
+    "xeofs_b200_varimax_update": (_int, [_p, _p, _p, C.c_double, _i64, _p, _p, _p, _p, _i64, _p]),
     "xeofs_b200_col_norms": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),
     "xeofs_b200_scaled_rows": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _p, _i64, _p]),
     "xeofs_b200_dgemm": (_int, [_int, _int, _i64, _i64, _i64, C.c_double, _p, _i64, _p, _i64, C.c_double, _p, _i64, _p]),

@@ -51,6 +51,8 @@ def _new_field(ops, comm, ff, X2, check_nans):
         valid_sample = row_nan < ff.S_global
         if not bool(valid_sample.all().item()):
             new.row_valid = valid_sample.to(torch.uint8)
+        else:
+            new.no_nan = ff.n_features == ff.S_global  # same NaN pattern as the fitted field: none at all
     return new, valid_sample
 
 

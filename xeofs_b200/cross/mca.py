@@ -86,7 +86,7 @@ class MCA:
             t1 = min(ff.T, t0 + 128)
             w = t1 - t0
             rv = None if f.row_valid is None else f.row_valid[t0:]
-            tail = Field(f.X[t0:], f.pivot, f.dscale, f.ccorr, f.valid, f.mean, f.std, rv)
+            tail = Field(f.X[t0:], f.pivot, f.dscale, f.ccorr, f.valid, f.mean, f.std, rv, no_nan=f.no_nan)
             blk = ops.scaled_rows(f, t0, t1)
             gi = ops.project_T(tail, blk, w, algo=algo)
             comm.sum_(gi)

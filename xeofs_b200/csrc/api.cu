@@ -39,7 +39,7 @@ int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo);
 int project_S_tc(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const uint8_t*,
                  const float*, int64_t, int64_t, float*, int64_t, void*, int64_t, int, cudaStream_t);
 int project_T_tc(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const uint8_t*,
-                 const float*, int64_t, int64_t, float*, int64_t, void*, int64_t, int, cudaStream_t);
+                 const float*, int64_t, int64_t, float*, int64_t, void*, int64_t, int, bool, cudaStream_t);
 
 int project_S_stats_tc(const float*, int64_t, int64_t, int64_t, const double*, int, const float*, int64_t, int64_t, float*,
                        float*, uint8_t*, float*, float*, float*, double*, int32_t*, float*, int64_t, void*, cudaStream_t);
@@ -89,6 +89,7 @@ extern "C" int xeofs_b200_round_tf32(float* M, int64_t rows, int64_t cols, int64
 }
 
 extern "C" int64_t xeofs_b200_project_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo) {
+  algo &= ~XEOFS_ALGO_FLAG_NO_NAN;
   int64_t simt = 2 * lpad(l) * (int64_t)sizeof(float) + 256;
   int64_t tc = tc_workspace_bytes(T, S, l, algo);
   return simt > tc ? simt : tc;
@@ -116,6 +117,7 @@ extern "C" int xeofs_b200_project_S(const float* X, int64_t T, int64_t S, int64_
                                     int64_t ldw, int64_t l, float* Yt, int64_t ldy, void* workspace, int64_t workspace_bytes, int algo,
                                     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  algo &= ~XEOFS_ALGO_FLAG_NO_NAN;  // (project_S tests for NaN only in stages that hold an all-NaN sample)
   int rc = check_project_args("project_S", X, T, S, ldx, pivot, dscale, W, Yt, ldw, ldy, l, workspace, workspace_bytes, algo);
   if (rc) return rc;
   XB_CHECK_ARG(ldw >= lpad(l) && ldy >= S, "project_S: ldw=%lld must be >= lp and ldy=%lld >= S", (long long)ldw, (long long)ldy);
@@ -134,6 +136,8 @@ extern "C" int xeofs_b200_project_T(const float* X, int64_t T, int64_t S, int64_
                                     int64_t ldy, int64_t l, float* Z, int64_t ldz, void* workspace, int64_t workspace_bytes, int algo,
                                     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const bool no_nan = (algo & XEOFS_ALGO_FLAG_NO_NAN) != 0;
+  algo &= ~XEOFS_ALGO_FLAG_NO_NAN;
   int rc = check_project_args("project_T", X, T, S, ldx, pivot, dscale, Yt, Z, ldy, ldz, l, workspace, workspace_bytes, algo);
   if (rc) return rc;
   XB_CHECK_ARG(ldz >= lpad(l) && ldy >= S, "project_T: ldz=%lld must be >= lp and ldy=%lld >= S", (long long)ldz, (long long)ldy);
@@ -144,7 +148,8 @@ extern "C" int xeofs_b200_project_T(const float* X, int64_t T, int64_t S, int64_
     set_error("project_T: tcgen05 path unavailable for this device/shape (need sm_100, ldx %% 4 == 0, 16-byte aligned X)");
     return XEOFS_E_UNSUPPORTED;
   }
-  return project_T_tc(X, T, S, ldx, pivot, dscale, ccorr, row_valid, Yt, ldy, l, Z, ldz, workspace, workspace_bytes, algo, stream);
+  return project_T_tc(X, T, S, ldx, pivot, dscale, ccorr, row_valid, Yt, ldy, l, Z, ldz, workspace, workspace_bytes, algo,
+                      no_nan, stream);
 }
 
 extern "C" int xeofs_b200_project_S_stats(const float* X, int64_t T, int64_t S, int64_t ldx, const double* featw, int flags,

@@ -274,3 +274,90 @@ extern "C" int xeofs_b200_sym_eig_wide(const double* G, int64_t n, double* evals
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ varimax: the m x m step
+// What follows the sweep over the loadings in one iteration of linalg/_numpy/_rotation.py:166-177, on the device and
+// without a host round trip:  G = G3 - alpha (XtX R) diag(W);  U, svals, V^T = svd(G);  R <- U V^T;  delta = sum(svals),
+// through the eigen-decomposition of G^T G taken in the eigenbasis of the previous iteration (where the matrix is
+// nearly diagonal already: the Jacobi sweeps of sym_eig end after two or three).
+namespace xb {
+__global__ void vu_form_G_kernel(const double* __restrict__ G3, const double* __restrict__ T1, const double* __restrict__ W,
+                                 double alpha, int m, double* __restrict__ G) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < m * m) G[idx] = G3[idx] - alpha * T1[idx] * W[idx % m];
+}
+// P = V diag(1 / sqrt(ev)),  delta = sum sqrt(ev)   (one block)
+__global__ void __launch_bounds__(256)
+vu_scale_kernel(const double* __restrict__ V, const double* __restrict__ ev, int m, double* __restrict__ P,
+                double* __restrict__ dsum) {
+  __shared__ double inv[128];
+  __shared__ double part[8];
+  const int tid = threadIdx.x;
+  double s = 0.0;
+  if (tid < m) {
+    const double sv = sqrt(fmax(ev[tid], 0.0));
+    inv[tid] = sv > 0.0 ? 1.0 / sv : 0.0;
+    s = sv;
+  }
+  s = warp_sum(s);
+  if ((tid & 31) == 0) part[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += part[i];
+    *dsum = t;
+  }
+  for (int idx = tid; idx < m * m; idx += 256) P[idx] = V[idx] * inv[idx % m];
+}
+template <bool TA, bool TB>
+static void dgemm_sq(int m, const double* A, const double* B, double* C, cudaStream_t stream) {
+  dim3 grid((unsigned)ceil_div(m, DG_T), (unsigned)ceil_div(m, DG_T));
+  dgemm_kernel<TA, TB><<<grid, 256, 0, stream>>>(m, m, m, 1.0, A, m, B, m, 0.0, C, m);
+}
+}  // namespace xb
+
+extern "C" int xeofs_b200_sym_eig(const double* G, int64_t l, double* evals, double* evecs, double* work, int32_t* info,
+                                  void* stream);
+
+extern "C" int64_t xeofs_b200_varimax_update_workspace_bytes(int64_t m) {
+  return (9 * m * m + m + (m + 2) * (m + 2) + 16) * (int64_t)sizeof(double);
+}
+
+extern "C" int xeofs_b200_varimax_update(const double* G3, const double* W, const double* XtX, double alpha, int64_t m,
+                                         double* R, double* basis, double* dsum, void* workspace,
+                                         int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(G3 && W && XtX && R && basis && dsum && workspace && m >= 2 && m <= 128,
+               "varimax_update: bad arguments (m=%lld must be in 2..128)", (long long)m);
+  XB_CHECK_ARG(workspace_bytes >= xeofs_b200_varimax_update_workspace_bytes(m), "varimax_update: workspace too small");
+  const int mi = (int)m;
+  const int64_t mm = m * m;
+  double* T1 = (double*)workspace;
+  double* G = T1 + mm;
+  double* M = G + mm;
+  double* T2 = M + mm;
+  double* Mp = T2 + mm;
+  double* Vp = Mp + mm;
+  double* V = Vp + mm;
+  double* P = V + mm;
+  double* T3 = P + mm;
+  double* ev = T3 + mm;
+  double* ework = ev + m;
+  int32_t* info = (int32_t*)(ework + (m + 2) * (m + 2));
+  const unsigned eb = (unsigned)ceil_div(mm, 256);
+  dgemm_sq<false, false>(mi, XtX, R, T1, stream);                       // XtX R
+  vu_form_G_kernel<<<eb, 256, 0, stream>>>(G3, T1, W, alpha, mi, G);    // G
+  dgemm_sq<true, false>(mi, G, G, M, stream);                           // G^T G
+  dgemm_sq<false, false>(mi, M, basis, T2, stream);                     // (G^T G) basis
+  dgemm_sq<true, false>(mi, basis, T2, Mp, stream);                     // basis^T (G^T G) basis
+  XB_LAUNCH_CHECK();
+  int rc = xeofs_b200_sym_eig(Mp, m, ev, Vp, ework, info, stream_);
+  if (rc) return rc;
+  dgemm_sq<false, false>(mi, basis, Vp, V, stream);                     // eigenvectors of G^T G
+  vu_scale_kernel<<<1, 256, 0, stream>>>(V, ev, mi, P, dsum);           // V diag(1/svals), delta
+  dgemm_sq<false, false>(mi, G, P, T3, stream);                         // G V diag(1/svals)  (= U)
+  dgemm_sq<false, true>(mi, T3, V, R, stream);                          // R = U V^T
+  XB_CUDA(cudaMemcpyAsync(basis, V, (size_t)mm * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}

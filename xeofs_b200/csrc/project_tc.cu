@@ -74,6 +74,7 @@ struct TcParams {
   int64_t ldx;
   const float* bimg_hi; // small operand as a sequence of shared-memory images, one per 32-wide K slab:
   const float* bimg_lo; //   [slab][lp rows][32 k], 16-byte chunks XOR-swizzled by (row & 7)  (lo: 3xTF32 only)
+  int b_bulk;           // fetch the operand image of a stage with one bulk copy (else: tensor-map rows of 1 KB)
 };
 
 
@@ -88,7 +89,12 @@ struct TcParams {
 // (profiles/r01_mma_issue_probe.txt): two instructions per K step instead of three.  The accumulator is then 2 lp
 // columns wide, so there is one buffer (not two taking turns): the issuer waits while the epilogue warps move it into
 // registers, every TC_FLUSH_PK slabs.
-template <int NS, bool SIDE_T, int KB, bool STATS = false, bool RN = false, bool PK = false>
+// TFAST (project_T): the caller vouches that the field holds no NaN (every feature and every sample valid), so the
+// operand stage skips its per-value test.  The operand warps of project_T are issue-bound (measured: three extra
+// integer instructions per value cost 40 % of a pass): every instruction taken out of their loop counts.  For the
+// same reason dscale is folded into the small operand's image (tile_Y_kernel) unless that operand has to stay
+// TF32-exact (NS == 2).
+template <int NS, bool SIDE_T, int KB, bool STATS = false, bool RN = false, bool PK = false, bool TFAST = false>
 __global__ void __launch_bounds__(tc_threads(tc_wide(NS, SIDE_T, RN)), (NS == 1 && !SIDE_T && !RN) ? 2 : 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBhi,
                   const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
@@ -169,9 +175,19 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           tma_load_2d(xs + (size_t)st * XB, &mapX, k0, tile0i, &full[st], HINT_EVICT_FIRST);
           bulk_load_1d(pd + st * KB * 256, p.pivot + 2 * k0, KB * 256, &full[st]);
         }
-        // packed: the image of a slab is [hi rows | lo rows], one box brings both for all KB slabs of the stage
-        tma_load_2d(b, &mapBhi, 0, PK ? 2 * brow : brow, &full[st], HINT_EVICT_LAST);
-        if (NS == 3 && !PK) tma_load_2d(b + (size_t)KB * bbytes, &mapBlo, 0, brow, &full[st], HINT_EVICT_LAST);
+        // the images of consecutive slabs are contiguous in global memory: one bulk copy brings the stage's operand
+        // (packed: [hi rows | lo rows] per slab, one copy for both parts) instead of lp/8 tensor-map rows of 1 KB —
+        // the TMA engine's cost is per piece
+        const size_t slab0 = (size_t)(chunk0 + c) * KB;
+        if (p.b_bulk) {
+          bulk_load_1d_hint(b, p.bimg_hi + slab0 * (PK ? 2 : 1) * lp * TC_KC, (PK ? 2 : 1) * KB * bbytes, &full[st],
+                            HINT_EVICT_LAST);
+          if (NS == 3 && !PK)
+            bulk_load_1d_hint(b + (size_t)KB * bbytes, p.bimg_lo + slab0 * lp * TC_KC, KB * bbytes, &full[st], HINT_EVICT_LAST);
+        } else {
+          tma_load_2d(b, &mapBhi, 0, PK ? 2 * brow : brow, &full[st], HINT_EVICT_LAST);
+          if (NS == 3 && !PK) tma_load_2d(b + (size_t)KB * bbytes, &mapBlo, 0, brow, &full[st], HINT_EVICT_LAST);
+        }
       }
       __syncwarp();
     }
@@ -364,17 +380,20 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           // features; beyond the last feature dscale is 0 and the small operand too)
           const uint32_t src = xs_u32 + st * XB + row * XPITCH + kb * 128;
           const uint32_t pv = pd_u32 + st * KB * 256 + kb * 256;
+          constexpr bool FOLD = NS != 2;  // dscale lives in the small operand's image
 #pragma unroll
           for (int cc = 0; cc < KW / 4; ++cc) {
             const int ch = part * (KW / 4) + cc;
             const float4 x = lds128(src + ch * 16);
             const float4 pq = lds128(pv + ch * 16);
-            const float4 dq = lds128(pv + 128 + ch * 16);
+            float4 dq = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (!FOLD) dq = lds128(pv + 128 + ch * 16);
             const float xa[4] = {x.x, x.y, x.z, x.w}, pa[4] = {pq.x, pq.y, pq.z, pq.w}, da[4] = {dq.x, dq.y, dq.z, dq.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float v = xa[e] - pa[e];
-              v = (fabsf(v) <= 3.4028234e38f) ? v * da[e] : 0.f;
+              if (!FOLD) v *= da[e];
+              if (!TFAST) v = (fabsf(v) <= 3.4028234e38f) ? v : 0.f;
               if (NS >= 2) {
                 hi[cc * 4 + e] = __float_as_uint(v) & 0xffffe000u;
                 lo[cc * 4 + e] = __float_as_uint(v - __uint_as_float(hi[cc * 4 + e]));
@@ -545,14 +564,16 @@ __global__ void chunk_flags_kernel(const uint8_t* __restrict__ row_valid, int64_
 // Yt (lp x ldy, space-side) -> images of its K slabs (K = s), zero beyond S.  One block per slab.
 __global__ void __launch_bounds__(256)
 tile_Y_kernel(const float* __restrict__ Yt, int64_t S, int64_t ldy, int lp, float* __restrict__ Yhi, float* __restrict__ Ylo,
-              int rn = 0, int slab_floats = 0) {
+              int rn = 0, int slab_floats = 0, const float* __restrict__ dscale = nullptr) {
   const int64_t s0 = (int64_t)blockIdx.x * 32;
   const size_t ss = slab_floats ? (size_t)slab_floats : (size_t)lp * 32;
   float* hi = Yhi + (size_t)blockIdx.x * ss;
   float* lo = Ylo ? Ylo + (size_t)blockIdx.x * ss : nullptr;
   const int kk = threadIdx.x & 31;
   for (int j = threadIdx.x >> 5; j < lp; j += 8) {
-    const float v = (s0 + kk < S) ? Yt[(int64_t)j * ldy + s0 + kk] : 0.f;
+    // dscale (the Scaler's per-feature factor, 0 for dropped features) rides on the small operand where given
+    const float ds = (dscale && s0 + kk < S) ? dscale[s0 + kk] : 1.f;
+    const float v = (s0 + kk < S) ? Yt[(int64_t)j * ldy + s0 + kk] * ds : 0.f;
     if (lo) {
       const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
       hi[img_offset(j, kk)] = h;
@@ -736,13 +757,25 @@ int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo) {
   return (bs > bt ? bs : bt) + 256;
 }
 
-template <int NS, bool SIDE_T, int KB, bool RN = false, bool PK = false>
+template <int NS, bool SIDE_T, int KB, bool RN = false, bool PK = false, bool TFAST = false>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p, dim3 grid,
                      size_t smem, cudaStream_t stream) {
-  XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<NS, SIDE_T, KB, false, RN, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  project_tc_kernel<NS, SIDE_T, KB, false, RN, PK><<<grid, tc_threads(tc_wide(NS, SIDE_T, RN)), smem, stream>>>(mx, mh, ml, p);
+  XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<NS, SIDE_T, KB, false, RN, PK, TFAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  project_tc_kernel<NS, SIDE_T, KB, false, RN, PK, TFAST><<<grid, tc_threads(tc_wide(NS, SIDE_T, RN)), smem, stream>>>(mx, mh, ml, p);
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
+}
+// project_T: pick the instantiation for (KB, no-NaN promise)
+template <int NS, bool RN, bool PK>
+static int launch_T(int kb, bool fast, const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p,
+                    dim3 grid, size_t smem, cudaStream_t stream) {
+  if (fast)
+    return kb == 1   ? launch_tc<NS, true, 1, RN, PK, true>(mx, mh, ml, p, grid, smem, stream)
+           : kb == 2 ? launch_tc<NS, true, 2, RN, PK, true>(mx, mh, ml, p, grid, smem, stream)
+                     : launch_tc<NS, true, 4, RN, PK, true>(mx, mh, ml, p, grid, smem, stream);
+  return kb == 1   ? launch_tc<NS, true, 1, RN, PK, false>(mx, mh, ml, p, grid, smem, stream)
+         : kb == 2 ? launch_tc<NS, true, 2, RN, PK, false>(mx, mh, ml, p, grid, smem, stream)
+                   : launch_tc<NS, true, 4, RN, PK, false>(mx, mh, ml, p, grid, smem, stream);
 }
 
 int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot, const float* dscale,
@@ -792,6 +825,7 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   p.pivot = pivot; p.dscale = dscale; p.ccorr = ccorr; p.wsum = wsum;
   p.out = Yt; p.ldo = ldy;
   p.X = X; p.ldx = ldx; p.bimg_hi = Whi; p.bimg_lo = Wlo;
+  p.b_bulk = env_int("XEOFS_TC_BBULK", 1);
   p.chunk_flags = row_valid ? flags : nullptr;
   dim3 grid((unsigned)ceil_div(S, TC_TILE));
   return ns == 3 && pk  ? launch_tc<3, false, 1, false, true>(mx, mh, ml, p, grid, sh.smem, stream)
@@ -850,6 +884,7 @@ int project_S_stats_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const 
   p.wsum = wsum;
   p.out = Yt; p.ldo = ldy;
   p.X = X; p.ldx = ldx; p.bimg_hi = Whi;
+  p.b_bulk = env_int("XEOFS_TC_BBULK", 1);
   p.featw = featw; p.stat_flags = flags;
   p.mean_out = mean; p.std_out = stdv; p.valid_out = valid; p.pivot_out = pivot; p.dscale_out = dscale; p.ccorr_out = ccorr;
   p.scalars_out = scalars; p.row_delta = row_delta; p.base_nan = base_nan;
@@ -864,7 +899,7 @@ int project_S_stats_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const 
 
 int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot, const float* dscale,
                  const float* ccorr, const uint8_t* row_valid, const float* Yt, int64_t ldy, int64_t l, float* Z,
-                 int64_t ldz, void* workspace, int64_t workspace_bytes, int algo, cudaStream_t stream) {
+                 int64_t ldz, void* workspace, int64_t workspace_bytes, int algo, bool no_nan, cudaStream_t stream) {
   (void)workspace_bytes;
   const int lp = (int)lpad(l);
   const int ns = algo_ns(algo);
@@ -883,7 +918,7 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   pad_vectors_kernel<<<(unsigned)ceil_div(g.Spad, 256), 256, 0, stream>>>(pivot, dscale, S, g.Spad, pdpad);
   XB_LAUNCH_CHECK();
   tile_Y_kernel<<<(unsigned)(g.Spad / TC_KC), 256, 0, stream>>>(Yt, S, ldy, lp, Yhi, Ylo, algo_rn(algo) ? 1 : 0,
-                                                                pk ? 2 * lp * 32 : 0);
+                                                                pk ? 2 * lp * 32 : 0, ns != 2 ? dscale : nullptr);
   XB_LAUNCH_CHECK();
   int rc;
   if (ccorr) {
@@ -898,6 +933,7 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   p.pivot = pdpad; p.dscale = nullptr; p.ccorr = nullptr; p.wsum = nullptr;
   p.out = part; p.ldo = lp;
   p.X = X; p.ldx = ldx; p.bimg_hi = Yhi; p.bimg_lo = Ylo;
+  p.b_bulk = env_int("XEOFS_TC_BBULK", 1);
   dim3 grid((unsigned)g.t_tiles, (unsigned)g.splits);
   CUtensorMap mx, mh, ml;
   // rows of X in pieces of KB*32 + 4 floats (the 4 extra only give the shared-memory rows their odd pitch)
@@ -911,19 +947,12 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
     rc = make_map2(&ml, Ylo, 256, (g.Spad / TC_KC) * (lp / 8), 256, 256, kb * lp / 8, false);
     if (rc) return rc;
   }
-#define XB_T_LAUNCH(NSV, KBV) launch_tc<NSV, true, KBV>(mx, mh, ml, p, grid, sh.smem, stream)
-  if (ns == 3 && pk)
-    rc = kb == 1   ? launch_tc<3, true, 1, false, true>(mx, mh, ml, p, grid, sh.smem, stream)
-         : kb == 2 ? launch_tc<3, true, 2, false, true>(mx, mh, ml, p, grid, sh.smem, stream)
-                   : launch_tc<3, true, 4, false, true>(mx, mh, ml, p, grid, sh.smem, stream);
-  else if (ns == 3) rc = kb == 1 ? XB_T_LAUNCH(3, 1) : kb == 2 ? XB_T_LAUNCH(3, 2) : XB_T_LAUNCH(3, 4);
-  else if (ns == 2) rc = kb == 1 ? XB_T_LAUNCH(2, 1) : kb == 2 ? XB_T_LAUNCH(2, 2) : XB_T_LAUNCH(2, 4);
-  else if (algo_rn(algo))
-    rc = kb == 1   ? launch_tc<1, true, 1, true>(mx, mh, ml, p, grid, sh.smem, stream)
-         : kb == 2 ? launch_tc<1, true, 2, true>(mx, mh, ml, p, grid, sh.smem, stream)
-                   : launch_tc<1, true, 4, true>(mx, mh, ml, p, grid, sh.smem, stream);
-  else rc = kb == 1 ? XB_T_LAUNCH(1, 1) : kb == 2 ? XB_T_LAUNCH(1, 2) : XB_T_LAUNCH(1, 4);
-#undef XB_T_LAUNCH
+  const bool fast = no_nan && !row_valid;
+  if (ns == 3 && pk) rc = launch_T<3, false, true>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
+  else if (ns == 3) rc = launch_T<3, false, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
+  else if (ns == 2) rc = launch_T<2, false, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
+  else if (algo_rn(algo)) rc = launch_T<1, true, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
+  else rc = launch_T<1, false, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
   if (rc) return rc;
   reduce_partials_kernel<<<(unsigned)ceil_div(T * lp, 256), 256, 0, stream>>>(part, g.splits, g.rows_pad, lp, T,
                                                                               ccorr ? rvec : nullptr, row_valid, Z, ldz);

@@ -504,7 +504,7 @@ extern "C" int xeofs_b200_gram(const float* M, int64_t n, int64_t l, int64_t ld,
   else gram_kernel<TI, NT, KG, 1><<<blocks, 256, 0, stream>>>(M, n, (int)l, ld, G)
   if (l <= 16) { XB_GRAM(2, 8, 4); }
   else if (l <= 32) { XB_GRAM(4, 8, 4); }
-  else if (l <= 64) { XB_GRAM(8, 8, 7); }
+  else if (l <= 64) { XB_GRAM(4, 16, 1); }
   else { XB_GRAM(8, 16, 1); }
 #undef XB_GRAM
   XB_LAUNCH_CHECK();

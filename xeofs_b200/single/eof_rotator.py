@@ -17,7 +17,7 @@ from .. import _labels as L
 
 
 TC_WINDOW = 8  # iterations the stopping test of the tensor-core phase of the varimax iteration looks back
-TC_SYNC = 4    # tensor-core iterations between two reads of delta on the host
+TC_SYNC = 8    # tensor-core iterations between two reads of delta on the host
 
 
 class EOFRotator:
@@ -30,23 +30,13 @@ class EOFRotator:
         self.n_iter_ = 0
 
     # ------------------------------------------------------------------ rotation of a space-side loadings block
-    @staticmethod
-    def _polar(ops, G, basis=None):
-        """U V^T and sum(svals) of svd(G) through eig(G^T G) (fp64, m x m).  ``basis``: eigenvectors of the previous
-        iteration's G^T G — in that basis the matrix is nearly diagonal already and the Jacobi sweeps of sym_eig end
-        after two or three instead of ten.  Returns (polar factor, sum(svals), eigenvectors)."""
-        M = G.t() @ G
-        if basis is not None:
-            M = basis.t() @ M @ basis
-        ev, V = ops.sym_eig(M.contiguous())
-        if basis is not None:
-            V = basis @ V
-        sv = torch.sqrt(torch.clamp(ev, min=0.0))
-        inv = torch.where(sv > 0, 1.0 / sv, torch.zeros_like(sv))
-        return G @ (V * inv[None, :]) @ V.t(), sv.sum(), V
-
     def _rotate(self, ops, comm, L0, S_local, n_rows, m):
-        """promax(loadings) of linalg/_numpy/_rotation.py:6-92.  Returns R_total (m x m fp64), phi, iterations."""
+        """promax(loadings) of linalg/_numpy/_rotation.py:6-92.  Returns R_total (m x m fp64), phi, iterations.
+
+        One iteration = one sweep over the loadings (``varimax_accumulate``: Ln^H B^3 and W) + the m x m step
+        (``varimax_update``: G, its polar factor R = U V^T and delta = sum(svals), all on the device).  Nothing comes
+        back to the host inside an iteration: delta is appended to a device array that is read every TC_SYNC iterations
+        during the tensor-core phase."""
         p = self._params
         if m < 2:
             raise ValueError(f"Cannot rotate {m} modes (columns), but must be 2 or more.")
@@ -54,47 +44,60 @@ class EOFRotator:
         XtX = ops.gram(Ln, S_local, m, 1)
         comm.sum_(XtX)
         R = torch.eye(m, dtype=torch.float64, device=ops.device)
+        basis = torch.eye(m, dtype=torch.float64, device=ops.device)
         alpha = 1.0 / n_rows  # gamma = 1 (varimax)
+        max_iter, rtol, test = int(p["max_iter"]), p["rtol"], bool(p["compute"])
+        hist_dev = torch.zeros(max_iter, dtype=torch.float64, device=ops.device)
         # The reference stops when sum(svals) changes by less than rtol (1e-8) between two iterations — a test that only
         # fp64 sweeps can decide.  The tcgen05 sweep (fp32-level noise in delta, ~20x faster) therefore does the bulk
         # of the iterations with the same test taken over a window of TC_WINDOW iterations (the noise of the windowed
         # mean change is 2/TC_WINDOW of the noise of delta); the fp64 sweep then takes over until the reference's own
-        # test holds, so the iteration ends where the reference's ends.
+        # test holds, so the iteration ends where the reference's ends.  compute=False: no test at all, max_iter
+        # iterations (_rotation.py:176-180), the last two in fp64.
         tc = getattr(ops, "_varimax_tc_applies", None)
-        use_tc = bool(tc and p["rtol"] >= 1e-9 and tc(Ln, S_local, m, False))
-        hist, basis, pending = [], None, []
-        d, d_old, converged, it = 0.0, None, False, 0
+        use_tc = bool(tc and rtol >= 1e-9 and tc(Ln, S_local, m, False))
+        hist, read, d, d_old, converged, it = [], 0, None, None, False, 0
         self.n_iter_tc_ = 0
-        for it in range(1, p["max_iter"] + 1):
+        for it in range(1, max_iter + 1):
+            if use_tc and not test and it > max_iter - 2:
+                use_tc, self.n_iter_tc_ = False, it - 1
             G3, W, _ = ops.varimax_accumulate(Ln, S_local, m, R, exact=not use_tc)
             comm.sum_(G3)
             comm.sum_(W)
-            G = G3 - alpha * (XtX @ R) * W[None, :]
-            R, dsum, basis = self._polar(ops, G, basis)
+            ops.varimax_update(G3, W, XtX, alpha, R, basis, hist_dev[it - 1:it])
             if use_tc:
-                # delta is read back only every TC_SYNC iterations (one host sync instead of four: the host keeps
-                # enqueueing while the device works); stopping up to TC_SYNC - 1 sweeps late is harmless here, the
-                # fp64 phase decides where the iteration ends
-                pending.append(dsum)
-                if len(pending) < TC_SYNC and it < p["max_iter"]:
+                if not test or (it - read < TC_SYNC and it < max_iter):
                     continue
-                vals = torch.stack(pending).cpu().tolist()
-                pending = []
+                vals = hist_dev[read:it].cpu().tolist()  # one host sync per TC_SYNC iterations
+                read = it
                 for v in vals:
                     hist.append(v)
                     w = min(TC_WINDOW, len(hist) - 1)
-                    if w >= 1 and abs(v - hist[-1 - w]) / (w * v) < p["rtol"]:
+                    if w >= 1 and abs(v - hist[-1 - w]) / (w * v) < rtol:
                         use_tc = False  # the next fp64 sweep has no fp64 predecessor to compare with
                         self.n_iter_tc_ = it
                         break
-                d = None if not use_tc else vals[-1]
+                d = None
                 continue
-            d_old, d = d, float(dsum.item())
-            if p["compute"] and d_old is not None and abs(d - d_old) / d < p["rtol"]:
+            if not test:
+                continue
+            d_old, d = d, float(hist_dev[it - 1].item())
+            if d_old is not None and abs(d - d_old) / d < rtol:
                 converged = True
                 break
-        # compute=False: the reference runs all max_iter iterations without a test and never raises (_rotation.py:176-180)
-        if p["compute"] and not converged:
+        if test and not converged and not use_tc and self.n_iter_tc_ >= max_iter - 2:
+            # the windowed test of the tensor-core phase passed within the last iterations allowed: let the fp64 sweeps
+            # that confirm it (normally two) run before the verdict
+            for _ in range(3):
+                G3, W, _ = ops.varimax_accumulate(Ln, S_local, m, R, exact=True)
+                comm.sum_(G3)
+                comm.sum_(W)
+                ops.varimax_update(G3, W, XtX, alpha, R, basis, hist_dev[0:1])
+                d_old, d = d, float(hist_dev[0].item())
+                if d_old is not None and abs(d - d_old) / d < rtol:
+                    converged = True
+                    break
+        if test and not converged:
             raise RuntimeError("Rotation process did not converge.")  # _rotation.py:179-180
         self.n_iter_ = it
         eye = torch.eye(m, dtype=torch.float64, device=ops.device)
