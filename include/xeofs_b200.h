@@ -51,6 +51,8 @@ extern "C" {
 /* OR-ed into `algo` of project_T: the caller vouches that the field holds no NaN / Inf at all (every feature and every
  * sample valid, row_valid NULL), so the tensor-core operand stage skips its per-value test.                          */
 #define XEOFS_ALGO_FLAG_NO_NAN 0x100
+#define XEOFS_ALGO_TF32X1F 7 /* as TF32X1R for a field that is ALREADY a TF32-rounded copy of the preprocessed matrix
+                               (xeofs_b200_materialize with round_tf32, pivot 0, dscale 1): no rounding, no test  */
 #define XEOFS_ALGO_TF32X1R 6 /* TF32X1 with both operands rounded to TF32 to nearest (unbiased sums; else as TF32X1) */
 
 /* flags for xeofs_b200_scaling_finalize */
@@ -211,6 +213,14 @@ int xeofs_b200_gram_wide(const float* M, int64_t n, int64_t l, int64_t ld, int s
 int64_t xeofs_b200_sym_eig_wide_workspace_bytes(int64_t n);
 int xeofs_b200_sym_eig_wide(const double* G, int64_t n, double* evals, double* evecs, void* workspace,
                             int64_t workspace_bytes, int32_t* info, int max_sweeps, void* stream);
+
+/* The preprocessed matrix itself, A[t,s] = (X[t,s] - pivot[s]) dscale[s] + ccorr[s] (NaN -> 0, all-NaN samples zero),
+ * written out as a T x S fp32 matrix with `rows_out` >= T rows (the extra rows zero) — for the sample Gram matrices
+ * behind the total squared covariance (cross/cpcca.py:991-1000), which stream the field ~T/256 times: one rounded copy
+ * lets those passes run as plain moves (XEOFS_ALGO_TF32X1F).  round_tf32 != 0: values rounded to TF32, ties to even. */
+int xeofs_b200_materialize(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot, const float* dscale,
+                           const float* ccorr, const uint8_t* row_valid, int64_t rows_out, int round_tf32, float* out,
+                           int64_t ldo, void* stream);
 
 #ifdef __cplusplus
 }

@@ -360,6 +360,26 @@ class CudaOps:
         self.launches += 1
         return out
 
+    def materialize(self, f: Field, round_tf32=True, row_multiple=128):
+        """The preprocessed matrix of a field written out once (rows padded with zeros to a multiple of
+        ``row_multiple``), optionally rounded to TF32: what the sample Gram matrices of MCA's total squared covariance
+        stream ~T/256 times.  Returns a Field over the copy (pivot 0, dscale 1) or None when it does not apply
+        (no tensor-core path, or not enough free memory for the copy)."""
+        if not bool(self.lib.xeofs_b200_has_tcgen05()) or self.accurate_algo == _lib.ALGO_SIMT:
+            return None
+        rows = (f.T + row_multiple - 1) // row_multiple * row_multiple
+        pitch = (f.S + 31) // 32 * 32
+        free, _ = torch.cuda.mem_get_info(self.device)
+        if rows * pitch * 4 + (2 << 30) > free + torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device):
+            return None
+        out = torch.empty((rows, pitch), dtype=torch.float32, device=self.device)
+        check(self.lib.xeofs_b200_materialize(ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr),
+                                              ptr(f.row_valid), rows, int(round_tf32), ptr(out), pitch,
+                                              self._stream()), "materialize")
+        self.launches += 1
+        zero, one = self._unit_vectors(f.S)
+        return Field(out[:, :f.S], zero, one, None, None, no_nan=True)
+
     def scaled_rows(self, f: Field, t0, t1):
         """Rows t0:t1 of the preprocessed matrix as a space-side block (pad rows zero)."""
         w = int(t1 - t0)

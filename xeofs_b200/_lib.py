@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libxeofs_b200.so")
 
-ALGO_AUTO, ALGO_SIMT, ALGO_TF32X1, ALGO_TF32X3, ALGO_AUTO_FAST, ALGO_TF32X2, ALGO_TF32X1R = 0, 1, 2, 3, 4, 5, 6
+ALGO_AUTO, ALGO_SIMT, ALGO_TF32X1, ALGO_TF32X3, ALGO_AUTO_FAST, ALGO_TF32X2, ALGO_TF32X1R, ALGO_TF32X1F = 0, 1, 2, 3, 4, 5, 6, 7
 ALGO_NAMES = {"auto": ALGO_AUTO, "simt": ALGO_SIMT, "tf32x1": ALGO_TF32X1, "tf32x3": ALGO_TF32X3, "tf32x2": ALGO_TF32X2, "tf32x1r": ALGO_TF32X1R}
 ALGO_FLAG_NO_NAN = 0x100
 F_CENTER, F_STANDARDIZE = 1, 2
@@ -52,6 +52,7 @@ SIGNATURES = {
     "xeofs_b200_gram_wide": (_int, [_p, _i64, _i64, _i64, _int, _p, _p]),
     "xeofs_b200_sym_eig_wide_workspace_bytes": (_i64, [_i64]),
     "xeofs_b200_sym_eig_wide": (_int, [_p, _i64, _p, _p, _p, _i64, _p, _int, _p]),
+    "xeofs_b200_materialize": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _int, _p, _i64, _p]),
     "xeofs_b200_reconstruct": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, _p]),
 }
 

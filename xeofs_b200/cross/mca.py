@@ -75,13 +75,25 @@ class MCA:
         return self
 
     # ------------------------------------------------------------------ PCA stage (preprocessing/pca.py:94-131)
-    def _gram_block_columns(self, ff, algo):
+    def _gram_block_columns(self, ff, algo, rounded=None):
         """Block columns G[t0:, t0:t1] (t1 - t0 <= 128) of the sample Gram matrix A A^T of a fitted field, as
         ((t0, t1), (T - t0) x (t1 - t0) fp32 device block).  The matrix is symmetric: only the samples t >= t0 are
-        streamed for the block starting at t0."""
+        streamed for the block starting at t0.  ``rounded``: a materialised TF32-rounded copy of the preprocessed
+        matrix (ops.materialize) — its rows are both operands, moved as they are (XEOFS_ALGO_TF32X1F)."""
         from .._cuda_ops import Field
+        from .. import _lib
         ops, comm = self.ops, self.comm
         f = ff.field
+        if rounded is not None:
+            A = rounded.X  # (rows padded to 128) x S view of the copy
+            for t0 in range(0, ff.T, 128):
+                t1 = min(ff.T, t0 + 128)
+                w = t1 - t0
+                tail = Field(A[t0:ff.T], rounded.pivot, rounded.dscale, None, None, no_nan=True)
+                gi = ops.project_T(tail, A[t0:t0 + 128], w, algo=_lib.ALGO_TF32X1F)
+                comm.sum_(gi)
+                yield (t0, t1), gi[:, :w]
+            return
         for t0 in range(0, ff.T, 128):
             t1 = min(ff.T, t0 + 128)
             w = t1 - t0
@@ -355,8 +367,16 @@ class MCA:
         # (operands rounded to nearest, 2e-4 per term) averages out below 1e-6; smaller fields take the 3xTF32 product
         S_all = min(self._f1.S_global, self._f2.S_global)
         algo = getattr(ops, "sum_algo", ops.accurate_algo) if S_all >= 65536 else ops.accurate_algo
-        for ((t0, t1), g1), (_, g2) in zip(self._gram_block_columns(self._f1, algo),
-                                           self._gram_block_columns(self._f2, algo)):
+        # wide fields: one TF32-rounded copy of each preprocessed matrix, then every Gram block is a plain streaming
+        # product of its rows (the field is read ~T/256 times: the copy pays for itself after the second block)
+        r1 = r2 = None
+        if S_all >= 65536 and hasattr(ops, "materialize") and algo == getattr(ops, "sum_algo", None):
+            r1 = ops.materialize(self._f1.field)
+            r2 = ops.materialize(self._f2.field) if r1 is not None else None
+            if r2 is None:
+                r1 = None
+        for ((t0, t1), g1), (_, g2) in zip(self._gram_block_columns(self._f1, algo, r1),
+                                           self._gram_block_columns(self._f2, algo, r2)):
             w = t1 - t0
             prod = g1.double() * g2.double()
             acc += prod[:w].sum() + 2.0 * prod[w:].sum()

@@ -58,7 +58,7 @@ extern "C" int xeofs_b200_has_tcgen05(void) {
 }
 
 static int resolve_algo(int algo, int64_t T, int64_t S, int64_t ldx, const float* X, int64_t l) {
-  if ((algo == XEOFS_ALGO_TF32X2 || algo == XEOFS_ALGO_TF32X1R) && !(xeofs_b200_has_tcgen05() && tc_supported(T, S, ldx, X, l)))
+  if ((algo == XEOFS_ALGO_TF32X2 || algo == XEOFS_ALGO_TF32X1R || algo == XEOFS_ALGO_TF32X1F) && !(xeofs_b200_has_tcgen05() && tc_supported(T, S, ldx, X, l)))
     return XEOFS_ALGO_SIMT;
   if (algo == XEOFS_ALGO_AUTO || algo == XEOFS_ALGO_AUTO_FAST) {
     const bool tc = xeofs_b200_has_tcgen05() && tc_supported(T, S, ldx, X, l);
@@ -103,7 +103,7 @@ static int check_project_args(const char* who, const float* X, int64_t T, int64_
   XB_CHECK_ARG(l > 0 && l <= 128, "%s: l=%lld must be in 1..128", who, (long long)l);
   XB_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0, "%s: leading dimensions of the small matrices must be multiples of 4", who);
   XB_CHECK_ARG(((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)ws % 256 == 0), "%s: misaligned buffer", who);
-  XB_CHECK_ARG(algo >= XEOFS_ALGO_AUTO && algo <= XEOFS_ALGO_TF32X1R, "%s: unknown algo %d", who, algo);
+  XB_CHECK_ARG(algo >= XEOFS_ALGO_AUTO && algo <= XEOFS_ALGO_TF32X1F, "%s: unknown algo %d", who, algo);
   if (ws_bytes < xeofs_b200_project_workspace_bytes(T, S, l, algo)) {
     set_error("%s: workspace too small (%lld < %lld bytes)", who, (long long)ws_bytes,
               (long long)xeofs_b200_project_workspace_bytes(T, S, l, algo));

@@ -94,8 +94,10 @@ struct TcParams {
 // integer instructions per value cost 40 % of a pass): every instruction taken out of their loop counts.  For the
 // same reason dscale is folded into the small operand's image (tile_Y_kernel) unless that operand has to stay
 // TF32-exact (NS == 2).
-template <int NS, bool SIDE_T, int KB, bool STATS = false, bool RN = false, bool PK = false, bool TFAST = false>
-__global__ void __launch_bounds__(tc_threads(tc_wide(NS, SIDE_T, RN)), (NS == 1 && !SIDE_T && !RN) ? 2 : 1)
+// RN = 2 (XEOFS_ALGO_TF32X1F): the field is a materialised, already TF32-rounded copy of the preprocessed matrix (pivot 0,
+// dscale 1, no NaN): the operand stage only moves it from shared memory into TMEM; accumulators flushed as for RN = 1.
+template <int NS, bool SIDE_T, int KB, bool STATS = false, int RN = 0, bool PK = false, bool TFAST = false>
+__global__ void __launch_bounds__(tc_threads(tc_wide(NS, SIDE_T, RN != 0)), (NS == 1 && !SIDE_T && RN == 0) ? 2 : 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBhi,
                   const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
   static_assert(SIDE_T || KB == 1, "project_S stages are 32 rows of t");
@@ -106,8 +108,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   constexpr int BPART = NS == 3 ? 2 : 1;            // parts of the small operand (NS == 2: it is TF32-exact already)
   // FL: two TMEM accumulators that take turns, each moved into fp32 registers (round-to-nearest adds) after TC_FLUSH
   // slabs — the tensor core's own adds truncate.  All multi-product modes, and the rounded single product.
-  constexpr bool FL = NS >= 2 || RN;
-  constexpr int NW = tc_nw(tc_wide(NS, SIDE_T, RN));  // operand-stage warps per TMEM lane quarter
+  constexpr bool FL = NS >= 2 || RN != 0;
+  constexpr int NW = tc_nw(tc_wide(NS, SIDE_T, RN != 0));  // operand-stage warps per TMEM lane quarter
   constexpr int KW = TC_KC / NW;                    // K values of a slab converted by one warp
   // project_T: a stage holds 128 rows of KB*32 (+4) floats, KB*128 + 16 bytes apart: TMA fetches them as 128 long
   // pieces (the engine's cost is per piece, about 7 cycles, whatever its length), one thread then reads one row, and
@@ -371,7 +373,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
               hi[r] = __float_as_uint(v[r]) & 0xffffe000u;
               lo[r] = __float_as_uint(v[r] - __uint_as_float(hi[r]));  // the hardware truncates it: -2^-22, see DESIGN.md
             } else {
-              hi[r] = RN ? to_tf32(v[r]) : __float_as_uint(v[r]);  // the tensor core reads the upper 19 bits
+              hi[r] = RN == 1 ? to_tf32(v[r]) : __float_as_uint(v[r]);  // the tensor core reads the upper 19 bits
             }
           }
         } else {
@@ -385,6 +387,11 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           for (int cc = 0; cc < KW / 4; ++cc) {
             const int ch = part * (KW / 4) + cc;
             const float4 x = lds128(src + ch * 16);
+            if (RN == 2) {  // materialised, rounded field: a plain move
+              hi[cc * 4 + 0] = __float_as_uint(x.x); hi[cc * 4 + 1] = __float_as_uint(x.y);
+              hi[cc * 4 + 2] = __float_as_uint(x.z); hi[cc * 4 + 3] = __float_as_uint(x.w);
+              continue;
+            }
             const float4 pq = lds128(pv + ch * 16);
             float4 dq = make_float4(1.f, 1.f, 1.f, 1.f);
             if (!FOLD) dq = lds128(pv + 128 + ch * 16);
@@ -398,7 +405,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 hi[cc * 4 + e] = __float_as_uint(v) & 0xffffe000u;
                 lo[cc * 4 + e] = __float_as_uint(v - __uint_as_float(hi[cc * 4 + e]));
               } else {
-                hi[cc * 4 + e] = RN ? to_tf32(v) : __float_as_uint(v);
+                hi[cc * 4 + e] = RN == 1 ? to_tf32(v) : __float_as_uint(v);
               }
             }
           }
@@ -670,7 +677,7 @@ bool tc_supported(int64_t T, int64_t S, int64_t ldx, const float* X, int64_t l) 
 static inline int64_t align256(int64_t b) { return round_up(b, 256); }
 static inline bool is_x3(int algo) { return algo == XEOFS_ALGO_TF32X3 || algo == XEOFS_ALGO_AUTO; }
 static inline int algo_ns(int algo) { return algo == XEOFS_ALGO_TF32X3 ? 3 : algo == XEOFS_ALGO_TF32X2 ? 2 : 1; }
-static inline bool algo_rn(int algo) { return algo == XEOFS_ALGO_TF32X1R; }
+static inline int algo_rn(int algo) { return algo == XEOFS_ALGO_TF32X1R ? 1 : algo == XEOFS_ALGO_TF32X1F ? 2 : 0; }
 // 3xTF32 with the two products of the big operand's upper part packed into one N = 2 lp instruction (see the kernel)
 static inline bool use_pack(int ns, int lp) { return ns == 3 && lp <= 96 && env_int("XEOFS_TC_PACK", 1) != 0; }
 
@@ -721,7 +728,7 @@ struct TGeom {
 // (the 3xTF32 / 2xTF32 / rounded-TF32 kernels flush into fp32 registers every TC_FLUSH slabs), 1024 for the
 // power-iteration products
 // (a bias of ~1e-4 that only rescales the iterate)
-static int t_cap(int algo) { return (algo_ns(algo) >= 2 || algo_rn(algo)) ? 0 : 1024; }
+static int t_cap(int algo) { return (algo_ns(algo) >= 2 || algo_rn(algo) != 0) ? 0 : 1024; }
 static TGeom t_geometry(int64_t T, int64_t S, int cap, int kb) {
   TGeom g;
   g.t_tiles = ceil_div(T, TC_TILE);
@@ -757,16 +764,16 @@ int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo) {
   return (bs > bt ? bs : bt) + 256;
 }
 
-template <int NS, bool SIDE_T, int KB, bool RN = false, bool PK = false, bool TFAST = false>
+template <int NS, bool SIDE_T, int KB, int RN = 0, bool PK = false, bool TFAST = false>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p, dim3 grid,
                      size_t smem, cudaStream_t stream) {
   XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<NS, SIDE_T, KB, false, RN, PK, TFAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  project_tc_kernel<NS, SIDE_T, KB, false, RN, PK, TFAST><<<grid, tc_threads(tc_wide(NS, SIDE_T, RN)), smem, stream>>>(mx, mh, ml, p);
+  project_tc_kernel<NS, SIDE_T, KB, false, RN, PK, TFAST><<<grid, tc_threads(tc_wide(NS, SIDE_T, RN != 0)), smem, stream>>>(mx, mh, ml, p);
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
 }
 // project_T: pick the instantiation for (KB, no-NaN promise)
-template <int NS, bool RN, bool PK>
+template <int NS, int RN, bool PK>
 static int launch_T(int kb, bool fast, const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p,
                     dim3 grid, size_t smem, cudaStream_t stream) {
   if (fast)
@@ -801,7 +808,7 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
     chunk_flags_kernel<<<(unsigned)ceil_div(Tpad / TC_KC, 128), 128, 0, stream>>>(row_valid, T, (int)(Tpad / TC_KC), flags);
     XB_LAUNCH_CHECK();
   }
-  prep_W_kernel<<<(unsigned)(Tpad / TC_KC), 256, 0, stream>>>(W, T, ldw, lp, Whi, Wlo, algo_rn(algo) ? 1 : 0,
+  prep_W_kernel<<<(unsigned)(Tpad / TC_KC), 256, 0, stream>>>(W, T, ldw, lp, Whi, Wlo, algo_rn(algo) == 1 ? 1 : 0,
                                                               pk ? 2 * lp * 32 : 0);
   XB_LAUNCH_CHECK();
   CUtensorMap mx, mh, ml;
@@ -816,7 +823,7 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
     rc = make_map2(&ml, Wlo, 256, (Tpad / TC_KC) * (lp / 8), 256, 256, lp / 8, false);
     if (rc) return rc;
   }
-  const Shape sh = pick_shape(lp, ns, false, 1, algo_rn(algo));
+  const Shape sh = pick_shape(lp, ns, false, 1, algo_rn(algo) != 0);
   TcParams p{};
   p.T = T; p.S = S; p.lp = lp;
   p.stages = sh.stages; p.dcols = sh.dcols; p.tmem_cols = sh.tmem_cols;
@@ -828,10 +835,11 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   p.b_bulk = env_int("XEOFS_TC_BBULK", 1);
   p.chunk_flags = row_valid ? flags : nullptr;
   dim3 grid((unsigned)ceil_div(S, TC_TILE));
-  return ns == 3 && pk  ? launch_tc<3, false, 1, false, true>(mx, mh, ml, p, grid, sh.smem, stream)
+  return ns == 3 && pk  ? launch_tc<3, false, 1, 0, true>(mx, mh, ml, p, grid, sh.smem, stream)
          : ns == 3      ? launch_tc<3, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
          : ns == 2      ? launch_tc<2, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
-         : algo_rn(algo) ? launch_tc<1, false, 1, true>(mx, mh, ml, p, grid, sh.smem, stream)
+         : algo_rn(algo) == 1 ? launch_tc<1, false, 1, 1>(mx, mh, ml, p, grid, sh.smem, stream)
+         : algo_rn(algo) == 2 ? launch_tc<1, false, 1, 2>(mx, mh, ml, p, grid, sh.smem, stream)
                         : launch_tc<1, false, 1>(mx, mh, ml, p, grid, sh.smem, stream);
 }
 
@@ -903,7 +911,7 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   (void)workspace_bytes;
   const int lp = (int)lpad(l);
   const int ns = algo_ns(algo);
-  const Shape sh = pick_shape_T(lp, ns, S, ldx, algo_rn(algo));
+  const Shape sh = pick_shape_T(lp, ns, S, ldx, algo_rn(algo) != 0);
   XB_CHECK_ARG(sh.stages >= 1, "project_T: no pipeline shape fits lp=%d", lp);
   const int kb = sh.kb;
   const TGeom g = t_geometry(T, S, t_cap(algo), kb);
@@ -917,8 +925,8 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   float* Ylo = ns == 3 ? (pk ? Yhi + lp * 32 : (float*)ws) : nullptr;
   pad_vectors_kernel<<<(unsigned)ceil_div(g.Spad, 256), 256, 0, stream>>>(pivot, dscale, S, g.Spad, pdpad);
   XB_LAUNCH_CHECK();
-  tile_Y_kernel<<<(unsigned)(g.Spad / TC_KC), 256, 0, stream>>>(Yt, S, ldy, lp, Yhi, Ylo, algo_rn(algo) ? 1 : 0,
-                                                                pk ? 2 * lp * 32 : 0, ns != 2 ? dscale : nullptr);
+  tile_Y_kernel<<<(unsigned)(g.Spad / TC_KC), 256, 0, stream>>>(Yt, S, ldy, lp, Yhi, Ylo, algo_rn(algo) == 1 ? 1 : 0,
+                                                                pk ? 2 * lp * 32 : 0, (ns != 2 && algo_rn(algo) != 2) ? dscale : nullptr);
   XB_LAUNCH_CHECK();
   int rc;
   if (ccorr) {
@@ -948,11 +956,12 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
     if (rc) return rc;
   }
   const bool fast = no_nan && !row_valid;
-  if (ns == 3 && pk) rc = launch_T<3, false, true>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
-  else if (ns == 3) rc = launch_T<3, false, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
-  else if (ns == 2) rc = launch_T<2, false, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
-  else if (algo_rn(algo)) rc = launch_T<1, true, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
-  else rc = launch_T<1, false, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
+  if (ns == 3 && pk) rc = launch_T<3, 0, true>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
+  else if (ns == 3) rc = launch_T<3, 0, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
+  else if (ns == 2) rc = launch_T<2, 0, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
+  else if (algo_rn(algo) == 1) rc = launch_T<1, 1, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
+  else if (algo_rn(algo) == 2) rc = launch_T<1, 2, false>(kb, true, mx, mh, ml, p, grid, sh.smem, stream);
+  else rc = launch_T<1, 0, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
   if (rc) return rc;
   reduce_partials_kernel<<<(unsigned)ceil_div(T * lp, 256), 256, 0, stream>>>(part, g.splits, g.rows_pad, lp, T,
                                                                               ccorr ? rvec : nullptr, row_valid, Z, ldz);

@@ -110,6 +110,41 @@ __global__ void scaled_rows_kernel(const float* __restrict__ X, int64_t S, int64
 }
 }  // namespace xb
 
+namespace xb {
+__global__ void __launch_bounds__(256)
+materialize_kernel(const float* __restrict__ X, int64_t T, int64_t S, int64_t ldx, const float* __restrict__ pivot,
+                   const float* __restrict__ dscale, const float* __restrict__ ccorr, const uint8_t* __restrict__ row_valid,
+                   int64_t rows_out, int round_tf32, float* __restrict__ out, int64_t ldo) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const float p = pivot[s], d = dscale[s], c = ccorr ? ccorr[s] : 0.f;
+  for (int64_t t = blockIdx.y; t < rows_out; t += gridDim.y) {
+    float v = 0.f;
+    if (t < T && (!row_valid || row_valid[t])) {
+      const float x = X[t * ldx + s] - p;
+      v = ((x == x) ? x * d : 0.f) + c;
+      if (round_tf32) {
+        const uint32_t u = __float_as_uint(v);
+        v = __uint_as_float((u + 0xFFFu + ((u >> 13) & 1u)) & 0xFFFFE000u);
+      }
+    }
+    out[t * ldo + s] = v;
+  }
+}
+}  // namespace xb
+
+extern "C" int xeofs_b200_materialize(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
+                                      const float* dscale, const float* ccorr, const uint8_t* row_valid, int64_t rows_out,
+                                      int round_tf32, float* out, int64_t ldo, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(X && pivot && dscale && out, "materialize: null pointer");
+  XB_CHECK_ARG(T > 0 && S > 0 && ldx >= S && ldo >= S && rows_out >= T, "materialize: bad shape");
+  materialize_kernel<<<dim3((unsigned)ceil_div(S, 256), (unsigned)imin(rows_out, 4096)), 256, 0, stream>>>(
+      X, T, S, ldx, pivot, dscale, ccorr, row_valid, rows_out, round_tf32, out, ldo);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
 extern "C" int xeofs_b200_scaled_rows(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
                                       const float* dscale, const float* ccorr, const uint8_t* row_valid, int64_t t0,
                                       int64_t nrows, int64_t rows_out, float* out, int64_t ldo, void* stream_) {
