@@ -20,7 +20,7 @@ def main():
     X = torch.randn((T, S), device="cuda") * 3 + 280
     st = ops.col_stats(X)
     fin = ops.scaling_finalize(st, None, True, False)
-    f = Field(X, fin["pivot"], fin["dscale"], None, fin["valid"])
+    f = Field(X, fin["pivot"], fin["dscale"], None, fin["valid"], no_nan=True)
     W = torch.zeros((T, lp), device="cuda")
     W[:, :l] = torch.randn((T, l), device="cuda")
     Y = ops.space_side(lp, S, zero=True)

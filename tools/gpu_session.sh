@@ -12,9 +12,10 @@ for step in "$@"; do
     bench_c5) timeout 600 python bench.py --workload c5 --steps 4 --warmup 3 > gpurun_out/${tag}_bench_c5.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_bench_c5.log ;;
     parity)   timeout 1800 python tools/parity_full.py c2 c3 c5 c4n1 > gpurun_out/${tag}_parity.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_parity.log ;;
     profile)  timeout 600 python tools/profile_fit.py c2 > gpurun_out/${tag}_profile.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_profile.log ;;
-    kern)     { timeout 600 python tools/bench_kernels.py 8760 1038240 60 --env=XEOFS_TC_PACK=0,1 --env=XEOFS_TC_BBULK=0,1;
-                timeout 600 python tools/bench_kernels.py 8760 518400 110 --env=XEOFS_TC_BBULK=0,1;
-                timeout 600 python tools/bench_kernels.py 8760 259200 30 --env=XEOFS_TC_PACK=0,1; } > gpurun_out/${tag}_kern.log 2>&1 ;;
+    kern)     { timeout 300 python tools/bench_kernels.py 8760 1038240 60 --env=XEOFS_TC_CLUSTER=1,2,4,1,2;
+                timeout 300 python tools/bench_kernels.py 8760 518400 110 --env=XEOFS_TC_CLUSTER=1,2,4;
+                timeout 300 python tools/bench_kernels.py 8760 259200 30 --env=XEOFS_TC_CLUSTER=1,2,4; } > gpurun_out/${tag}_kern.log 2>&1 ;;
+    clchk)    XEOFS_TC_CLUSTER=2 timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "tcgen05 or fused" > gpurun_out/${tag}_clchk.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_clchk.log ;;
     small)    { timeout 300 python tools/bench_small.py; timeout 300 python tools/bench_small.py 518400 110; } > gpurun_out/${tag}_small.log 2>&1 ;;
     profile_c4) timeout 900 python tools/profile_fit.py c4 > gpurun_out/${tag}_profile_c4.log 2>&1 ;;
     smoke)    timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_smoke.log ;;

@@ -75,6 +75,7 @@ struct TcParams {
   const float* bimg_hi; // small operand as a sequence of shared-memory images, one per 32-wide K slab:
   const float* bimg_lo; //   [slab][lp rows][32 k], 16-byte chunks XOR-swizzled by (row & 7)  (lo: 3xTF32 only)
   int b_bulk;           // fetch the operand image of a stage with one bulk copy (else: tensor-map rows of 1 KB)
+  int cl;               // CTAs per cluster (1, 2 or 4): they share the operand image through TMA multicast
 };
 
 
@@ -138,10 +139,12 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   const int chunk0 = SIDE_T ? blockIdx.y * p.chunks_per_cta : 0;
   const int nchunks = SIDE_T ? min(p.chunks_per_cta, p.nchunks_total - chunk0) : p.nchunks_total;
 
+  const int cl = p.cl;  // cluster size; > 1: every CTA of the cluster fetches 1/cl of the operand image for all
+  const uint16_t cl_mask = (uint16_t)((1u << cl) - 1u);
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < stages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], cl);  // released by the MMAs of every CTA that the stage's operand image was written to
       mbar_init(&aready[i], 4 * NW);
     }
     mbar_init(&dfull[0], 1);
@@ -153,6 +156,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync_all();  // the peers' barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t a_col0 = (FL ? NBUF : 1) * p.dcols;  // first TMEM column of the A-operand ring
@@ -181,7 +185,17 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         // (packed: [hi rows | lo rows] per slab, one copy for both parts) instead of lp/8 tensor-map rows of 1 KB —
         // the TMA engine's cost is per piece
         const size_t slab0 = (size_t)(chunk0 + c) * KB;
-        if (p.b_bulk) {
+        if (cl > 1) {
+          // this CTA's share of the image, written into every CTA of the cluster (same offsets, their barriers)
+          const uint32_t nb0 = (PK ? 2 : 1) * KB * bbytes, share = nb0 / cl, off = share * cluster_ctarank();
+          bulk_load_1d_mc(b + off, (const uint8_t*)(p.bimg_hi + slab0 * (PK ? 2 : 1) * lp * TC_KC) + off, share, &full[st],
+                          cl_mask, HINT_EVICT_LAST);
+          if (NS == 3 && !PK) {
+            const uint32_t sh2 = KB * bbytes / cl, of2 = sh2 * cluster_ctarank();
+            bulk_load_1d_mc(b + (size_t)KB * bbytes + of2, (const uint8_t*)(p.bimg_lo + slab0 * lp * TC_KC) + of2, sh2,
+                            &full[st], cl_mask, HINT_EVICT_LAST);
+          }
+        } else if (p.b_bulk) {
           bulk_load_1d_hint(b, p.bimg_hi + slab0 * (PK ? 2 : 1) * lp * TC_KC, (PK ? 2 : 1) * KB * bbytes, &full[st],
                             HINT_EVICT_LAST);
           if (NS == 3 && !PK)
@@ -235,7 +249,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
               }
             }
           }
-          mma_commit(&empty[st]);
+          if (cl > 1) mma_commit_mc(&empty[st], cl_mask);
+          else mma_commit(&empty[st]);
           if (group_end) mma_commit(&dfull[g % NBUF]);
           if (!FL && c == nchunks - 1) mma_commit(&dfull[0]);
         }
@@ -515,6 +530,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (cl > 1) cluster_sync_all();  // no CTA leaves while a peer may still write into its shared memory / barriers
 }
 
 // ------------------------------------------------------------------------------------------------ small helpers
@@ -729,9 +745,18 @@ struct TGeom {
 // power-iteration products
 // (a bias of ~1e-4 that only rescales the iterate)
 static int t_cap(int algo) { return (algo_ns(algo) >= 2 || algo_rn(algo) != 0) ? 0 : 1024; }
-static TGeom t_geometry(int64_t T, int64_t S, int cap, int kb) {
+// CTAs per cluster sharing the small operand's image through TMA multicast (XEOFS_TC_CLUSTER = 1, 2 or 4).
+// Measured on B200 (profiles/r02_cluster_multicast_sweep.txt): clusters of 2 or 4 change nothing for project_S and cost
+// project_T 5-10 % at lp = 64 .. 112 — the operand image is an L2 hit either way and ncu shows the L2 at 57 % of its
+// peak in these passes, so the traffic multicast removes was never the limiter; the lock-step it adds between the
+// CTAs of a cluster is what shows.  Default 1.
+static int pick_cluster() {
+  const int c = env_int("XEOFS_TC_CLUSTER", 1);
+  return c == 4 ? 4 : c == 2 ? 2 : 1;
+}
+static TGeom t_geometry(int64_t T, int64_t S, int cap, int kb, int cl = 1) {
   TGeom g;
-  g.t_tiles = ceil_div(T, TC_TILE);
+  g.t_tiles = round_up(ceil_div(T, TC_TILE), cl);  // whole clusters along the row tiles (the extra tiles hold no rows)
   g.rows_pad = g.t_tiles * TC_TILE;
   g.Spad = round_up(S, 128);  // covers every KB
   g.chunks_total = (int)ceil_div(S, TC_KC * kb);
@@ -755,7 +780,7 @@ int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo) {
   // (the finest split has the largest partial buffer)
   int64_t part = 0;
   for (int kb = 1; kb <= 4; kb *= 2) {
-    const TGeom g = t_geometry(T, S, t_cap(algo), kb);
+    const TGeom g = t_geometry(T, S, t_cap(algo), kb, 4);
     const int64_t b = (int64_t)g.splits * g.rows_pad * lp * 4;
     if (b > part) part = b;
   }
@@ -764,13 +789,37 @@ int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo) {
   return (bs > bt ? bs : bt) + 256;
 }
 
+// One launch, as a grid of clusters of p.cl CTAs along x (grid.x is a multiple of p.cl)
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
+static int launch_kernel(TcKernel kern, int threads, const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml,
+                         const TcParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
+  XB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (p.cl <= 1) {
+    kern<<<grid, threads, smem, stream>>>(mx, mh, ml, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)p.cl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    XB_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, mh, ml, p));
+  }
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
 template <int NS, bool SIDE_T, int KB, int RN = 0, bool PK = false, bool TFAST = false>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p, dim3 grid,
                      size_t smem, cudaStream_t stream) {
-  XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<NS, SIDE_T, KB, false, RN, PK, TFAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  project_tc_kernel<NS, SIDE_T, KB, false, RN, PK, TFAST><<<grid, tc_threads(tc_wide(NS, SIDE_T, RN != 0)), smem, stream>>>(mx, mh, ml, p);
-  XB_LAUNCH_CHECK();
-  return XEOFS_OK;
+  return launch_kernel(project_tc_kernel<NS, SIDE_T, KB, false, RN, PK, TFAST>, tc_threads(tc_wide(NS, SIDE_T, RN != 0)), mx, mh, ml,
+                       p, grid, smem, stream);
 }
 // project_T: pick the instantiation for (KB, no-NaN promise)
 template <int NS, int RN, bool PK>
@@ -833,8 +882,9 @@ int project_S_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   p.out = Yt; p.ldo = ldy;
   p.X = X; p.ldx = ldx; p.bimg_hi = Whi; p.bimg_lo = Wlo;
   p.b_bulk = env_int("XEOFS_TC_BBULK", 1);
+  p.cl = pick_cluster();
   p.chunk_flags = row_valid ? flags : nullptr;
-  dim3 grid((unsigned)ceil_div(S, TC_TILE));
+  dim3 grid((unsigned)round_up(ceil_div(S, TC_TILE), p.cl));
   return ns == 3 && pk  ? launch_tc<3, false, 1, 0, true>(mx, mh, ml, p, grid, sh.smem, stream)
          : ns == 3      ? launch_tc<3, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
          : ns == 2      ? launch_tc<2, false, 1>(mx, mh, ml, p, grid, sh.smem, stream)
@@ -893,13 +943,13 @@ int project_S_stats_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const 
   p.out = Yt; p.ldo = ldy;
   p.X = X; p.ldx = ldx; p.bimg_hi = Whi;
   p.b_bulk = env_int("XEOFS_TC_BBULK", 1);
+  p.cl = pick_cluster();
   p.featw = featw; p.stat_flags = flags;
   p.mean_out = mean; p.std_out = stdv; p.valid_out = valid; p.pivot_out = pivot; p.dscale_out = dscale; p.ccorr_out = ccorr;
   p.scalars_out = scalars; p.row_delta = row_delta; p.base_nan = base_nan;
-  dim3 grid((unsigned)ceil_div(S, TC_TILE));
-  XB_CUDA(cudaFuncSetAttribute(project_tc_kernel<1, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
-  project_tc_kernel<1, false, 1, true><<<grid, tc_threads(false), sh.smem, stream>>>(mx, mh, mh, p);
-  XB_LAUNCH_CHECK();
+  dim3 grid((unsigned)round_up(ceil_div(S, TC_TILE), p.cl));
+  rc = launch_kernel(project_tc_kernel<1, false, 1, true>, tc_threads(false), mx, mh, mh, p, grid, sh.smem, stream);
+  if (rc) return rc;
   row_nan_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, stream>>>(row_delta, base_nan, T, row_nan);
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
@@ -914,7 +964,8 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   const Shape sh = pick_shape_T(lp, ns, S, ldx, algo_rn(algo) != 0);
   XB_CHECK_ARG(sh.stages >= 1, "project_T: no pipeline shape fits lp=%d", lp);
   const int kb = sh.kb;
-  const TGeom g = t_geometry(T, S, t_cap(algo), kb);
+  const int cl = pick_cluster();
+  const TGeom g = t_geometry(T, S, t_cap(algo), kb, cl);
   XB_CHECK_ARG(g.splits <= 65535, "project_T: too many splits");
   uint8_t* ws = (uint8_t*)workspace;
   float* rvec = (float*)ws; ws += align256(lp * 4);
@@ -942,6 +993,7 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   p.out = part; p.ldo = lp;
   p.X = X; p.ldx = ldx; p.bimg_hi = Yhi; p.bimg_lo = Ylo;
   p.b_bulk = env_int("XEOFS_TC_BBULK", 1);
+  p.cl = cl;
   dim3 grid((unsigned)g.t_tiles, (unsigned)g.splits);
   CUtensorMap mx, mh, ml;
   // rows of X in pieces of KB*32 + 4 floats (the 4 extra only give the shared-memory rows their odd pitch)
