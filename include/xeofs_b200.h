@@ -174,11 +174,12 @@ int xeofs_b200_varimax_sweep(const float* Ln, int64_t S, int64_t m, int64_t ld, 
  * Ln^T Ln and alpha = gamma / n_rows,  G = Gout - alpha (XtX R) diag(Wout);  R <- U V^T of svd(G) (in place);
  * *dsum = sum(svals).  `basis` (m x m, in/out; identity before the first iteration) carries the eigenvectors of
  * G^T G from one iteration to the next — in that basis the matrix is nearly diagonal and the Jacobi solver ends early.
+ * eig_tol: relative off-diagonal norm at which the Jacobi sweeps may stop (0 = the solver's own 3e-15).
  * m <= 128; all matrices fp64 row-major.                                                                            */
 int64_t xeofs_b200_varimax_update_workspace_bytes(int64_t m);
 int xeofs_b200_varimax_update(const double* Gout, const double* Wout, const double* XtX, double alpha, int64_t m,
-                              double* R, double* basis, double* dsum, void* workspace, int64_t workspace_bytes,
-                              void* stream);
+                              double* R, double* basis, double* dsum, double eig_tol, void* workspace,
+                              int64_t workspace_bytes, void* stream);
 /* Kaiser norms (_rotation.py:155-160): h[s] = sqrt(sum_j L[j,s]^2); rownorm[s] = 1/(h+eps);
  * Ln[j,s] = L[j,s] * rownorm[s] (space-side, ldn >= S).  Any of h / rownorm / Ln may be NULL.             */
 int xeofs_b200_col_norms(const float* L, int64_t S, int64_t m, int64_t ld, float* h, float* rownorm, float* Ln,
@@ -221,6 +222,21 @@ int xeofs_b200_sym_eig_wide(const double* G, int64_t n, double* evals, double* e
 int xeofs_b200_materialize(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot, const float* dscale,
                            const float* ccorr, const uint8_t* row_valid, int64_t rows_out, int round_tf32, float* out,
                            int64_t ldo, void* stream);
+
+/* ---- M3: the sample Gram matrix A A^T of a preprocessed field as a plain tcgen05 GEMM (kind::f16 on a bf16 copy) ----
+ * materialize_bf16: the preprocessed matrix (as xeofs_b200_materialize) rounded to bf16, rows_out x cols_out with zero
+ *                   padding (rows_out a multiple of 256, cols_out a multiple of 64 for gram_rows_bf16).
+ * gram_rows_bf16:   G (T_pad x ldg fp32) <- the block-lower triangle (t >= 256 floor(t'/256)) of A A^T, both operands
+ *                   TMA-fed row tiles of the bf16 copy, fp32 accumulation in TMEM over at most 512 instructions per
+ *                   accumulator, deterministic second-stage sum.  For sums over >= 65 536 features (the bf16 rounding
+ *                   errors average out to ~5e-6 relative): the total squared covariance of cross/cpcca.py:991-1000 as
+ *                   <X X^T, Y Y^T>_F / (n-1)^2.                                                                     */
+int xeofs_b200_materialize_bf16(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
+                                const float* dscale, const float* ccorr, const uint8_t* row_valid, int64_t rows_out,
+                                int64_t cols_out, void* out, int64_t ldo, void* stream);
+int64_t xeofs_b200_gram_rows_bf16_workspace_bytes(int64_t T_pad, int64_t S_pad);
+int xeofs_b200_gram_rows_bf16(const void* A, int64_t T_pad, int64_t S_pad, int64_t ld, float* G, int64_t ldg,
+                              void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -192,7 +192,7 @@ class TorchCpuOps:
             Ln[:m] = L[:m, :S] * rn[None, :]
         return h, rn, Ln
 
-    def varimax_update(self, G3, W, XtX, alpha, R, basis, dsum):
+    def varimax_update(self, G3, W, XtX, alpha, R, basis, dsum, eig_tol=0.0):
         G = G3 - alpha * (XtX @ R) * W[None, :]
         U, sv, Vh = torch.linalg.svd(G)
         R.copy_(U @ Vh)

@@ -302,8 +302,8 @@ def test_mca_patterns_and_score_statistics(use_pca):
 
 
 def test_mca_total_squared_covariance_wide_fields():
-    """cpcca.py:991-1000 at a width (S >= 2^16) where the sample Gram matrices take the single rounded TF32 product
-    (XEOFS_ALGO_TF32X1R): sum |C|^2 = <A1 A1^T, A2 A2^T> / (n-1)^2 against fp64 torch on the preprocessed fields."""
+    """cpcca.py:991-1000 at a width (S >= 2^16) where the sample Gram matrices come from the bf16 tcgen05 GEMM
+    (csrc/gram_bf16.cu): sum |C|^2 = <A1 A1^T, A2 A2^T> / (n-1)^2 against fp64 torch on the preprocessed fields."""
     import xeofs_b200 as xb
     from xeofs_b200 import _lib
     T, S1, S2, k = 300, 70000, 66000, 4

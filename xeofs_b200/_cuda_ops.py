@@ -380,6 +380,30 @@ class CudaOps:
         zero, one = self._unit_vectors(f.S)
         return Field(out[:, :f.S], zero, one, None, None, no_nan=True)
 
+    def sample_gram(self, f: Field):
+        """Block-lower triangle of the sample Gram matrix A A^T (T x T fp32) of a field's preprocessed matrix: one bf16
+        copy of the matrix, then a TMA-fed tcgen05 GEMM of its row tiles against themselves (csrc/gram_bf16.cu).
+        Entries above the diagonal are valid only inside the 256 x 256 diagonal blocks: read it through torch.tril.
+        None when it does not apply (no tensor-core path / not enough memory for the copy)."""
+        if not bool(self.lib.xeofs_b200_has_tcgen05()) or self.accurate_algo == _lib.ALGO_SIMT:
+            return None
+        Tp, Sp = (f.T + 255) // 256 * 256, (f.S + 63) // 64 * 64
+        need_ws = int(self.lib.xeofs_b200_gram_rows_bf16_workspace_bytes(Tp, Sp))
+        free, _ = torch.cuda.mem_get_info(self.device)
+        cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        if Tp * Sp * 2 + Tp * Tp * 4 + need_ws + (2 << 30) > free + cached:
+            return None
+        Ab = torch.empty((Tp, Sp), dtype=torch.bfloat16, device=self.device)
+        check(self.lib.xeofs_b200_materialize_bf16(ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr),
+                                                   ptr(f.row_valid), Tp, Sp, ptr(Ab), Sp, self._stream()),
+              "materialize_bf16")
+        G = torch.empty((Tp, Tp), dtype=torch.float32, device=self.device)
+        ws = torch.empty(need_ws, dtype=torch.uint8, device=self.device)
+        check(self._timed("gram_rows_bf16", 256, lambda: self.lib.xeofs_b200_gram_rows_bf16(
+            ptr(Ab), Tp, Sp, Sp, ptr(G), Tp, ptr(ws), need_ws, self._stream())), "gram_rows_bf16")
+        self.launches += 1 + 2 * (Tp // 256)
+        return G[:f.T, :f.T]
+
     def scaled_rows(self, f: Field, t0, t1):
         """Rows t0:t1 of the preprocessed matrix as a space-side block (pad rows zero)."""
         w = int(t1 - t0)
@@ -412,7 +436,7 @@ class CudaOps:
             return False
         return self.varimax_algo == "tc" or (S >= self.varimax_tc_min_S and m >= 8)
 
-    def varimax_update(self, G3, W, XtX, alpha, R, basis, dsum):
+    def varimax_update(self, G3, W, XtX, alpha, R, basis, dsum, eig_tol=0.0):
         """The m x m step of a varimax iteration on the device (xeofs_b200_varimax_update): R and basis are updated in
         place, the sum of the singular values lands in the one-element fp64 tensor ``dsum``.  No host round trip."""
         m = int(R.shape[0])
@@ -420,7 +444,8 @@ class CudaOps:
         if getattr(self, "_uws", None) is None or self._uws.numel() < need:
             self._uws = torch.empty(need, dtype=torch.uint8, device=self.device)
         check(self.lib.xeofs_b200_varimax_update(ptr(G3), ptr(W), ptr(XtX), float(alpha), m, ptr(R), ptr(basis),
-                                                 ptr(dsum), ptr(self._uws), need, self._stream()), "varimax_update")
+                                                 ptr(dsum), float(eig_tol), ptr(self._uws), need, self._stream()),
+              "varimax_update")
         self.launches += 12
         return dsum
 

@@ -45,7 +45,7 @@ SIGNATURES = {
     "xeofs_b200_varimax_workspace_bytes": (_i64, [_i64, _i64]),
     "xeofs_b200_varimax_sweep": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _int, _p, _i64, _p]),
     "xeofs_b200_varimax_update_workspace_bytes": (_i64, [_i64]),
-    "xeofs_b200_varimax_update": (_int, [_p, _p, _p, C.c_double, _i64, _p, _p, _p, _p, _i64, _p]),
+    "xeofs_b200_varimax_update": (_int, [_p, _p, _p, C.c_double, _i64, _p, _p, _p, C.c_double, _p, _i64, _p]),
     "xeofs_b200_col_norms": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),
     "xeofs_b200_scaled_rows": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _p, _i64, _p]),
     "xeofs_b200_dgemm": (_int, [_int, _int, _i64, _i64, _i64, C.c_double, _p, _i64, _p, _i64, C.c_double, _p, _i64, _p]),
@@ -53,6 +53,9 @@ SIGNATURES = {
     "xeofs_b200_sym_eig_wide_workspace_bytes": (_i64, [_i64]),
     "xeofs_b200_sym_eig_wide": (_int, [_p, _i64, _p, _p, _p, _i64, _p, _int, _p]),
     "xeofs_b200_materialize": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _int, _p, _i64, _p]),
+    "xeofs_b200_materialize_bf16": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p]),
+    "xeofs_b200_gram_rows_bf16_workspace_bytes": (_i64, [_i64, _i64]),
+    "xeofs_b200_gram_rows_bf16": (_int, [_p, _i64, _i64, _i64, _p, _i64, _p, _i64, _p]),
     "xeofs_b200_reconstruct": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p, _i64, _p]),
 }
 

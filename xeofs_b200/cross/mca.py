@@ -367,8 +367,21 @@ class MCA:
         # (operands rounded to nearest, 2e-4 per term) averages out below 1e-6; smaller fields take the 3xTF32 product
         S_all = min(self._f1.S_global, self._f2.S_global)
         algo = getattr(ops, "sum_algo", ops.accurate_algo) if S_all >= 65536 else ops.accurate_algo
-        # wide fields: one TF32-rounded copy of each preprocessed matrix, then every Gram block is a plain streaming
-        # product of its rows (the field is read ~T/256 times: the copy pays for itself after the second block)
+        # wide fields: the two sample Gram matrices as tcgen05 GEMMs on a bf16 copy of each preprocessed matrix
+        # (csrc/gram_bf16.cu): every entry sums >= 65 536 products whose rounding errors average out
+        if S_all >= 65536 and hasattr(ops, "sample_gram") and algo == getattr(ops, "sum_algo", None):
+            G1 = ops.sample_gram(self._f1.field)
+            G2 = ops.sample_gram(self._f2.field) if G1 is not None else None
+            if G2 is not None:
+                self.comm.sum_(G1)
+                self.comm.sum_(G2)
+                P = G1.double() * G2.double()
+                del G1, G2
+                tot = 2.0 * torch.tril(P, -1).sum() + torch.diagonal(P).sum()
+                self._tsc_cache = float(tot.item()) / float(self._f1.n_samples - 1) ** 2
+                return self._tsc_cache
+        # else: one TF32-rounded copy of each preprocessed matrix, then every Gram block is a plain streaming product
+        # of its rows (the field is read ~T/256 times: the copy pays for itself after the second block)
         r1 = r2 = None
         if S_all >= 65536 and hasattr(ops, "materialize") and algo == getattr(ops, "sum_algo", None):
             r1 = ops.materialize(self._f1.field)

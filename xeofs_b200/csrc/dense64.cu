@@ -316,15 +316,17 @@ static void dgemm_sq(int m, const double* A, const double* B, double* C, cudaStr
 }
 }  // namespace xb
 
-extern "C" int xeofs_b200_sym_eig(const double* G, int64_t l, double* evals, double* evecs, double* work, int32_t* info,
-                                  void* stream);
+namespace xb {
+int sym_eig_launch(const double* G, int64_t l, double* evals, double* evecs, double* work, int32_t* info, double tol2,
+                   cudaStream_t stream);
+}
 
 extern "C" int64_t xeofs_b200_varimax_update_workspace_bytes(int64_t m) {
   return (9 * m * m + m + (m + 2) * (m + 2) + 16) * (int64_t)sizeof(double);
 }
 
 extern "C" int xeofs_b200_varimax_update(const double* G3, const double* W, const double* XtX, double alpha, int64_t m,
-                                         double* R, double* basis, double* dsum, void* workspace,
+                                         double* R, double* basis, double* dsum, double eig_tol, void* workspace,
                                          int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   XB_CHECK_ARG(G3 && W && XtX && R && basis && dsum && workspace && m >= 2 && m <= 128,
@@ -351,7 +353,9 @@ extern "C" int xeofs_b200_varimax_update(const double* G3, const double* W, cons
   dgemm_sq<false, false>(mi, M, basis, T2, stream);                     // (G^T G) basis
   dgemm_sq<true, false>(mi, basis, T2, Mp, stream);                     // basis^T (G^T G) basis
   XB_LAUNCH_CHECK();
-  int rc = xeofs_b200_sym_eig(Mp, m, ev, Vp, ework, info, stream_);
+  // eig_tol: relative off-diagonal norm at which the Jacobi sweeps may stop (0: the solver's own 3e-15); the
+  // tensor-core iterations carry fp32-level noise in G anyway and pass 1e-9
+  int rc = sym_eig_launch(Mp, m, ev, Vp, ework, info, eig_tol > 0.0 ? eig_tol * eig_tol : 1e-29, stream);
   if (rc) return rc;
   dgemm_sq<false, false>(mi, basis, Vp, V, stream);                     // eigenvectors of G^T G
   vu_scale_kernel<<<1, 256, 0, stream>>>(V, ev, mi, P, dsum);           // V diag(1/svals), delta

@@ -1,0 +1,275 @@
+// Sample Gram matrix A A^T of a preprocessed field on the tensor cores, for the total squared covariance of the cross
+// models:  sum |C|^2 = sum |X^T Y|^2 / (n-1)^2 = <X X^T, Y Y^T>_F / (n-1)^2   (reference: cross/cpcca.py:991-1000 forms
+// C = X^T Y / (n-1) densely, cpcca.py:1008-1015 — at BASELINE config 3 that matrix has 6.7e10 entries).
+//
+// A plain tcgen05 GEMM: both operands are row tiles of ONE bf16 copy of the preprocessed matrix (xeofs_b200_materialize_bf16:
+// T_pad x S_pad, rows = samples, features contiguous), fetched by TMA with the 128-byte swizzle straight into the K-major
+// layout kind::f16 reads — no register staging.  Every entry of the Gram matrix is a sum over >= 65 536 features of
+// products whose bf16 rounding errors (2^-9, round-to-nearest) are independent: they average out to ~5e-6 relative,
+// an order of magnitude inside the tolerance of the quantity (and unbiased to 1.3e-6).
+//
+//   D[128 t][256 t'] += A[t, s-chunk] . A[t', s-chunk]^T       M = 128, N = 256, K = 16 per instruction, 64 per stage
+//
+// Grid per panel of 256 columns t': (row tiles with t >= panel start) x (splits of the feature axis).  The tensor core
+// adds into its fp32 accumulator with truncation, so one accumulator never sums more than GB_MAX_STEPS instructions;
+// the partial sums of the splits are added by a second, deterministic kernel.  Only the block-lower triangle is
+// computed (the matrix is symmetric).
+//
+// 6 warps: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (TMEM -> global).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "tc_common.cuh"
+
+namespace xb {
+
+constexpr int GB_KS = 64;          // features per stage (= one 128-byte swizzle row of bf16)
+constexpr int GB_N = 256;          // columns of the panel
+constexpr int GB_STAGES = 4;
+constexpr int GB_A_BYTES = TC_TILE * GB_KS * 2;  // 16 KB
+constexpr int GB_B_BYTES = GB_N * GB_KS * 2;     // 32 KB
+constexpr int GB_MAX_STEPS = 512;  // MMA instructions (K = 16) one accumulator may sum: bias ~2e-8 each
+
+struct GbParams {
+  int row_tile0;   // first row tile (of 128 rows) of this launch
+  int col0;        // first column t' of the panel
+  int ksteps;      // stages' worth of K over the whole feature axis
+  int ksteps_per_split;
+  float* part;     // [split][n_row_tiles * 128][256]
+  int64_t rows;    // n_row_tiles * 128
+};
+
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// D fp32, A / B bf16, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(192, 1)
+gram_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GbParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* as = smem;                                   // [stages][16 KB]
+  uint8_t* bs = smem + GB_STAGES * GB_A_BYTES;          // [stages][32 KB]
+  uint64_t* bars = (uint64_t*)(bs + GB_STAGES * GB_B_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + GB_STAGES;
+  uint64_t* dfull = bars + 2 * GB_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(dfull + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = (p.row_tile0 + (int)blockIdx.x) * TC_TILE;
+  const int k0 = (int)blockIdx.y * p.ksteps_per_split;
+  const int nk = min(p.ksteps_per_split, p.ksteps - k0);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < GB_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(dfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, GB_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    Pipe pp;
+    for (int c = 0; c < nk; ++c, pp.advance(GB_STAGES)) {
+      mbar_wait(&empty[pp.st], pp.ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&full[pp.st], GB_A_BYTES + GB_B_BYTES);
+        const int s0 = (k0 + c) * GB_KS;
+        tma_load_2d(as + pp.st * GB_A_BYTES, &mapA, s0, row0, &full[pp.st], HINT_EVICT_FIRST);
+        tma_load_2d(bs + pp.st * GB_B_BYTES, &mapB, s0, p.col0, &full[pp.st], HINT_EVICT_LAST);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16(GB_N);
+    Pipe pp;
+    for (int c = 0; c < nk; ++c, pp.advance(GB_STAGES)) {
+      mbar_wait(&full[pp.st], pp.ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = make_b_desc(smem_u32(as + pp.st * GB_A_BYTES));
+        const uint64_t db = make_b_desc(smem_u32(bs + pp.st * GB_B_BYTES));
+#pragma unroll
+        for (int k = 0; k < GB_KS / 16; ++k)  // +32 bytes (16 bf16) along K = +2 in the (address >> 4) field
+          mma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, !(c == 0 && k == 0));
+        mma_commit(&empty[pp.st]);
+        if (c == nk - 1) mma_commit(dfull);
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue: lane quarter q of TMEM = rows q*32 .. q*32+31 of the tile
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    float* dst = p.part + ((int64_t)blockIdx.y * p.rows + (int64_t)blockIdx.x * TC_TILE + row) * GB_N;
+    if (nk > 0) {
+      mbar_wait(dfull, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < GB_N; j += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + j, v);
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(dst + j + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+      }
+    } else {
+      for (int j = 0; j < GB_N; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, GB_N);
+}
+
+// G[row, col0 + j] = sum_split part[split][row - row0][j]
+__global__ void gram_bf16_reduce_kernel(const float* __restrict__ part, int splits, int64_t rows, int64_t row0, int col0,
+                                        float* __restrict__ G, int64_t ldg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * (GB_N / 4)) return;
+  const int64_t r = i / (GB_N / 4);
+  const int j = (int)(i % (GB_N / 4)) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(part + ((int64_t)s * rows + r) * GB_N + j);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  *reinterpret_cast<float4*>(G + (row0 + r) * ldg + col0 + j) = a;
+}
+
+__global__ void __launch_bounds__(256)
+materialize_bf16_kernel(const float* __restrict__ X, int64_t T, int64_t S, int64_t ldx, const float* __restrict__ pivot,
+                        const float* __restrict__ dscale, const float* __restrict__ ccorr,
+                        const uint8_t* __restrict__ row_valid, int64_t rows_out, int64_t cols_out,
+                        __nv_bfloat16* __restrict__ out, int64_t ldo) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= cols_out) return;
+  const bool in = s < S;
+  const float p = in ? pivot[s] : 0.f, d = in ? dscale[s] : 0.f, c = (in && ccorr) ? ccorr[s] : 0.f;
+  for (int64_t t = blockIdx.y; t < rows_out; t += gridDim.y) {
+    float v = 0.f;
+    if (in && t < T && (!row_valid || row_valid[t])) {
+      const float x = X[t * ldx + s] - p;
+      v = ((x == x) ? x * d : 0.f) + c;
+    }
+    out[t * ldo + s] = __float2bfloat16_rn(v);
+  }
+}
+
+// project_tc.cu
+typedef CUresult (*EncodeTiledFnB)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map_bf16(CUtensorMap* m, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
+  static EncodeTiledFnB enc = nullptr;
+  if (!enc) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      enc = (EncodeTiledFnB)fp;
+  }
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return XEOFS_E_UNSUPPORTED;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer}, gstr[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t bx[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer}, estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (bf16) failed (%d)", (int)r);
+    return XEOFS_E_CUDA;
+  }
+  return XEOFS_OK;
+}
+
+static int gb_splits(int n_tiles, int ksteps) {
+  // enough CTAs for two waves, no accumulator past GB_MAX_STEPS instructions (4 per stage)
+  int64_t s = ceil_div(2 * (int64_t)num_sms(), n_tiles);
+  const int64_t need = ceil_div((int64_t)ksteps * (GB_KS / 16), GB_MAX_STEPS);
+  if (s < need) s = need;
+  if (s > ksteps) s = ksteps;
+  return (int)(s < 1 ? 1 : s);
+}
+
+}  // namespace xb
+
+using namespace xb;
+
+extern "C" int xeofs_b200_materialize_bf16(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
+                                           const float* dscale, const float* ccorr, const uint8_t* row_valid,
+                                           int64_t rows_out, int64_t cols_out, void* out, int64_t ldo, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(X && pivot && dscale && out, "materialize_bf16: null pointer");
+  XB_CHECK_ARG(T > 0 && S > 0 && ldx >= S && rows_out >= T && cols_out >= S && ldo >= cols_out, "materialize_bf16: bad shape");
+  materialize_bf16_kernel<<<dim3((unsigned)ceil_div(cols_out, 256), (unsigned)imin(rows_out, 4096)), 256, 0, stream>>>(
+      X, T, S, ldx, pivot, dscale, ccorr, row_valid, rows_out, cols_out, (__nv_bfloat16*)out, ldo);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
+extern "C" int64_t xeofs_b200_gram_rows_bf16_workspace_bytes(int64_t T_pad, int64_t S_pad) {
+  const int ksteps = (int)(S_pad / GB_KS);
+  int64_t mx = 0;
+  for (int64_t c0 = 0; c0 < T_pad; c0 += GB_N) {
+    const int n_tiles = (int)((T_pad - c0) / TC_TILE);
+    const int64_t b = (int64_t)gb_splits(n_tiles, ksteps) * n_tiles * TC_TILE * GB_N * 4;
+    if (b > mx) mx = b;
+  }
+  return mx + 256;
+}
+
+// G (T_pad x ldg fp32): the block-lower triangle (rows t >= 256 * (t' / 256)) of A A^T for the bf16 matrix A
+// (T_pad x S_pad, T_pad a multiple of 256, S_pad a multiple of 64, row pitch ld elements).
+extern "C" int xeofs_b200_gram_rows_bf16(const void* A, int64_t T_pad, int64_t S_pad, int64_t ld, float* G, int64_t ldg,
+                                         void* workspace, int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(A && G && workspace, "gram_rows_bf16: null pointer");
+  XB_CHECK_ARG(T_pad > 0 && T_pad % GB_N == 0 && S_pad > 0 && S_pad % GB_KS == 0 && ld >= S_pad && ld % 8 == 0 && ldg >= T_pad &&
+                   ldg % 4 == 0 && ((uintptr_t)A % 128 == 0) && ((uintptr_t)G % 16 == 0) && ((uintptr_t)workspace % 16 == 0),
+               "gram_rows_bf16: bad shape / alignment");
+  XB_CHECK_ARG(workspace_bytes >= xeofs_b200_gram_rows_bf16_workspace_bytes(T_pad, S_pad), "gram_rows_bf16: workspace too small");
+  CUtensorMap mA, mB;
+  int rc = make_map_bf16(&mA, A, S_pad, T_pad, ld, GB_KS, TC_TILE);
+  if (rc) return rc;
+  rc = make_map_bf16(&mB, A, S_pad, T_pad, ld, GB_KS, GB_N);
+  if (rc) return rc;
+  const size_t smem = (size_t)GB_STAGES * (GB_A_BYTES + GB_B_BYTES) + 1024 + 256;
+  XB_CUDA(cudaFuncSetAttribute(gram_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int ksteps = (int)(S_pad / GB_KS);
+  for (int64_t c0 = 0; c0 < T_pad; c0 += GB_N) {
+    const int n_tiles = (int)((T_pad - c0) / TC_TILE);
+    const int splits = gb_splits(n_tiles, ksteps);
+    GbParams p{};
+    p.row_tile0 = (int)(c0 / TC_TILE);
+    p.col0 = (int)c0;
+    p.ksteps = ksteps;
+    p.ksteps_per_split = (int)ceil_div(ksteps, splits);
+    p.part = (float*)workspace;
+    p.rows = (int64_t)n_tiles * TC_TILE;
+    const int used = (int)ceil_div(ksteps, p.ksteps_per_split);
+    gram_bf16_kernel<<<dim3((unsigned)n_tiles, (unsigned)used), 192, smem, stream>>>(mA, mB, p);
+    XB_LAUNCH_CHECK();
+    gram_bf16_reduce_kernel<<<(unsigned)ceil_div(p.rows * (GB_N / 4), 256), 256, 0, stream>>>((const float*)workspace, used, p.rows,
+                                                                                             c0, (int)c0, G, ldg);
+    XB_LAUNCH_CHECK();
+  }
+  return XEOFS_OK;
+}

@@ -291,7 +291,7 @@ __device__ __forceinline__ void eig_pair(int q, int r, int le, int& p, int& s) {
 template <bool VS>
 __global__ void __launch_bounds__(EIG_THREADS)
 sym_eig_kernel(const double* __restrict__ G, int l, double* __restrict__ evals, double* __restrict__ evecs,
-               double* __restrict__ work, int32_t* __restrict__ info) {
+               double* __restrict__ work, int32_t* __restrict__ info, double tol2) {
   extern __shared__ double sh[];
   const int le = (l + 1) & ~1;  // even size for the tournament
   const int ldA = le + 1;
@@ -340,7 +340,7 @@ sym_eig_kernel(const double* __restrict__ G, int l, double* __restrict__ evals, 
     off = warp_sum(off); dg = warp_sum(dg);
     if ((tid & 31) == 0) { atomicAdd(&offnorm, off); atomicAdd(&diagnorm, dg); }
     __syncthreads();
-    const bool done = offnorm <= 1e-29 * diagnorm || diagnorm == 0.0;
+    const bool done = offnorm <= tol2 * diagnorm || diagnorm == 0.0;
     __syncthreads();
     if (done) break;
     sweeps_done = sweep + 1;
@@ -547,9 +547,17 @@ extern "C" int xeofs_b200_apply(const float* In, int64_t n, int64_t l, int64_t l
   return XEOFS_OK;
 }
 
+// tol2: the sweeps end when the squared off-diagonal Frobenius norm falls below tol2 x the squared diagonal norm
+namespace xb {
+int sym_eig_launch(const double* G, int64_t l, double* evals, double* evecs, double* work, int32_t* info, double tol2,
+                   cudaStream_t stream);
+}
 extern "C" int xeofs_b200_sym_eig(const double* G, int64_t l, double* evals, double* evecs, double* work,
                                   int32_t* info, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+  return xb::sym_eig_launch(G, l, evals, evecs, work, info, 1e-29, (cudaStream_t)stream_);
+}
+int xb::sym_eig_launch(const double* G, int64_t l, double* evals, double* evecs, double* work, int32_t* info,
+                       double tol2, cudaStream_t stream) {
   XB_CHECK_ARG(G && evals && evecs && work && info && l > 0 && l <= 128, "sym_eig: bad arguments (l=%lld must be in 1..128)", (long long)l);
   const int le = ((int)l + 1) & ~1;
   const size_t base = ((size_t)le * (le + 1) + le) * sizeof(double) + (size_t)2 * le * sizeof(int);
@@ -557,10 +565,10 @@ extern "C" int xeofs_b200_sym_eig(const double* G, int64_t l, double* evals, dou
   const int threads = EIG_THREADS;  // the kernel's block table assumes half^2 <= 4 * threads
   if (with_v <= 227 * 1024) {
     XB_CUDA(cudaFuncSetAttribute(sym_eig_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_v));
-    sym_eig_kernel<true><<<1, threads, with_v, stream>>>(G, (int)l, evals, evecs, work, info);
+    sym_eig_kernel<true><<<1, threads, with_v, stream>>>(G, (int)l, evals, evecs, work, info, tol2);
   } else {
     XB_CUDA(cudaFuncSetAttribute(sym_eig_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));
-    sym_eig_kernel<false><<<1, threads, base, stream>>>(G, (int)l, evals, evecs, work, info);
+    sym_eig_kernel<false><<<1, threads, base, stream>>>(G, (int)l, evals, evecs, work, info, tol2);
   }
   XB_LAUNCH_CHECK();
   return XEOFS_OK;

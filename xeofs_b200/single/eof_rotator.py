@@ -64,7 +64,7 @@ class EOFRotator:
             G3, W, _ = ops.varimax_accumulate(Ln, S_local, m, R, exact=not use_tc)
             comm.sum_(G3)
             comm.sum_(W)
-            ops.varimax_update(G3, W, XtX, alpha, R, basis, hist_dev[it - 1:it])
+            ops.varimax_update(G3, W, XtX, alpha, R, basis, hist_dev[it - 1:it], eig_tol=1e-9 if use_tc else 0.0)
             if use_tc:
                 if not test or (it - read < TC_SYNC and it < max_iter):
                     continue
