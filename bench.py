@@ -48,10 +48,16 @@ WORKLOADS = {
     "mid": (8760, 90, 1440, 50, 4, {}),                                        # 1/8 of c2 (quick looks)
     "c4mid": (8760, 176, 2880, 100, 4, {"use_coslat": True, "standardize": True}),  # 1/8 of c4 (quick looks)
 }
+# synthetic-field parameters per workload: every requested mode must stand clear of the noise floor eps (sqrt(T) +
+# sqrt(S)) — noise-level singular values are nearly degenerate and no two summation orders (1 GPU vs 8) agree on them
+# to 1e-4.  config 4 asks for 100 modes: sigma_i = 1e6 0.95^i keeps sigma_100 = 6.2e3 a factor 29 above it
+FIELD = {"c4": dict(seed=4, decay=0.95), "c4mid": dict(seed=4, decay=0.95)}
 C3 = dict(T=8760, n_lat=360, n_lon=720, k=20)          # BASELINE configs[2]
 C5 = dict(T=1024, n_lat=1440, n_lon=2880, k=100)       # configs[4]: the loadings are (1440 x 2880) x 100
 RANDOM_STATE = 5
-CPU_SAMPLE_COLS = 16384  # columns of the field the CPU legs fit per step (8760 x 16384 fp32 = 0.57 GB)
+CPU_SAMPLE_COLS = 32768  # columns of the field the CPU legs fit per step (22 latitude rows of config 2: 1.11 GB, ~6 s;
+# the CPU rate grows with the sample — 0.09 GB/s at 16 384 columns, 0.18 at S/8, 0.166 on the whole field
+# (profiles/r02_reference_arm_s8.json, r02_parity_full.json) — so the bounded sample is as wide as the time budget allows)
 EXPECTED = os.path.join(ROOT, "profiles", "r02_expected_sv.json")
 DIMS = ("time", "lat", "lon")
 
@@ -180,8 +186,7 @@ def cpu_fit_sample(X_host, n_lat_rows, n_lon, k, n_iter, kw, threads):
 
 
 def sample_geometry(n_lon, cols=CPU_SAMPLE_COLS):
-    n_lon_s = min(n_lon, 1024) if cols <= CPU_SAMPLE_COLS else n_lon
-    return max(1, cols // n_lon_s), n_lon_s
+    return max(1, cols // n_lon), n_lon
 
 
 def run_reference(args):
@@ -343,8 +348,10 @@ def check_sv(s, key, rtol=1e-4):
         return {"checked": False, "why": f"no entry {key!r} in profiles/r02_expected_sv.json"}
     ref = np.asarray(exp["s"], dtype=np.float64)
     n = min(len(ref), len(s))
-    err = float(np.max(np.abs(np.asarray(s[:n], dtype=np.float64) / ref[:n] - 1.0)))
-    return {"checked": True, "against": exp.get("source"), "modes": n, "max_rel_err": err, "rtol": rtol,
+    rel = np.abs(np.asarray(s[:n], dtype=np.float64) / ref[:n] - 1.0)
+    err = float(rel.max())
+    return {"checked": True, "against": exp.get("source"), "modes": n, "max_rel_err": err,
+            "worst_mode": int(rel.argmax()) + 1, "median_rel_err": float(np.median(rel)), "rtol": rtol,
             "ok": bool(err <= rtol)}
 
 
@@ -371,8 +378,8 @@ def eof_case(d, args, wl, scaling, steps, warmup, e2e=True, cpu=True, clock=True
     S_local = lat_rows * n_lon
     lat_all = np.linspace(90.0, -90.0, n_lat_total)
     coords = {"lat": lat_all[lat0:lat0 + lat_rows], "lon": np.arange(n_lon) * (360.0 / n_lon)}
-    seed = {"c4": 4, "c4mid": 4}.get(wl, 1)
-    X = planted_field_device(T, lat_rows, n_lon, lat0, n_lat_total, 2 * k, seed, d.device)
+    fp = FIELD.get(wl, dict(seed=1, decay=0.9))
+    X = planted_field_device(T, lat_rows, n_lon, lat0, n_lat_total, 2 * k, fp["seed"], d.device, decay=fp["decay"])
     if args.land_frac > 0:
         # a land mask: a fixed fraction of the grid points is NaN at every time step (the Sanitizer's full-dimensional
         # NaN case, sanitizer.py:46-56); every 1/frac-th block of 64 points
@@ -449,7 +456,8 @@ def eof_case(d, args, wl, scaling, steps, warmup, e2e=True, cpu=True, clock=True
         dt, _ = cpu_fit_sample(Xs, rows_s, n_lon_s, k, n_iter, kw, threads)
         res["cpu"] = {"value": T * S_s * 4 / dt / 1e9, "unit": "GB/s", "cores": threads, "kind": "port",
                       "sample": f"one oracle eof_fit on {T}x{S_s} fp32 ({T * S_s * 4 / 1e9:.2f} GB) of the same "
-                                f"synthetic recipe: {dt:.1f} s"}
+                                f"synthetic recipe: {dt:.1f} s (the whole config-2 field, once: 219.8 s = 0.166 GB/s, "
+                                "profiles/r02_parity_full.json)"}
     return res
 
 

@@ -165,11 +165,14 @@ int xeofs_b200_varimax_accumulate(const float* L, int64_t S, int64_t m, int64_t 
 /* The varimax sweep (power = 3, colscale NULL, rownorm NULL: Ln already Kaiser-normalised) on the tensor cores:
  * both products of _rotation.py:166-170 (B = X R and X^H B^3) as tcgen05 kind::tf32 MMAs with hi/lo split operands
  * (~fp32 accuracy per product, fp64 accumulation across tiles), the tile of Ln read from HBM once.  Ln is space-side
- * with lpad(m) rows (pad rows zero).  Returns XEOFS_E_UNSUPPORTED where tcgen05 does not apply (use
- * xeofs_b200_varimax_accumulate).                                                                              */
+ * with lpad(m) rows (pad rows zero).  products = 3: hi/lo split operands as described; products = 1: one product per
+ * GEMM with operands rounded to TF32 (a third of the tensor work, ~1e-3 per term, averaging out over the features) for
+ * the iterations in which the rotation is still far from converged.  Returns XEOFS_E_UNSUPPORTED where tcgen05 does
+ * not apply (use xeofs_b200_varimax_accumulate).                                                                              */
 int64_t xeofs_b200_varimax_workspace_bytes(int64_t S, int64_t m);
 int xeofs_b200_varimax_sweep(const float* Ln, int64_t S, int64_t m, int64_t ld, const double* R, double* Gout,
-                             double* Wout, int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
+                             double* Wout, int accumulate, int products, void* workspace, int64_t workspace_bytes,
+                             void* stream);
 /* The m x m step of one varimax iteration (_rotation.py:170-175), on the device: with Gout / Wout of the sweep, XtX =
  * Ln^T Ln and alpha = gamma / n_rows,  G = Gout - alpha (XtX R) diag(Wout);  R <- U V^T of svd(G) (in place);
  * *dsum = sum(svals).  `basis` (m x m, in/out; identity before the first iteration) carries the eigenvectors of

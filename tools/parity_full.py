@@ -62,8 +62,8 @@ def compare_modes(s, s_ref, V, V_ref, Sc, Sc_ref):
 def run_c2(report, expected, wl="c2"):
     T, n_lat, n_lon, k, n_iter, kw = bench.WORKLOADS[wl]
     dev = torch.device("cuda")
-    seed = {"c4": 4, "c4mid": 4}.get(wl, 1)
-    X = bench.planted_field_device(T, n_lat, n_lon, 0, n_lat, 2 * k, seed, dev)
+    fp = bench.FIELD.get(wl, dict(seed=1, decay=0.9))
+    X = bench.planted_field_device(T, n_lat, n_lon, 0, n_lat, 2 * k, fp["seed"], dev, decay=fp["decay"])
     coords = {"lat": np.linspace(90.0, -90.0, n_lat), "lon": np.arange(n_lon) * (360.0 / n_lon)}
     m = xb.single.EOF(n_modes=k, random_state=bench.RANDOM_STATE, solver_kwargs={"n_iter": n_iter}, **kw)
     t0 = time.perf_counter()
@@ -129,7 +129,8 @@ def run_c4n1(report, expected):
     """The one-GPU fit of the strong-scaling field: its singular values are what every N is compared with."""
     T, n_lat, n_lon, k, n_iter, kw = bench.WORKLOADS["c4"]
     dev = torch.device("cuda")
-    X = bench.planted_field_device(T, n_lat, n_lon, 0, n_lat, 2 * k, 4, dev)
+    fp = bench.FIELD["c4"]
+    X = bench.planted_field_device(T, n_lat, n_lon, 0, n_lat, 2 * k, fp["seed"], dev, decay=fp["decay"])
     coords = {"lat": np.linspace(90.0, -90.0, n_lat), "lon": np.arange(n_lon) * (360.0 / n_lon)}
 
     def fit():

@@ -449,7 +449,7 @@ class CudaOps:
         self.launches += 12
         return dsum
 
-    def varimax_accumulate(self, L, S, m, R, power=3.0, colscale=None, want_absmax=False, exact=False):
+    def varimax_accumulate(self, L, S, m, R, power=3.0, colscale=None, want_absmax=False, exact=False, products=3):
         """One sweep over the normalised loadings (linalg/_numpy/_rotation.py:166-170): Gout = Ln^T f(Ln R), W = colsum
         ((Ln R)^2).  exact=True keeps every product in fp64 (stopping thresholds below ~1e-9)."""
         G = self.empty((m, m), torch.float64)
@@ -458,9 +458,10 @@ class CudaOps:
             need = int(self.lib.xeofs_b200_varimax_workspace_bytes(S, m))
             if self._vws is None or self._vws.numel() < need:
                 self._vws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            check(self._timed("varimax_sweep", m, lambda: self.lib.xeofs_b200_varimax_sweep(
-                ptr(L), S, m, int(L.stride(0)), ptr(R), ptr(G), ptr(Wv), 0, ptr(self._vws), self._vws.numel(),
-                self._stream())), "varimax_sweep")
+            check(self._timed("varimax_sweep" if products == 3 else "varimax_sweep_x1", m,
+                              lambda: self.lib.xeofs_b200_varimax_sweep(
+                ptr(L), S, m, int(L.stride(0)), ptr(R), ptr(G), ptr(Wv), 0, int(products), ptr(self._vws),
+                self._vws.numel(), self._stream())), "varimax_sweep")
             self.launches += 4
             return G, Wv, None
         amax = self.empty(m) if want_absmax else None

@@ -130,7 +130,7 @@ varimax_accumulate_kernel(const float* __restrict__ L, int64_t S, int m, int64_t
 int64_t varimax_tc_workspace_bytes(int64_t S, int64_t m);
 bool varimax_tc_supported(const float* L, int64_t S, int64_t m, int64_t ld);
 int varimax_sweep_tc(const float* L, int64_t S, int64_t m, int64_t ld, const double* R, double* Gout, double* Wout,
-                     int accumulate, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+                     int accumulate, int products, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 
 }  // namespace xb
 
@@ -139,17 +139,18 @@ using namespace xb;
 extern "C" int64_t xeofs_b200_varimax_workspace_bytes(int64_t S, int64_t m) { return varimax_tc_workspace_bytes(S, m); }
 
 extern "C" int xeofs_b200_varimax_sweep(const float* Ln, int64_t S, int64_t m, int64_t ld, const double* R, double* Gout,
-                                        double* Wout, int accumulate, void* workspace, int64_t workspace_bytes,
-                                        void* stream_) {
+                                        double* Wout, int accumulate, int products, void* workspace,
+                                        int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   XB_CHECK_ARG(Ln && R && Gout && Wout && workspace && S > 0 && ld >= S, "varimax_sweep: bad arguments");
+  XB_CHECK_ARG(products == 1 || products == 3, "varimax_sweep: products must be 1 (single TF32) or 3 (3xTF32)");
   XB_CHECK_ARG(m >= 2 && m <= 128, "varimax_sweep: m=%lld must be in 2..128", (long long)m);
   XB_CHECK_ARG((uintptr_t)workspace % 256 == 0, "varimax_sweep: misaligned workspace");
   if (!xeofs_b200_has_tcgen05() || !varimax_tc_supported(Ln, S, m, ld)) {
     set_error("varimax_sweep: needs the tcgen05 path (sm_100, 16-byte aligned Ln, ld %% 4 == 0)");
     return XEOFS_E_UNSUPPORTED;
   }
-  return varimax_sweep_tc(Ln, S, m, ld, R, Gout, Wout, accumulate, workspace, workspace_bytes, stream);
+  return varimax_sweep_tc(Ln, S, m, ld, R, Gout, Wout, accumulate, products, workspace, workspace_bytes, stream);
 }
 
 extern "C" int xeofs_b200_col_norms(const float* L, int64_t S, int64_t m, int64_t ld, float* h, float* rownorm,

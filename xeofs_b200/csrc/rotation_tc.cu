@@ -43,6 +43,7 @@ struct VtParams {
   int k1;         // K of GEMM1 (m rounded up to 8)
   int stages;
   int ntiles;
+  int x1;            // 1: single TF32 products (hi parts only, rounded to nearest) — the first phase of the iteration
   const float* rhi;  // [128][128]: rhi[j'][i] = TF32 bits of (float)R[i][j']
   const float* rlo;  // [128][128]: remainder
   double* gpart;     // [grid][128][ng]
@@ -51,11 +52,12 @@ struct VtParams {
 
 // R (m x m fp64, row-major) -> A = R^T (row j', K = i):  hi = TF32 bits of (float)R, lo = remainder
 __global__ void __launch_bounds__(256)
-vt_prep_R_kernel(const double* __restrict__ R, int m, float* __restrict__ rhi, float* __restrict__ rlo) {
+vt_prep_R_kernel(const double* __restrict__ R, int m, float* __restrict__ rhi, float* __restrict__ rlo, int x1) {
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 128 * 128; idx += gridDim.x * blockDim.x) {
     const int j = idx >> 7, k = idx & 127;
     const float r32 = (k < m && j < m) ? (float)R[(int64_t)k * m + j] : 0.f;
-    const float hi = __uint_as_float(__float_as_uint(r32) & 0xffffe000u);
+    // (single-product mode: the one part is the value rounded to nearest, not its upper bits)
+    const float hi = x1 ? __uint_as_float(to_tf32(r32)) : __uint_as_float(__float_as_uint(r32) & 0xffffe000u);
     rhi[idx] = hi;
     // the tensor core reads the top 19 bits of a value: rounding the remainder to that width here (to nearest) keeps
     // the split unbiased, where the hardware's truncation would shrink every value by about 2^-22
@@ -168,14 +170,17 @@ varimax_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
           const uint32_t hi = smem_u + st * stage_bytes + boxb, lo = hi + 2 * boxb;  // the MN-major images
           // the small cross terms first: the tensor core adds with truncation, an error of up to one ulp of the
           // running sum per instruction, which costs nothing while the sum is 2^-11 of its final size
-          for (int kk = 0; kk < (k1 >> 3); ++kk) {
-            const uint64_t b_hi = make_mn32_desc(hi + kk * 1024, boxb, sbo1);
-            const uint64_t b_lo = make_mn32_desc(lo + kk * 1024, boxb, sbo1);
-            mma_tf32_ts(d1, tmem_base + VT_COL_RLO + kk * 8, b_hi, idesc1, kk > 0);
-            mma_tf32_ts(d1, tmem_base + VT_COL_RHI + kk * 8, b_lo, idesc1, 1);
+          if (!p.x1) {
+            for (int kk = 0; kk < (k1 >> 3); ++kk) {
+              const uint64_t b_hi = make_mn32_desc(hi + kk * 1024, boxb, sbo1);
+              const uint64_t b_lo = make_mn32_desc(lo + kk * 1024, boxb, sbo1);
+              mma_tf32_ts(d1, tmem_base + VT_COL_RLO + kk * 8, b_hi, idesc1, kk > 0);
+              mma_tf32_ts(d1, tmem_base + VT_COL_RHI + kk * 8, b_lo, idesc1, 1);
+            }
           }
           for (int kk = 0; kk < (k1 >> 3); ++kk)
-            mma_tf32_ts(d1, tmem_base + VT_COL_RHI + kk * 8, make_mn32_desc(hi + kk * 1024, boxb, sbo1), idesc1, 1);
+            mma_tf32_ts(d1, tmem_base + VT_COL_RHI + kk * 8, make_mn32_desc(hi + kk * 1024, boxb, sbo1), idesc1,
+                        !p.x1 || kk > 0);
           mma_commit(&d1full[b]);
         }
         __syncwarp();
@@ -189,16 +194,18 @@ varimax_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
         if (elect_one()) {
           const uint32_t g = tmem_base + VT_COL_G;
           const uint32_t hi = smem_u + st * stage_bytes, lo = hi + 2 * boxb;  // the K-major images
+          if (!p.x1) {
 #pragma unroll
-          for (int kk = 0; kk < VT_TS / 8; ++kk) {
-            const uint32_t a_hi = tmem_base + VT_COL_D1 + b * VT_TS + kk * 8;
-            const uint32_t a_lo = tmem_base + VT_COL_FLO + b * VT_TS + kk * 8;
-            mma_tf32_ts(g, a_lo, make_b_desc(hi) + 2 * kk, idesc2, kk > 0);
-            mma_tf32_ts(g, a_hi, make_b_desc(lo) + 2 * kk, idesc2, 1);
+            for (int kk = 0; kk < VT_TS / 8; ++kk) {
+              const uint32_t a_hi = tmem_base + VT_COL_D1 + b * VT_TS + kk * 8;
+              const uint32_t a_lo = tmem_base + VT_COL_FLO + b * VT_TS + kk * 8;
+              mma_tf32_ts(g, a_lo, make_b_desc(hi) + 2 * kk, idesc2, kk > 0);
+              mma_tf32_ts(g, a_hi, make_b_desc(lo) + 2 * kk, idesc2, 1);
+            }
           }
 #pragma unroll
           for (int kk = 0; kk < VT_TS / 8; ++kk)
-            mma_tf32_ts(g, tmem_base + VT_COL_D1 + b * VT_TS + kk * 8, make_b_desc(hi) + 2 * kk, idesc2, 1);
+            mma_tf32_ts(g, tmem_base + VT_COL_D1 + b * VT_TS + kk * 8, make_b_desc(hi) + 2 * kk, idesc2, !p.x1 || kk > 0);
           mma_commit(&empty[st]);
           mma_commit(gfull);
         }
@@ -243,7 +250,7 @@ varimax_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
     auto split = [&](int st, uint32_t ph) {
       mbar_wait(&full[st], ph);
       const uint32_t hi = smem_u + st * stage_bytes, lo_k = hi + 2 * boxb, lo_mn = hi + 3 * boxb;
-      for (uint32_t off = et * 16; off < boxb; off += 256 * 16) {
+      for (uint32_t off = et * 16; off < boxb && !p.x1; off += 256 * 16) {
         const float4 v = lds128(hi + off);
         float4 r;
         r.x = __uint_as_float(to_tf32(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u)));
@@ -273,11 +280,11 @@ varimax_tc_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constan
         const float b2 = v[e] * v[e];
         w2 += b2;
         const float f = b2 * v[e];
-        fh[e] = __float_as_uint(f) & 0xffffe000u;
+        fh[e] = p.x1 ? to_tf32(f) : (__float_as_uint(f) & 0xffffe000u);
         fl[e] = to_tf32(f - __uint_as_float(fh[e]));
       }
       tmem_st16(tmem_base + lane_addr + VT_COL_D1 + col, fh);
-      tmem_st16(tmem_base + lane_addr + VT_COL_FLO + col, fl);
+      if (!p.x1) tmem_st16(tmem_base + lane_addr + VT_COL_FLO + col, fl);
       wacc += (double)w2;
       tmem_wait_st();
       tc_fence_before();
@@ -338,7 +345,7 @@ bool varimax_tc_supported(const float* L, int64_t S, int64_t m, int64_t ld) {
 }
 
 int varimax_sweep_tc(const float* L, int64_t S, int64_t m, int64_t ld, const double* R, double* Gout, double* Wout,
-                     int accumulate, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+                     int accumulate, int products, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
   if (workspace_bytes < varimax_tc_workspace_bytes(S, m)) {
     set_error("varimax_sweep: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes,
               (long long)varimax_tc_workspace_bytes(S, m));
@@ -348,6 +355,7 @@ int varimax_sweep_tc(const float* L, int64_t S, int64_t m, int64_t ld, const dou
   const int nb = (int)lpad(m);  // rows the caller's space-side matrix holds (pad rows zero)
   VtParams p{};
   p.S = S; p.nb = nb; p.ng = ng; p.k1 = k1;
+  p.x1 = products == 1 ? 1 : 0;
   p.ntiles = (int)ceil_div(S, VT_TS);
   const int stage_bytes = nb * 512;
   const int budget = 227 * 1024 - 1024 /*alignment*/ - 512 /*barriers*/;
@@ -367,7 +375,7 @@ int varimax_sweep_tc(const float* L, int64_t S, int64_t m, int64_t ld, const dou
   double* gpart = (double*)ws; ws += (int64_t)grid * 128 * ng * 8;
   double* wpart = (double*)ws;
   p.rhi = rhi; p.rlo = rlo; p.gpart = gpart; p.wpart = wpart;
-  vt_prep_R_kernel<<<16, 256, 0, stream>>>(R, (int)m, rhi, rlo);
+  vt_prep_R_kernel<<<16, 256, 0, stream>>>(R, (int)m, rhi, rlo, p.x1);
   XB_LAUNCH_CHECK();
   CUtensorMap mapK, mapMN;
   int rc = make_map2(&mapK, L, S, nb, ld, VT_TS, nb, 1);

@@ -18,6 +18,7 @@ from .. import _labels as L
 
 TC_WINDOW = 8  # iterations the stopping test of the tensor-core phase of the varimax iteration looks back
 TC_SYNC = 8    # tensor-core iterations between two reads of delta on the host
+X1_RTOL = 1e-5  # the single-TF32 sweeps hand over to the 3xTF32 ones when delta moves less than this per iteration
 
 
 class EOFRotator:
@@ -56,15 +57,19 @@ class EOFRotator:
         # iterations (_rotation.py:176-180), the last two in fp64.
         tc = getattr(ops, "_varimax_tc_applies", None)
         use_tc = bool(tc and rtol >= 1e-9 and tc(Ln, S_local, m, False))
+        # Far from convergence the tensor-core phase starts with single-TF32 sweeps (a third of the tensor work): their
+        # rounding noise (1e-3 per term, averaged over the features) is far below the change of the rotation there.
+        x1 = use_tc and rtol < X1_RTOL
         hist, read, d, d_old, converged, it = [], 0, None, None, False, 0
-        self.n_iter_tc_ = 0
+        self.n_iter_tc_ = self.n_iter_x1_ = 0
         for it in range(1, max_iter + 1):
             if use_tc and not test and it > max_iter - 2:
                 use_tc, self.n_iter_tc_ = False, it - 1
-            G3, W, _ = ops.varimax_accumulate(Ln, S_local, m, R, exact=not use_tc)
+            G3, W, _ = ops.varimax_accumulate(Ln, S_local, m, R, exact=not use_tc, products=1 if (use_tc and x1) else 3)
             comm.sum_(G3)
             comm.sum_(W)
-            ops.varimax_update(G3, W, XtX, alpha, R, basis, hist_dev[it - 1:it], eig_tol=1e-9 if use_tc else 0.0)
+            ops.varimax_update(G3, W, XtX, alpha, R, basis, hist_dev[it - 1:it],
+                               eig_tol=(1e-6 if x1 else 1e-9) if use_tc else 0.0)
             if use_tc:
                 if not test or (it - read < TC_SYNC and it < max_iter):
                     continue
@@ -73,7 +78,12 @@ class EOFRotator:
                 for v in vals:
                     hist.append(v)
                     w = min(TC_WINDOW, len(hist) - 1)
-                    if w >= 1 and abs(v - hist[-1 - w]) / (w * v) < rtol:
+                    if x1:
+                        if w >= 1 and abs(v - hist[-1 - w]) / (w * v) < X1_RTOL:
+                            x1, self.n_iter_x1_ = False, it
+                            hist = []  # the two arithmetics differ by a constant in delta: a fresh window
+                            break
+                    elif w >= 1 and abs(v - hist[-1 - w]) / (w * v) < rtol:
                         use_tc = False  # the next fp64 sweep has no fp64 predecessor to compare with
                         self.n_iter_tc_ = it
                         break
