@@ -655,7 +655,8 @@ def run_rotator(args):
     parity = {"variance_conserved": {"rel_err": abs(ev_rot / ev_eof - 1), "rtol": 1e-5,
                                      "ok": bool(abs(ev_rot / ev_eof - 1) < 1e-5)},
               "rotation_orthogonal": {"max_abs_err": orth, "atol": 1e-8, "ok": bool(orth < 1e-8)},
-              "iterations": iters, "iterations_tensor_core": int(getattr(r, "n_iter_tc_", 0))}
+              "iterations": iters, "iterations_tensor_core": int(getattr(r, "n_iter_tc_", 0)),
+              "iterations_single_tf32": int(getattr(r, "n_iter_x1_", 0))}
     parity["ok"] = bool(parity["variance_conserved"]["ok"] and parity["rotation_orthogonal"]["ok"])
     cpu = None
     if not args.no_cpu:
