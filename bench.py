@@ -487,6 +487,25 @@ def run_eof(args):
                       "s_head": st["s"][:5], "parity_vs_n1": chk, "invariant_transform_eq_scores": st["invariant"]}
         except Exception as exc:
             strong = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    # BASELINE configs[2] and [4] ride along on the one-GPU headline line in compact form (the full lines:
+    # --workload c3 / c5), so that every driver run records them
+    models = None
+    if wl == "c2" and d.world == 1 and not args.no_models:
+        models = {}
+        for name, case in (("c3_mca", mca_case), ("c5_varimax", rotator_case)):
+            try:
+                ln, okm = case(d, args, cpu=False)
+                rf = ln.get("roofline") or {}
+                models[name] = {"workload": ln["config"]["workload"], "metric": ln["metric"], "value": ln["value"],
+                                "unit": ln["unit"], "ms_per_step": ln["ms_per_step"], "steps": ln["steps"],
+                                "roofline": {k: rf.get(k) for k in ("bound", "kernel", "achieved", "peak", "unit", "frac",
+                                                                    "launch_ms", "share_of_step", "ms_per_iteration")},
+                                "parity": ln["parity"], "ok": okm}
+                for extra in ("ms_per_step_without_total_squared_covariance", "iterations"):
+                    if extra in ln:
+                        models[name][extra] = ln[extra]
+            except Exception as exc:
+                models[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if d.rank != 0:
         d.close()
         return 0
@@ -498,6 +517,8 @@ def run_eof(args):
     ok = parity["transform_eq_scores"]["ok"] and parity["singular_values"].get("ok", True)
     if strong and "error" not in strong:
         ok = ok and strong["invariant_transform_eq_scores"]["ok"] and strong["parity_vs_n1"].get("ok", True)
+    if models:
+        ok = ok and all(v.get("ok", False) for v in models.values())
     parity["ok"] = bool(ok)
     line = {
         "metric": "EOF.fit GB/s (time x space fp32 streamed)", "value": res["value"], "unit": "GB/s",
@@ -507,7 +528,7 @@ def run_eof(args):
         "config": {"workload": res["desc"], "l2": "inputs larger than L2 (no flush needed)", "algo": args.algo,
                    "extra": res["extra"]},
         "e2e": res["e2e"], "gpu_launches": res["launches"], "roofline": roof, "cpu_baseline": res["cpu"],
-        "clocks": res["clocks"], "parity": parity, "strong_c4": strong,
+        "clocks": res["clocks"], "parity": parity, "strong_c4": strong, "models": models,
         "singular_values_head": res["s"][:3],
     }
     print(json.dumps(line), flush=True)
@@ -517,11 +538,19 @@ def run_eof(args):
 
 # ------------------------------------------------------------------------------------------------ MCA (config 3)
 def run_mca(args):
+    d = Dist()
+    line, ok = mca_case(d, args, cpu=not args.no_cpu)
+    if d.rank == 0:
+        print(json.dumps(line), flush=True)
+    d.close()
+    return 0 if ok else 3
+
+
+def mca_case(d, args, cpu=True):
     """BASELINE configs[2]: MCA n_modes=20 on two 8760 x (360 x 720) fields, cross-covariance applied implicitly.
     value = bytes of both fields / fit time; the fit includes the total squared covariance (cpcca.py:197)."""
     import xeofs_b200 as xb
 
-    d = Dist()
     torch = d.torch
     peak, peak_src, _ = load_peak()
     T, n_lat, n_lon, k = C3["T"], int(C3["n_lat"] * args.scale), C3["n_lon"], C3["k"]
@@ -561,8 +590,8 @@ def run_mca(args):
               else {"checked": False}}
     parity["ok"] = bool(parity["scores_reproduce_singular_values"]["ok"] and parity["squared_covariance_le_total"]
                         and parity["singular_values"].get("ok", True))
-    cpu = None
-    if d.world == 1 and not args.no_cpu:
+    want_cpu, cpu = cpu, None
+    if d.world == 1 and want_cpu:
         from threadpoolctl import threadpool_limits
 
         from oracle import mca as omca
@@ -582,31 +611,38 @@ def run_mca(args):
                "sample": f"one oracle mca_fit (explicit C = X^T Y/(n-1), {cols} x {cols}, then sklearn randomized_svd) on "
                          f"two {T}x{cols} fields: {dt:.1f} s; the explicit C grows with S^2 and cannot be formed at "
                          "the full size"}
-    if d.rank == 0:
-        line = {
-            "metric": "MCA.fit GB/s (both time x space fp32 fields streamed)", "value": total_bytes / (ms * 1e-3) / 1e9,
-            "unit": "GB/s", "n_gpus": d.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak" if d.world == 1 else args.scaling, "vs_baseline": None,
-            "dtype": "tf32/f32 (fp64 small matrices)", "data": "synthetic",
-            "config": {"workload": f"c3: MCA n_modes={k} (use_pca=False, n_iter auto=7, implicit cross-covariance, total "
-                                   f"squared covariance included) on two {T}x({n_lat_total}x{n_lon}) fp32 fields "
-                                   f"({total_bytes / 1e9:.2f} GB)", "l2": "inputs larger than L2 (no flush needed)"},
-            "ms_per_step_without_total_squared_covariance": ms_no_tsc, "total_squared_covariance": tsc,
-            "e2e": None, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
-            "parity": parity, "singular_values_head": [float(v) for v in s[:3]],
-        }
-        print(json.dumps(line), flush=True)
-    d.close()
-    return 0 if parity["ok"] else 3
+    del X, Y, m
+    torch.cuda.empty_cache()
+    line = {
+        "metric": "MCA.fit GB/s (both time x space fp32 fields streamed)", "value": total_bytes / (ms * 1e-3) / 1e9,
+        "unit": "GB/s", "n_gpus": d.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak" if d.world == 1 else args.scaling, "vs_baseline": None,
+        "dtype": "tf32/f32 (fp64 small matrices)", "data": "synthetic",
+        "config": {"workload": f"c3: MCA n_modes={k} (use_pca=False, n_iter auto=7, implicit cross-covariance, total "
+                               f"squared covariance included) on two {T}x({n_lat_total}x{n_lon}) fp32 fields "
+                               f"({total_bytes / 1e9:.2f} GB)", "l2": "inputs larger than L2 (no flush needed)"},
+        "ms_per_step_without_total_squared_covariance": ms_no_tsc, "total_squared_covariance": tsc,
+        "e2e": None, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+        "parity": parity, "singular_values_head": [float(v) for v in s[:3]],
+    }
+    return line, bool(parity["ok"])
 
 
 # ------------------------------------------------------------------------------------------------ varimax (config 5)
 def run_rotator(args):
+    d = Dist()
+    line, ok = rotator_case(d, args, cpu=not args.no_cpu)
+    if d.rank == 0:
+        print(json.dumps(line), flush=True)
+    d.close()
+    return 0 if ok else 3
+
+
+def rotator_case(d, args, cpu=True):
     """BASELINE configs[4]: EOFRotator varimax (power=1, max_iter=1000) on 100 modes of a model as wide as config 4
     (loadings 4 147 200 x 100 = 1.66 GB).  value = loadings bytes x iterations / fit time."""
     import xeofs_b200 as xb
 
-    d = Dist()
     torch = d.torch
     peak, peak_src, peaks = load_peak()
     T, n_lat, n_lon, k = C5["T"], int(C5["n_lat"] * args.scale), C5["n_lon"], C5["k"]
@@ -658,8 +694,8 @@ def run_rotator(args):
               "iterations": iters, "iterations_tensor_core": int(getattr(r, "n_iter_tc_", 0)),
               "iterations_single_tf32": int(getattr(r, "n_iter_x1_", 0))}
     parity["ok"] = bool(parity["variance_conserved"]["ok"] and parity["rotation_orthogonal"]["ok"])
-    cpu = None
-    if not args.no_cpu:
+    want_cpu, cpu = cpu, None
+    if want_cpu:
         from threadpoolctl import threadpool_limits
 
         from oracle import rotation as orot
@@ -687,9 +723,9 @@ def run_rotator(args):
         "iterations": iters, "e2e": None, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
         "clocks": clocks, "parity": parity,
     }
-    print(json.dumps(line), flush=True)
-    d.close()
-    return 0 if parity["ok"] else 3
+    del r, model
+    torch.cuda.empty_cache()
+    return line, bool(parity["ok"])
 
 
 def main():
@@ -704,6 +740,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-strong-c4", action="store_true")
+    ap.add_argument("--no-models", action="store_true", help="skip the compact config-3 / config-5 objects of the line")
     ap.add_argument("--strong-workload", default="c4", choices=["c4", "c4mid"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--scale", type=float, default=1.0, help="c3 / c5: shrink the latitude axis (quick looks)")

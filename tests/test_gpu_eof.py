@@ -59,6 +59,16 @@ def test_planted_config1_shape():
     coords = {"lat": np.linspace(75, 15, nlat), "lon": np.arange(nlon) * 2.5}
     o, m = _fit_both(X, coords, k, random_state=5, use_coslat=True)
     _compare(o, m, k)
+    # 1325 features: rows of 5300 bytes are not 16-byte aligned — the field must have been given a padded pitch so that
+    # the tensor-core kernels (TMA descriptors) take it, not the CUDA-core fallback
+    from xeofs_b200._cuda_ops import Field  # noqa: F401
+    f = m.preprocessor.fitted.field
+    assert f.ldx % 4 == 0 and f.X.data_ptr() % 16 == 0 and f.S == nlat * nlon
+    import xeofs_b200._lib as lib
+    m.ops.time_products = True
+    m.ops._prod_events = []
+    W = m.ops.zeros((T, 16))
+    m.ops.project_S(f, W, 10, algo=lib.ALGO_TF32X3)   # raises XEOFS_E_UNSUPPORTED if the tcgen05 path did not apply
 
 
 @pytest.mark.parametrize("missing_sample", [True, False])

@@ -265,6 +265,14 @@ def test_fused_stats_and_first_product(T, S, l, center, standardize):
     got = Yt.cpu().numpy()
     np.testing.assert_allclose(got[:l], want, atol=3e-3 * np.abs(want).max())
     assert (got[l:] == 0).all() and (got[:, ~v] == 0).all()
+    # and the statistics against an fp64 numpy statement of Scaler.fit / total_variance (not only against the library's
+    # own stand-alone kernels): scaler.py:100-108 (mean, std ddof = 0), utils/xarray_utils.py:236-253 (ddof = 1)
+    X64 = X.astype(np.float64)
+    np.testing.assert_array_equal(v, ~np.isnan(X64).all(axis=0))
+    np.testing.assert_allclose(fin["mean"].cpu().numpy()[v], X64[:, v].mean(axis=0), rtol=3e-7)
+    np.testing.assert_allclose(fin["std"].cpu().numpy()[v], X64[:, v].std(axis=0), rtol=3e-5)
+    np.testing.assert_allclose(sc[0], A[:, v].var(axis=0, ddof=1).sum(), rtol=2e-5)
+    assert sc[1] == v.sum()
 
 
 def _varimax_case(ops, S, m, seed):

@@ -7,7 +7,7 @@ for step in "$@"; do
   case $step in
     tests)    timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_pytest.log ;;
     bench)    timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_bench.log ;;
-    benchq)   timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-strong-c4 --no-e2e > gpurun_out/${tag}_benchq.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_benchq.log ;;
+    benchq)   timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-strong-c4 --no-e2e --no-models > gpurun_out/${tag}_benchq.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_benchq.log ;;
     bench_c3) timeout 600 python bench.py --workload c3 --steps 5 --warmup 3 > gpurun_out/${tag}_bench_c3.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_bench_c3.log ;;
     bench_c5) timeout 600 python bench.py --workload c5 --steps 4 --warmup 3 > gpurun_out/${tag}_bench_c5.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_bench_c5.log ;;
     parity)   timeout 1800 python tools/parity_full.py c2 c3 c5 c4n1 > gpurun_out/${tag}_parity.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_parity.log ;;

@@ -5,12 +5,12 @@
 # The raw CSVs are turned into profiles/<tag>_ncu_full_*_summary.csv and profiles/<tag>_traffic.json by tools/ncu_traffic.py.
 tag=$1; shift
 mkdir -p gpurun_out
-Q="--steps 1 --warmup 1 --no-e2e --no-cpu --no-strong-c4"
+Q="--steps 1 --warmup 1 --no-e2e --no-cpu --no-strong-c4 --no-models"
 for wl in "$@"; do
   case $wl in
     c2)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${tag}_launches_c2.csv \
-          python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-strong-c4 > gpurun_out/${tag}_launches_c2.log 2>&1
+          python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-strong-c4 --no-models > gpurun_out/${tag}_launches_c2.log 2>&1
       # warm-up fit = 14 project_tc launches (10 passes + 4 k-column applies); capture the 14 of the timed fit
       timeout 1500 ncu --set full --clock-control none --import-source on -k regex:project_tc_kernel -s 14 -c 14 -f \
           -o gpurun_out/${tag}_full_c2 python bench.py $Q > gpurun_out/${tag}_full_c2.log 2>&1

@@ -41,6 +41,9 @@ class EOFRotator:
         p = self._params
         if m < 2:
             raise ValueError(f"Cannot rotate {m} modes (columns), but must be 2 or more.")
+        if m > 128:
+            raise NotImplementedError(f"rotation of {m} modes: the varimax kernels of this build take at most 128 "
+                                      "(one TMEM lane per mode)")
         _, _, Ln = ops.col_norms(L0, S_local, m, normalized_out=True)
         XtX = ops.gram(Ln, S_local, m, 1)
         comm.sum_(XtX)
