@@ -226,6 +226,31 @@ int xeofs_b200_materialize(const float* X, int64_t T, int64_t S, int64_t ldx, co
                            const float* ccorr, const uint8_t* row_valid, int64_t rows_out, int round_tf32, float* out,
                            int64_t ldo, void* stream);
 
+/* ---- D2: a half-precision copy of the preprocessed matrix for the power iterations ------------------------------
+ * The q power iterations of the range finder (sklearn _randomized_range_finder; call site linalg/decomposer.py:141-146)
+ * only have to keep the right subspace: this build runs them as single TF32 products, which read 11 significant bits
+ * of every operand.  fp16 holds those 11 bits at half the bytes: the first project_T pass of a fit also writes
+ *     A16[t,s] = fp16( (X[t,s] - pivot[s]) e16[s] ),   e16 = dscale c,  c = 2^round(log2(512 / (|dscale| std)))
+ * (round to nearest, NaN -> 0, |value| > 65504 = 127 sigma saturated) and the remaining power-iteration passes stream
+ * that copy through kind::f16 products — half the HBM bytes per pass.  The two passes that decide the singular values
+ * (XEOFS_ALGO_TF32X2 / TF32X3) always read the fp32 field.  Only for centred fields with every sample present.
+ * h16_scales:        e16[s], ic16[s] = 1/c[s] from the Scaler vectors (0 for dropped features).
+ * project_T_h16copy: xeofs_b200_project_T(XEOFS_ALGO_TF32X1) that also writes A16 (T x ldc halves, ldc >= S rounded
+ *                    up to 128, ldc % 8 == 0); no_nan as XEOFS_ALGO_FLAG_NO_NAN.
+ * project_S16 / project_T16: Yt = A^T W / Z = A Y with A[t,s] = A16[t,s] ic16[s] (same layouts and workspace size as
+ *                    project_S / project_T with XEOFS_ALGO_TF32X1).                                                  */
+int xeofs_b200_h16_scales(const float* dscale, const float* std, int64_t S, float* e16, float* ic16, void* stream);
+int xeofs_b200_project_T_h16copy(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
+                                 const float* dscale, const float* Yt, int64_t ldy, int64_t l, float* Z, int64_t ldz,
+                                 void* workspace, int64_t workspace_bytes, int no_nan, const float* e16, void* copy16,
+                                 int64_t ldc, void* stream);
+int xeofs_b200_project_S16(const void* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* W,
+                           int64_t ldw, int64_t l, float* Yt, int64_t ldy, void* workspace, int64_t workspace_bytes,
+                           void* stream);
+int xeofs_b200_project_T16(const void* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* Yt,
+                           int64_t ldy, int64_t l, float* Z, int64_t ldz, void* workspace, int64_t workspace_bytes,
+                           void* stream);
+
 /* ---- M3: the sample Gram matrix A A^T of a preprocessed field as a plain tcgen05 GEMM (kind::f16 on a bf16 copy) ----
  * materialize_bf16: the preprocessed matrix (as xeofs_b200_materialize) rounded to bf16, rows_out x cols_out with zero
  *                   padding (rows_out a multiple of 256, cols_out a multiple of 64 for gram_rows_bf16).

@@ -344,3 +344,51 @@ def test_sample_gram_bf16_gemm(T, S, nan_cols):
     err = np.tril(np.abs(G.cpu().numpy().astype(np.float64) - ref) / np.outer(d, d))
     assert err.max() < 1.5e-4, err.max()
     assert np.median(err[np.tril_indices(T)]) < 1e-5
+
+
+@pytest.mark.parametrize("T,S,l,standardize", [(300, 1000, 10, False), (1000, 4100, 60, True), (777, 2048 + 64, 110, True)])
+def test_half_precision_copy_passes(T, S, l, standardize):
+    """The fp16 copy of the preprocessed matrix (include/xeofs_b200.h): the single-TF32 project_T pass that writes it
+    (xeofs_b200_project_T_h16copy), then project_S16 / project_T16 on the copy (kind::f16), all against the fp64
+    statement at the accuracy of a single TF32 product; a land mask (NaN features) and a feature 1e4 times larger than
+    the rest exercise the per-feature power-of-two scale."""
+    from xeofs_b200 import _lib
+    from xeofs_b200._cuda_ops import CudaOps
+    from xeofs_b200._lib import lpad
+    tc_ops = CudaOps()
+    rng = np.random.default_rng(T + l)
+    X = (280 + 3 * rng.standard_normal((T, S))).astype(np.float32)
+    X[:, 5] = 280 + 3e4 * rng.standard_normal(T)
+    X[:, rng.random(S) < 0.05] = np.nan
+    f, _, _ = _field(tc_ops, X, center=True, standardize=standardize)
+    assert f.ccorr is None or float(f.ccorr.abs().max()) == 0.0
+    f.ccorr = None
+    f.want_h16 = True
+    A = np.nan_to_num(_A_ref(X, center=True, standardize=standardize), nan=0.0)
+    lp = lpad(l)
+    Y = tc_ops.space_side(lp, S, zero=True)
+    Y[:l] = torch.randn((l, S), device="cuda") * torch.logspace(0, -4, l, device="cuda")[:, None]  # graded columns
+    W = torch.zeros((T, lp), device="cuda")
+    W[:, :l] = torch.linalg.qr(torch.randn((T, l), device="cuda", dtype=torch.float64))[0].float()
+    wantT = A @ Y[:l].double().cpu().numpy().T
+    wantS = (A.T @ W[:, :l].double().cpu().numpy()).T
+    colT = np.abs(wantT).max(axis=0)
+    # 1. the pass that writes the copy is an ordinary single-TF32 product
+    Z = tc_ops.project_T(f, Y, l, algo=_lib.ALGO_TF32X1)
+    assert f.h16 is not None and not f.want_h16
+    np.testing.assert_allclose(Z.cpu().numpy()[:, :l] / colT, wantT / colT, atol=3e-3)
+    # the copy itself: A16 ic16 == A to fp16 accuracy (11 bits), zero at the NaN features
+    A16, ic16 = f.h16
+    got = (A16.view(torch.float16)[:, :S].double() * ic16.double()[None, :]).cpu().numpy()
+    scale = np.abs(A).max(axis=0) + 1e-30
+    assert np.max(np.abs(got - A) / scale) < 1e-3
+    # 2. products on the copy
+    Z2 = tc_ops.project_T(f, Y, l, algo=_lib.ALGO_TF32X1)
+    np.testing.assert_allclose(Z2.cpu().numpy()[:, :l] / colT, wantT / colT, atol=3e-3)
+    assert (Z2.cpu().numpy()[:, l:] == 0).all()
+    Yt = tc_ops.project_S(f, W, l, algo=_lib.ALGO_TF32X1)
+    np.testing.assert_allclose(Yt.cpu().numpy()[:l], wantS, atol=3e-3 * np.abs(wantS).max())
+    assert (Yt.cpu().numpy()[l:] == 0).all()
+    # the accurate products never take the copy
+    Z3 = tc_ops.project_T(f, Y, l, algo=_lib.ALGO_TF32X3)
+    np.testing.assert_allclose(Z3.cpu().numpy()[:, :l] / colT, wantT / colT, atol=2e-5)

@@ -6,6 +6,8 @@ test double with the same interface to exercise the host logic on CPU boxes).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -22,6 +24,8 @@ class Field:
 
     def __init__(self, X, pivot, dscale, ccorr, valid, mean=None, std=None, row_valid=None, no_nan=False):
         self.no_nan = no_nan  # True: no NaN anywhere in X (every feature and every sample valid), known to the caller
+        self.want_h16 = False  # set by fit_field: the power iterations may run on an fp16 copy of the matrix
+        self.h16 = None        # (copy (T x pitch) int16 view, ic16) once the first fast project_T has written it
         self.X = X
         self.T, self.S = int(X.shape[0]), int(X.shape[1])
         self.ldx = int(X.stride(0))
@@ -55,6 +59,7 @@ class CudaOps:
         self._ws = None
         self._vws = None
         self._unit = None
+        self.use_h16 = os.environ.get("XEOFS_H16", "1") != "0"  # fp16 copy of the matrix for the power iterations
         self.launches = 0  # kernels enqueued through this object (bench.py reports it)
         self.time_products = False  # bench.py: CUDA events around every streaming product on the launch stream
         self._prod_events = []
@@ -176,6 +181,14 @@ class CudaOps:
                 w = min(BLOCK_L, l - j0)
                 self.project_S(f, W[:, j0:], w, algo=algo, out=Yt[j0:j0 + lpad(w)], tag=tag)
             return Yt
+        if f.h16 is not None and algo in self._fast_algos and tag == "project_S":
+            A16, ic16 = f.h16
+            ws = self.workspace(f.T, f.S, l, _lib.ALGO_TF32X1)
+            check(self._timed("project_S_h16", l, lambda: self.lib.xeofs_b200_project_S16(
+                ptr(A16), f.T, f.S, int(A16.stride(0)), ptr(ic16), ptr(W), int(W.stride(0)), l, ptr(Yt),
+                int(Yt.stride(0)), ptr(ws), ws.numel(), self._stream())), "project_S16")
+            self.launches += 6
+            return Yt
         ws = self.workspace(f.T, f.S, l, algo)
         check(self._timed(tag + self._algo_tag(algo), l, lambda: self.lib.xeofs_b200_project_S(
             ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(f.ccorr), ptr(f.row_valid), ptr(W),
@@ -194,6 +207,25 @@ class CudaOps:
                 w = min(BLOCK_L, l - j0)
                 self.project_T(f, Yt[j0:], w, algo=algo, out=Z[:, j0:j0 + lpad(w)])
             return Z
+        if algo in self._fast_algos and (f.h16 is not None or f.want_h16):
+            ws = self.workspace(f.T, f.S, l, _lib.ALGO_TF32X1)
+            if f.h16 is not None:
+                A16, ic16 = f.h16
+                check(self._timed("project_T_h16", l, lambda: self.lib.xeofs_b200_project_T16(
+                    ptr(A16), f.T, f.S, int(A16.stride(0)), ptr(ic16), ptr(Yt), int(Yt.stride(0)), l, ptr(Z),
+                    int(Z.stride(0)), ptr(ws), ws.numel(), self._stream())), "project_T16")
+                self.launches += 7
+                return Z
+            made = self._make_h16(f)
+            if made is not None:
+                A16, e16, ic16 = made
+                check(self._timed("project_T_wcopy", l, lambda: self.lib.xeofs_b200_project_T_h16copy(
+                    ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(Yt), int(Yt.stride(0)), l, ptr(Z),
+                    int(Z.stride(0)), ptr(ws), ws.numel(), int(f.no_nan), ptr(e16), ptr(A16), int(A16.stride(0)),
+                    self._stream())), "project_T_h16copy")
+                f.h16 = (A16, ic16)
+                self.launches += 3
+                return Z
         ws = self.workspace(f.T, f.S, l, algo)
         flag = _lib.ALGO_FLAG_NO_NAN if (f.no_nan and f.row_valid is None) else 0
         check(self._timed("project_T" + self._algo_tag(algo), l, lambda: self.lib.xeofs_b200_project_T(
@@ -202,6 +234,28 @@ class CudaOps:
             ptr(Z), int(Z.stride(0)), ptr(ws), ws.numel(), algo | flag, self._stream())), "project_T")
         self.launches += 2 + (2 if f.ccorr is not None else 0)
         return Z
+
+    _fast_algos = (_lib.ALGO_AUTO_FAST, _lib.ALGO_TF32X1)
+    h16_min_bytes = 1 << 28  # fields below 256 MB are not worth a copy
+
+    def _make_h16(self, f: Field):
+        """Buffers for the fp16 copy of a field's preprocessed matrix (include/xeofs_b200.h, 'a half-precision copy'):
+        (copy, e16, ic16), or None where it does not apply — un-centred fields (rank-1 term), missing samples, no
+        tensor-core path, not enough free memory — in which case the field is not asked again."""
+        f.want_h16 = False
+        if (f.ccorr is not None or f.row_valid is not None or f.std is None
+                or not bool(self.lib.xeofs_b200_has_tcgen05()) or f.ldx % 4 != 0 or f.X.data_ptr() % 16 != 0):
+            return None
+        pitch = (f.S + 127) // 128 * 128
+        free, _ = torch.cuda.mem_get_info(self.device)
+        cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        if f.T * pitch * 2 + (4 << 30) > free + cached:
+            return None
+        A16 = torch.empty((f.T, pitch), dtype=torch.int16, device=self.device)
+        e16, ic16 = self.empty(f.S), self.empty(f.S)
+        check(self.lib.xeofs_b200_h16_scales(ptr(f.dscale), ptr(f.std), f.S, ptr(e16), ptr(ic16), self._stream()),
+              "h16_scales")
+        return A16, e16, ic16
 
     def round_tf32_(self, M, rows, cols):
         """In place: keep the TF32 bits of every value (so that ALGO_TF32X2 products with M are exact)."""

@@ -139,6 +139,9 @@ def fit_field(ops, X, featw=None, center=True, standardize=False, check_nans=Tru
     row_valid = valid_sample.to(torch.uint8) if n_samples < T else None
     ff.field = Field(X, fin["pivot"], fin["dscale"], ccorr, fin["valid"], fin["mean"], fin["std"], row_valid,
                      no_nan=(n_valid == S_global and n_samples == T))
+    # the power iterations may stream an fp16 copy of the preprocessed matrix (written by their first time-side pass)
+    ff.field.want_h16 = bool(center and row_valid is None and T * S * 4 >= getattr(ops, "h16_min_bytes", 1 << 62)
+                             and getattr(ops, "use_h16", True))
     ff.mean, ff.std, ff.valid, ff.featw = fin["mean"], fin["std"], fin["valid"], featw
     ff.valid_sample, ff.n_samples, ff.n_features = valid_sample, n_samples, n_valid
     ff.total_variance = total_variance

@@ -35,11 +35,19 @@ int project_T_simt(const float*, int64_t, int64_t, int64_t, const float*, const 
                    const float*, int64_t, int64_t, float*, int64_t, float*, cudaStream_t);
 // project_tc.cu
 bool tc_supported(int64_t T, int64_t S, int64_t ldx, const float* X, int64_t l);
+bool tensor_maps_available();
+static inline bool tensor_maps_ok() { return tensor_maps_available(); }
 int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo);
 int project_S_tc(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const uint8_t*,
                  const float*, int64_t, int64_t, float*, int64_t, void*, int64_t, int, cudaStream_t);
 int project_T_tc(const float*, int64_t, int64_t, int64_t, const float*, const float*, const float*, const uint8_t*,
-                 const float*, int64_t, int64_t, float*, int64_t, void*, int64_t, int, bool, cudaStream_t);
+                 const float*, int64_t, int64_t, float*, int64_t, void*, int64_t, int, bool, cudaStream_t, uint16_t*, int64_t,
+                 const float*);
+int h16_scales(const float*, const float*, int64_t, float*, float*, cudaStream_t);
+int project_S16_tc(const uint16_t*, int64_t, int64_t, int64_t, const float*, const float*, int64_t, int64_t, float*, int64_t,
+                   void*, cudaStream_t);
+int project_T16_tc(const uint16_t*, int64_t, int64_t, int64_t, const float*, const float*, int64_t, int64_t, float*, int64_t,
+                   void*, cudaStream_t);
 
 int project_S_stats_tc(const float*, int64_t, int64_t, int64_t, const double*, int, const float*, int64_t, int64_t, float*,
                        float*, uint8_t*, float*, float*, float*, double*, int32_t*, float*, int64_t, void*, cudaStream_t);
@@ -149,7 +157,63 @@ extern "C" int xeofs_b200_project_T(const float* X, int64_t T, int64_t S, int64_
     return XEOFS_E_UNSUPPORTED;
   }
   return project_T_tc(X, T, S, ldx, pivot, dscale, ccorr, row_valid, Yt, ldy, l, Z, ldz, workspace, workspace_bytes, algo,
-                      no_nan, stream);
+                      no_nan, stream, nullptr, 0, nullptr);
+}
+
+// ---- the half-precision copy for the power iterations (include/xeofs_b200.h)
+extern "C" int xeofs_b200_h16_scales(const float* dscale, const float* std, int64_t S, float* e16, float* ic16, void* stream_) {
+  XB_CHECK_ARG(dscale && std && e16 && ic16 && S > 0, "h16_scales: bad arguments");
+  return h16_scales(dscale, std, S, e16, ic16, (cudaStream_t)stream_);
+}
+
+extern "C" int xeofs_b200_project_T_h16copy(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
+                                            const float* dscale, const float* Yt, int64_t ldy, int64_t l, float* Z,
+                                            int64_t ldz, void* workspace, int64_t workspace_bytes, int no_nan,
+                                            const float* e16, void* copy16, int64_t ldc, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_project_args("project_T_h16copy", X, T, S, ldx, pivot, dscale, Yt, Z, ldy, ldz, l, workspace, workspace_bytes,
+                              XEOFS_ALGO_TF32X1);
+  if (rc) return rc;
+  XB_CHECK_ARG(e16 && copy16 && ((uintptr_t)copy16 % 16 == 0) && ldz >= lpad(l) && ldy >= S, "project_T_h16copy: bad arguments");
+  if (!xeofs_b200_has_tcgen05() || !tc_supported(T, S, ldx, X, l)) {
+    set_error("project_T_h16copy: needs the tcgen05 path");
+    return XEOFS_E_UNSUPPORTED;
+  }
+  return project_T_tc(X, T, S, ldx, pivot, dscale, nullptr, nullptr, Yt, ldy, l, Z, ldz, workspace, workspace_bytes,
+                      XEOFS_ALGO_TF32X1, no_nan != 0, stream, (uint16_t*)copy16, ldc, e16);
+}
+
+static int check_h16_args(const char* who, const void* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const void* a,
+                          const void* b, int64_t l, void* ws, int64_t ws_bytes) {
+  XB_CHECK_ARG(A16 && ic16 && a && b && ws && T > 0 && S > 0 && l > 0 && l <= 128, "%s: bad arguments", who);
+  XB_CHECK_ARG(ldc >= S && ldc % 8 == 0 && ((uintptr_t)A16 % 16 == 0) && ((uintptr_t)ws % 256 == 0), "%s: misaligned copy / workspace", who);
+  if (ws_bytes < xeofs_b200_project_workspace_bytes(T, S, l, XEOFS_ALGO_TF32X1)) {
+    set_error("%s: workspace too small", who);
+    return XEOFS_E_WORKSPACE;
+  }
+  if (!xeofs_b200_has_tcgen05() || !tensor_maps_ok()) {
+    set_error("%s: needs the tcgen05 path", who);
+    return XEOFS_E_UNSUPPORTED;
+  }
+  return XEOFS_OK;
+}
+
+extern "C" int xeofs_b200_project_S16(const void* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* W,
+                                      int64_t ldw, int64_t l, float* Yt, int64_t ldy, void* workspace, int64_t workspace_bytes,
+                                      void* stream_) {
+  int rc = check_h16_args("project_S16", A16, T, S, ldc, ic16, W, Yt, l, workspace, workspace_bytes);
+  if (rc) return rc;
+  XB_CHECK_ARG(ldw >= lpad(l) && ldy >= S, "project_S16: ldw=%lld must be >= lp and ldy=%lld >= S", (long long)ldw, (long long)ldy);
+  return project_S16_tc((const uint16_t*)A16, T, S, ldc, ic16, W, ldw, l, Yt, ldy, workspace, (cudaStream_t)stream_);
+}
+
+extern "C" int xeofs_b200_project_T16(const void* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* Yt,
+                                      int64_t ldy, int64_t l, float* Z, int64_t ldz, void* workspace, int64_t workspace_bytes,
+                                      void* stream_) {
+  int rc = check_h16_args("project_T16", A16, T, S, ldc, ic16, Yt, Z, l, workspace, workspace_bytes);
+  if (rc) return rc;
+  XB_CHECK_ARG(ldz >= lpad(l) && ldy >= S, "project_T16: ldz=%lld must be >= lp and ldy=%lld >= S", (long long)ldz, (long long)ldy);
+  return project_T16_tc((const uint16_t*)A16, T, S, ldc, ic16, Yt, ldy, l, Z, ldz, workspace, (cudaStream_t)stream_);
 }
 
 extern "C" int xeofs_b200_project_S_stats(const float* X, int64_t T, int64_t S, int64_t ldx, const double* featw, int flags,

@@ -76,6 +76,8 @@ struct TcParams {
   const float* bimg_lo; //   [slab][lp rows][32 k], 16-byte chunks XOR-swizzled by (row & 7)  (lo: 3xTF32 only)
   int b_bulk;           // fetch the operand image of a stage with one bulk copy (else: tensor-map rows of 1 KB)
   int cl;               // CTAs per cluster (1, 2 or 4): they share the operand image through TMA multicast
+  uint16_t* copy16;     // MODE_WCOPY: the fp16 copy this pass writes (T x ldc16)
+  int64_t ldc16;
 };
 
 
@@ -97,10 +99,25 @@ struct TcParams {
 // TF32-exact (NS == 2).
 // RN = 2 (XEOFS_ALGO_TF32X1F): the field is a materialised, already TF32-rounded copy of the preprocessed matrix (pivot 0,
 // dscale 1, no NaN): the operand stage only moves it from shared memory into TMEM; accumulators flushed as for RN = 1.
-template <int NS, bool SIDE_T, int KB, bool STATS = false, int RN = 0, bool PK = false, bool TFAST = false>
+// MODE (single TF32 only) — the half-precision copy of the preprocessed matrix for the power iterations:
+//   MODE_WCOPY  project_T, fp32 field: besides its product the pass writes A16[t,s] = fp16((X[t,s] - pivot[s]) e16[s]),
+//               e16 = dscale x a power of two per feature that puts the column's standard deviation at 512 (values up
+//               to 127 sigma representable, beyond that saturated); NaN -> 0.
+//   MODE_H16    the field IS that copy (T x S fp16, features contiguous): the operand stage is a plain move of packed
+//               pairs into TMEM, the products are kind::f16 (K = 16 per instruction, a slab = 64 K values = the same
+//               128 bytes per row and 32 TMEM columns as 32 fp32 values), the small operand's image is fp16.
+//               fp16 holds the 11 significant bits the tensor core reads of a TF32 operand — rounded to nearest here,
+//               truncated there — so these passes lose nothing against the single-TF32 ones and move half the bytes.
+constexpr int MODE_F32 = 0, MODE_WCOPY = 1, MODE_H16 = 2;
+
+template <int NS, bool SIDE_T, int KB, bool STATS = false, int RN = 0, bool PK = false, bool TFAST = false, int MODE = MODE_F32>
 __global__ void __launch_bounds__(tc_threads(tc_wide(NS, SIDE_T, RN != 0)), (NS == 1 && !SIDE_T && RN == 0) ? 2 : 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBhi,
                   const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
+  static_assert(MODE == MODE_F32 || (NS == 1 && RN == 0 && !STATS && !PK), "the fp16 copy serves the single-product passes");
+  static_assert(MODE != MODE_WCOPY || SIDE_T, "the copy is written by the first project_T pass");
+  constexpr bool H16 = MODE == MODE_H16;
+  constexpr int KEL = H16 ? 2 * TC_KC : TC_KC;      // K values per slab (32 fp32 or 64 fp16: 128 bytes either way)
   static_assert(SIDE_T || KB == 1, "project_S stages are 32 rows of t");
   static_assert(!STATS || (NS == 1 && !SIDE_T), "the statistics ride on the first (single TF32) project_S pass");
   static_assert(!PK || NS == 3, "operand packing is the 3xTF32 mode's");
@@ -164,7 +181,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   if (warp == 0) {
     // ===================================================================== TMA producer
     // the whole warp walks the ring; one elected lane issues
-    const uint32_t tx = XB + bbytes * BPART * KB + (SIDE_T ? KB * 256 : 0);
+    const uint32_t tx = XB + bbytes * BPART * KB + ((SIDE_T && !H16) ? KB * 256 : 0);
     const int tile0i = (int)tile0;
     Pipe pp;
     for (int c = 0; c < nchunks; ++c, pp.advance(stages)) {
@@ -175,11 +192,11 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         uint8_t* b = bs + (size_t)st * BPART * KB * bbytes;
         const int brow = (chunk0 + c) * KB * (lp >> 3);
         if (!SIDE_T) {
-          tma_load_2d(xs + (size_t)st * XB, &mapX, tile0i, c * TC_KC, &full[st], HINT_EVICT_FIRST);
+          tma_load_2d(xs + (size_t)st * XB, &mapX, tile0i, c * KEL, &full[st], HINT_EVICT_FIRST);
         } else {
-          const int k0 = (chunk0 + c) * TC_KC * KB;
+          const int k0 = (chunk0 + c) * KEL * KB;
           tma_load_2d(xs + (size_t)st * XB, &mapX, k0, tile0i, &full[st], HINT_EVICT_FIRST);
-          bulk_load_1d(pd + st * KB * 256, p.pivot + 2 * k0, KB * 256, &full[st]);
+          if (!H16) bulk_load_1d(pd + st * KB * 256, p.pivot + 2 * k0, KB * 256, &full[st]);
         }
         // the images of consecutive slabs are contiguous in global memory: one bulk copy brings the stage's operand
         // (packed: [hi rows | lo rows] per slab, one copy for both parts) instead of lp/8 tensor-map rows of 1 KB —
@@ -210,7 +227,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     {
-      const uint32_t idesc = make_idesc(lp);
+      const uint32_t idesc = H16 ? make_idesc_f16(lp) : make_idesc(lp);
       const uint32_t idesc2 = make_idesc(2 * lp);  // packed: N = 2 lp
       Pipe pp;
       int g = 0, cg = 0;  // flush group and stage within it (NS == 3)
@@ -242,6 +259,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
               if (PK) {
                 mma_tf32_ts(d_tmem, a, dh + 2 * k, idesc2, !(first && kb == 0 && k == 0));  // a_hi [b_hi | b_lo]
                 mma_tf32_ts(d_tmem, a + TC_KC * KB, dh + 2 * k, idesc, 1);                  // a_lo b_hi
+              } else if (H16) {
+                mma_f16_ts(d_tmem, a, dh + 2 * k, idesc, !(first && kb == 0 && k == 0));  // K = 16: 8 columns of pairs
               } else {
                 mma_tf32_ts(d_tmem, a, dh + 2 * k, idesc, !(first && kb == 0 && k == 0));
                 if (NS == 3) mma_tf32_ts(d_tmem, a, dl + 2 * k, idesc, 1);
@@ -269,7 +288,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const int row = q * 32 + lane;      // row of D / TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float piv = 0.f;
-    if (!SIDE_T && !STATS) piv = (tile0 + row < p.S) ? p.pivot[tile0 + row] : 0.f;
+    if (!SIDE_T && !STATS && !H16) piv = (tile0 + row < p.S) ? p.pivot[tile0 + row] : 0.f;
     // fused statistics: the first sample is the shift of the sums and the pivot of this pass
     bool n0 = false;           // the first sample of this feature is NaN
     double sum1 = 0.0, sum2 = 0.0;
@@ -330,7 +349,14 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
         uint32_t hi[KW], lo[KW];
-        if (!SIDE_T) {
+        if (!SIDE_T && H16) {
+          // X stage = [64 t][128 s] fp16; this thread owns column `row`: TMEM column i of the slab holds the pair
+          // (t = 2i, 2i + 1), this warp converts columns part*KW .. +KW-1
+          const uint32_t src = xs_u32 + st * XB + (part * KW * 2) * (TC_TILE * 2) + row * 2;
+#pragma unroll
+          for (int r = 0; r < KW; ++r)
+            hi[r] = lds16(src + (2 * r) * (TC_TILE * 2)) | (lds16(src + (2 * r + 1) * (TC_TILE * 2)) << 16);
+        } else if (!SIDE_T) {
           // X stage = [32 t][128 s] fp32; this thread owns column `row`, rows part*KW .. +KW-1
           const uint32_t src = xs_u32 + st * XB + ((part * KW) * TC_TILE + row) * 4;
           float v[KW];
@@ -398,24 +424,27 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           const uint32_t src = xs_u32 + st * XB + row * XPITCH + kb * 128;
           const uint32_t pv = pd_u32 + st * KB * 256 + kb * 256;
           constexpr bool FOLD = NS != 2;  // dscale lives in the small operand's image
+          uint32_t cw[KW / 2 > 0 ? KW / 2 : 1];  // MODE_WCOPY: the packed fp16 pairs of this thread's values
 #pragma unroll
           for (int cc = 0; cc < KW / 4; ++cc) {
             const int ch = part * (KW / 4) + cc;
             const float4 x = lds128(src + ch * 16);
-            if (RN == 2) {  // materialised, rounded field: a plain move
+            if (RN == 2 || H16) {  // materialised field (rounded fp32 copy, or packed fp16 pairs): a plain move
               hi[cc * 4 + 0] = __float_as_uint(x.x); hi[cc * 4 + 1] = __float_as_uint(x.y);
               hi[cc * 4 + 2] = __float_as_uint(x.z); hi[cc * 4 + 3] = __float_as_uint(x.w);
               continue;
             }
             const float4 pq = lds128(pv + ch * 16);
             float4 dq = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (!FOLD) dq = lds128(pv + 128 + ch * 16);
+            if (!FOLD || MODE == MODE_WCOPY) dq = lds128(pv + 128 + ch * 16);  // (WCOPY: the slot carries e16)
             const float xa[4] = {x.x, x.y, x.z, x.w}, pa[4] = {pq.x, pq.y, pq.z, pq.w}, da[4] = {dq.x, dq.y, dq.z, dq.w};
+            float wv[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float v = xa[e] - pa[e];
               if (!FOLD) v *= da[e];
               if (!TFAST) v = (fabsf(v) <= 3.4028234e38f) ? v : 0.f;
+              if (MODE == MODE_WCOPY) wv[e] = v;
               if (NS >= 2) {
                 hi[cc * 4 + e] = __float_as_uint(v) & 0xffffe000u;
                 lo[cc * 4 + e] = __float_as_uint(v - __uint_as_float(hi[cc * 4 + e]));
@@ -423,6 +452,17 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 hi[cc * 4 + e] = RN == 1 ? to_tf32(v) : __float_as_uint(v);
               }
             }
+            if (MODE == MODE_WCOPY) {
+              cw[cc * 2] = pack_h2(wv[0] * da[0], wv[1] * da[1]);
+              cw[cc * 2 + 1] = pack_h2(wv[2] * da[2], wv[3] * da[3]);
+            }
+          }
+          if (MODE == MODE_WCOPY && tile0 + row < p.T) {
+            // this thread's KW values of the slab: KW * 2 contiguous bytes of its row of the copy
+            uint16_t* dst = p.copy16 + (tile0 + row) * p.ldc16 + ((int64_t)(chunk0 + c) * KB + kb) * TC_KC + part * KW;
+#pragma unroll
+            for (int i = 0; i < KW / 8; ++i)
+              *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(cw[i * 4], cw[i * 4 + 1], cw[i * 4 + 2], cw[i * 4 + 3]);
           }
         }
         tmem_st<KW>(a_slot + kb * TC_KC, hi);
@@ -517,9 +557,11 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           if (ok) {
             // an invalid feature (dscale 0) gives a zero row even if its accumulator holds NaN
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
+            for (int e = 0; e < 4; ++e) {
+              if (H16) v[e] *= p.wsum[j0 + e];  // undo the power-of-two column scale of the fp16 operand image
               p.out[(int64_t)(j0 + e) * p.ldo + rrow] =
                   ds != 0.f ? fmaf(ds, v[e], (STATS || p.ccorr) ? cs * p.wsum[j0 + e] : 0.f) : 0.f;
+            }
           }
         } else {
           *reinterpret_cast<float4*>(dstT + j0) = make_float4(v[0], v[1], v[2], v[3]);
@@ -610,14 +652,98 @@ tile_Y_kernel(const float* __restrict__ Yt, int64_t S, int64_t ldy, int lp, floa
 // Z[t, j] = sum_split P[split][t][j] + r[j]   (r only on the valid samples)
 __global__ void reduce_partials_kernel(const float* __restrict__ P, int splits, int64_t rows_pad, int lp, int64_t T,
                                        const float* __restrict__ r, const uint8_t* __restrict__ row_valid,
-                                       float* __restrict__ Z, int64_t ldz) {
+                                       float* __restrict__ Z, int64_t ldz, const float* __restrict__ colfac = nullptr) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T * lp) return;
   const int64_t t = i / lp;
   const int j = (int)(i % lp);
   float acc = (r && (!row_valid || row_valid[t])) ? r[j] : 0.f;
   for (int s = 0; s < splits; ++s) acc += P[((int64_t)s * rows_pad + t) * lp + j];
-  Z[t * ldz + j] = acc;
+  Z[t * ldz + j] = colfac ? acc * colfac[j] : acc;
+}
+
+// ------------------------------------------------------------------------------------------------ fp16 path helpers
+// Offset (in halves) of element (row j, k) inside the fp16 image of one 64-wide K slab: [rows][64 k], 16-byte chunks
+// (8 halves) XOR-swizzled by (row & 7) — the K-major SWIZZLE_128B layout.
+__device__ __forceinline__ int img16_offset(int j, int kk) { return j * 64 + ((((kk >> 3) ^ (j & 7)) << 3) | (kk & 7)); }
+
+// e16[s] = dscale[s] c[s], ic16[s] = 1 / c[s] with c = 2^round(log2(512 / (|dscale| std))): the copy's columns get a
+// standard deviation of ~512 (fp16: +-65504 = 127 sigma, full 11 bits down to 1e-7 sigma); dropped features: 0
+__global__ void h16_scales_kernel(const float* __restrict__ dscale, const float* __restrict__ stdv, int64_t S,
+                                  float* __restrict__ e16, float* __restrict__ ic16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S) return;
+  const float d = dscale[i], sd = stdv[i];
+  float e = 0.f, ic = 0.f;
+  if (d != 0.f && sd == sd && sd > 0.f) {
+    int k = (int)rintf(log2f(512.f / (fabsf(d) * sd)));
+    k = max(-60, min(60, k));
+    e = ldexpf(d, k);
+    ic = ldexpf(1.f, -k);
+  }
+  e16[i] = e;
+  ic16[i] = ic;
+}
+
+// amax[j] = max_n |M(n, j) f(n)| over a k-column matrix (side 0: time-side n x ld, f = 1; side 1: space-side, f = fac)
+__global__ void __launch_bounds__(256)
+absmax_cols_kernel(const float* __restrict__ M, int64_t n, int64_t ld, int lp, int side, const float* __restrict__ fac,
+                   float* __restrict__ amax) {
+  if (side == 1) {
+    const int j = blockIdx.y;
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      m = fmaxf(m, fabsf(M[(int64_t)j * ld + i] * (fac ? fac[i] : 1.f)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(&amax[j]), __float_as_int(m));
+  } else {
+    // consecutive threads walk a row; thread t owns column t % lp for rows t / lp + i * (256 / lp)... simple version:
+    for (int j = threadIdx.x; j < lp; j += blockDim.x) {
+      float m = 0.f;
+      for (int64_t i = blockIdx.x; i < n; i += gridDim.x) m = fmaxf(m, fabsf(M[i * ld + j]));
+      if (m > 0.f) atomicMax(reinterpret_cast<int*>(&amax[j]), __float_as_int(m));
+    }
+  }
+}
+__global__ void recip_kernel(const float* __restrict__ a, int n, float* __restrict__ o) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) o[j] = 1.f / a[j];
+}
+// gs[j] = the power of two that brings amax[j] to ~2^12 (1 for an empty column)
+__global__ void h16_colscale_kernel(const float* __restrict__ amax, int lp, float* __restrict__ gs) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= lp) return;
+  const float a = amax[j];
+  int k = 0;
+  if (a > 0.f && a == a && a < 3.0e38f) k = max(-100, min(100, 12 - (int)ceilf(log2f(a))));
+  gs[j] = ldexpf(1.f, k);
+}
+// W (T x ldw, time-side) -> fp16 images of the 64-wide K slabs of W^T (K = t), column j scaled by gs[j].  Zero beyond T.
+__global__ void __launch_bounds__(256)
+prep_W16_kernel(const float* __restrict__ W, int64_t T, int64_t ldw, int lp, const float* __restrict__ gs,
+                uint16_t* __restrict__ img) {
+  const int64_t t0 = (int64_t)blockIdx.x * 64;
+  uint16_t* o = img + (size_t)blockIdx.x * lp * 64;
+  for (int idx = threadIdx.x; idx < lp * 64; idx += 256) {
+    const int kk = idx / lp, j = idx % lp;  // consecutive threads walk a row of W
+    const int64_t t = t0 + kk;
+    const float v = t < T ? W[t * ldw + j] * gs[j] : 0.f;
+    o[img16_offset(j, kk)] = (uint16_t)(pack_h2(v, 0.f) & 0xffffu);
+  }
+}
+// Yt (lp x ldy, space-side) -> fp16 images of its 64-wide K slabs (K = s): Yt[j,s] ic16[s] gs[j].  Zero beyond S.
+__global__ void __launch_bounds__(256)
+tile_Y16_kernel(const float* __restrict__ Yt, int64_t S, int64_t ldy, int lp, const float* __restrict__ ic16,
+                const float* __restrict__ gs, uint16_t* __restrict__ img) {
+  const int64_t s0 = (int64_t)blockIdx.x * 64;
+  uint16_t* o = img + (size_t)blockIdx.x * lp * 64;
+  const int kk = threadIdx.x & 63;
+  const float f = (s0 + kk < S) ? ic16[s0 + kk] : 0.f;
+  for (int j = threadIdx.x >> 6; j < lp; j += 4) {
+    const float v = (s0 + kk < S) ? Yt[(int64_t)j * ldy + s0 + kk] * f * gs[j] : 0.f;
+    o[img16_offset(j, kk)] = (uint16_t)(pack_h2(v, 0.f) & 0xffffu);
+  }
 }
 
 // project_simt.cu
@@ -681,6 +807,25 @@ int make_map2(CUtensorMap* m, const float* base, int64_t inner, int64_t outer, i
   const int64_t dims[2] = {inner, outer}, str[1] = {ld};
   const int box[2] = {box_inner, box_outer};
   return make_map(m, base, 2, dims, str, box, swizzle);
+}
+
+// 16-bit tensor map of rank 2 (the fp16 copy of the preprocessed matrix), no swizzle, OOB -> 0
+static int make_map16(CUtensorMap* m, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return XEOFS_E_UNSUPPORTED;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer}, gstr[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t bx[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer}, estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, (void*)base, gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (16-bit) failed (%d): extent %lld x %lld box %d x %d", (int)r, (long long)inner,
+              (long long)outer, box_inner, box_outer);
+    return XEOFS_E_CUDA;
+  }
+  return XEOFS_OK;
 }
 
 bool tensor_maps_available() { return get_encode() != nullptr; }
@@ -754,12 +899,12 @@ static int pick_cluster() {
   const int c = env_int("XEOFS_TC_CLUSTER", 1);
   return c == 4 ? 4 : c == 2 ? 2 : 1;
 }
-static TGeom t_geometry(int64_t T, int64_t S, int cap, int kb, int cl = 1) {
+static TGeom t_geometry(int64_t T, int64_t S, int cap, int kb, int cl = 1, int kel = TC_KC) {
   TGeom g;
   g.t_tiles = round_up(ceil_div(T, TC_TILE), cl);  // whole clusters along the row tiles (the extra tiles hold no rows)
   g.rows_pad = g.t_tiles * TC_TILE;
   g.Spad = round_up(S, 128);  // covers every KB
-  g.chunks_total = (int)ceil_div(S, TC_KC * kb);
+  g.chunks_total = (int)ceil_div(S, kel * kb);  // kel: K values per slab (32 fp32, 64 fp16)
   int64_t want = ceil_div(2 * (int64_t)num_sms(), g.t_tiles);
   if (want < 1) want = 1;
   if (want > g.chunks_total) want = g.chunks_total;
@@ -815,11 +960,23 @@ static int launch_kernel(TcKernel kern, int threads, const CUtensorMap& mx, cons
   return XEOFS_OK;
 }
 
-template <int NS, bool SIDE_T, int KB, int RN = 0, bool PK = false, bool TFAST = false>
+template <int NS, bool SIDE_T, int KB, int RN = 0, bool PK = false, bool TFAST = false, int MODE = MODE_F32>
 static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p, dim3 grid,
                      size_t smem, cudaStream_t stream) {
-  return launch_kernel(project_tc_kernel<NS, SIDE_T, KB, false, RN, PK, TFAST>, tc_threads(tc_wide(NS, SIDE_T, RN != 0)), mx, mh, ml,
-                       p, grid, smem, stream);
+  return launch_kernel(project_tc_kernel<NS, SIDE_T, KB, false, RN, PK, TFAST, MODE>, tc_threads(tc_wide(NS, SIDE_T, RN != 0)), mx,
+                       mh, ml, p, grid, smem, stream);
+}
+// project_T, single product, with MODE (the pass that writes the fp16 copy / the passes that read it)
+template <int MODE>
+static int launch_T_mode(int kb, bool fast, const CUtensorMap& mx, const CUtensorMap& mh, const TcParams& p, dim3 grid,
+                         size_t smem, cudaStream_t stream) {
+  if (fast || MODE == MODE_H16)
+    return kb == 1   ? launch_tc<1, true, 1, 0, false, true, MODE>(mx, mh, mh, p, grid, smem, stream)
+           : kb == 2 ? launch_tc<1, true, 2, 0, false, true, MODE>(mx, mh, mh, p, grid, smem, stream)
+                     : launch_tc<1, true, 4, 0, false, true, MODE>(mx, mh, mh, p, grid, smem, stream);
+  return kb == 1   ? launch_tc<1, true, 1, 0, false, false, MODE>(mx, mh, mh, p, grid, smem, stream)
+         : kb == 2 ? launch_tc<1, true, 2, 0, false, false, MODE>(mx, mh, mh, p, grid, smem, stream)
+                   : launch_tc<1, true, 4, 0, false, false, MODE>(mx, mh, mh, p, grid, smem, stream);
 }
 // project_T: pick the instantiation for (KB, no-NaN promise)
 template <int NS, int RN, bool PK>
@@ -957,7 +1114,8 @@ int project_S_stats_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const 
 
 int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot, const float* dscale,
                  const float* ccorr, const uint8_t* row_valid, const float* Yt, int64_t ldy, int64_t l, float* Z,
-                 int64_t ldz, void* workspace, int64_t workspace_bytes, int algo, bool no_nan, cudaStream_t stream) {
+                 int64_t ldz, void* workspace, int64_t workspace_bytes, int algo, bool no_nan, cudaStream_t stream,
+                 uint16_t* copy16, int64_t ldc16, const float* e16) {
   (void)workspace_bytes;
   const int lp = (int)lpad(l);
   const int ns = algo_ns(algo);
@@ -974,7 +1132,8 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   const bool pk = use_pack(ns, lp);
   float* Yhi = (float*)ws; ws += align256(lp * g.Spad * 4);
   float* Ylo = ns == 3 ? (pk ? Yhi + lp * 32 : (float*)ws) : nullptr;
-  pad_vectors_kernel<<<(unsigned)ceil_div(g.Spad, 256), 256, 0, stream>>>(pivot, dscale, S, g.Spad, pdpad);
+  // (the pass that writes the fp16 copy carries e16 where dscale would go: dscale itself rides on the operand image)
+  pad_vectors_kernel<<<(unsigned)ceil_div(g.Spad, 256), 256, 0, stream>>>(pivot, copy16 ? e16 : dscale, S, g.Spad, pdpad);
   XB_LAUNCH_CHECK();
   tile_Y_kernel<<<(unsigned)(g.Spad / TC_KC), 256, 0, stream>>>(Yt, S, ldy, lp, Yhi, Ylo, algo_rn(algo) == 1 ? 1 : 0,
                                                                 pk ? 2 * lp * 32 : 0, (ns != 2 && algo_rn(algo) != 2) ? dscale : nullptr);
@@ -1008,7 +1167,12 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
     if (rc) return rc;
   }
   const bool fast = no_nan && !row_valid;
-  if (ns == 3 && pk) rc = launch_T<3, 0, true>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
+  p.copy16 = copy16; p.ldc16 = ldc16;
+  if (copy16) {
+    XB_CHECK_ARG(ns == 1 && algo_rn(algo) == 0 && !ccorr && !row_valid && e16 && ldc16 >= g.Spad && ldc16 % 8 == 0,
+                 "project_T: the fp16 copy is written by a single-TF32 pass over a centred field with every sample present");
+    rc = launch_T_mode<MODE_WCOPY>(kb, fast, mx, mh, p, grid, sh.smem, stream);
+  } else if (ns == 3 && pk) rc = launch_T<3, 0, true>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
   else if (ns == 3) rc = launch_T<3, 0, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
   else if (ns == 2) rc = launch_T<2, 0, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
   else if (algo_rn(algo) == 1) rc = launch_T<1, 1, false>(kb, fast, mx, mh, ml, p, grid, sh.smem, stream);
@@ -1017,6 +1181,92 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   if (rc) return rc;
   reduce_partials_kernel<<<(unsigned)ceil_div(T * lp, 256), 256, 0, stream>>>(part, g.splits, g.rows_pad, lp, T,
                                                                               ccorr ? rvec : nullptr, row_valid, Z, ldz);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ the fp16 passes
+// project_S / project_T on the fp16 copy A16 (T x S, pitch ldc halves) written by the MODE_WCOPY pass:
+// A[t,s] = A16[t,s] ic16[s].  Single product (kind::f16); the small operand goes into its image as fp16 with a power
+// of two per column (from its absolute maximum) that the epilogue takes out again.
+int h16_scales(const float* dscale, const float* stdv, int64_t S, float* e16, float* ic16, cudaStream_t stream) {
+  h16_scales_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, stream>>>(dscale, stdv, S, e16, ic16);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
+int project_S16_tc(const uint16_t* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* W, int64_t ldw,
+                   int64_t l, float* Yt, int64_t ldy, void* workspace, cudaStream_t stream) {
+  const int lp = (int)lpad(l);
+  const int64_t Tpad = round_up(T, 64);
+  uint8_t* ws = (uint8_t*)workspace;
+  float* amax = (float*)ws; ws += align256(lp * 4);
+  float* gs = (float*)ws; ws += align256(lp * 4);
+  float* igs = (float*)ws; ws += align256(lp * 4);
+  uint16_t* Wimg = (uint16_t*)ws;
+  XB_CUDA(cudaMemsetAsync(amax, 0, lp * 4, stream));
+  absmax_cols_kernel<<<(unsigned)imin(T, 512), 128, 0, stream>>>(W, T, ldw, lp, 0, nullptr, amax);
+  h16_colscale_kernel<<<1, 128, 0, stream>>>(amax, lp, gs);
+  recip_kernel<<<1, 128, 0, stream>>>(gs, lp, igs);
+  prep_W16_kernel<<<(unsigned)(Tpad / 64), 256, 0, stream>>>(W, T, ldw, lp, gs, Wimg);
+  XB_LAUNCH_CHECK();
+  CUtensorMap mx;
+  int rc = make_map16(&mx, A16, S, T, ldc, TC_TILE, 64);
+  if (rc) return rc;
+  const Shape sh = pick_shape(lp, 1, false, 1);
+  TcParams p{};
+  p.T = T; p.S = S; p.lp = lp;
+  p.stages = sh.stages; p.dcols = sh.dcols; p.tmem_cols = sh.tmem_cols;
+  p.nchunks_total = (int)(Tpad / 64);
+  p.chunks_per_cta = p.nchunks_total;
+  p.dscale = ic16; p.wsum = igs;
+  p.out = Yt; p.ldo = ldy;
+  p.bimg_hi = (const float*)Wimg;
+  p.b_bulk = 1;
+  p.cl = 1;
+  dim3 grid((unsigned)ceil_div(S, TC_TILE));
+  return launch_tc<1, false, 1, 0, false, false, MODE_H16>(mx, mx, mx, p, grid, sh.smem, stream);
+}
+
+int project_T16_tc(const uint16_t* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* Yt, int64_t ldy,
+                   int64_t l, float* Z, int64_t ldz, void* workspace, cudaStream_t stream) {
+  const int lp = (int)lpad(l);
+  const Shape sh = pick_shape_T(lp, 1, S, ldc);
+  XB_CHECK_ARG(sh.stages >= 1, "project_T16: no pipeline shape fits lp=%d", lp);
+  const int kb = sh.kb;
+  const TGeom g = t_geometry(T, S, 1024, kb, 1, 64);
+  XB_CHECK_ARG(g.splits <= 65535, "project_T16: too many splits");
+  const int64_t Spad = round_up(S, 256);
+  uint8_t* ws = (uint8_t*)workspace;
+  float* amax = (float*)ws; ws += align256(lp * 4);
+  float* gs = (float*)ws; ws += align256(lp * 4);
+  float* igs = (float*)ws; ws += align256(lp * 4);
+  float* part = (float*)ws; ws += align256((int64_t)g.splits * g.rows_pad * lp * 4);
+  uint16_t* Yimg = (uint16_t*)ws;
+  XB_CUDA(cudaMemsetAsync(amax, 0, lp * 4, stream));
+  absmax_cols_kernel<<<dim3((unsigned)imin(ceil_div(S, 256 * 8), 2 * (int64_t)num_sms()), (unsigned)lp), 256, 0, stream>>>(
+      Yt, S, ldy, lp, 1, ic16, amax);
+  h16_colscale_kernel<<<1, 128, 0, stream>>>(amax, lp, gs);
+  recip_kernel<<<1, 128, 0, stream>>>(gs, lp, igs);
+  tile_Y16_kernel<<<(unsigned)(Spad / 64), 256, 0, stream>>>(Yt, S, ldy, lp, ic16, gs, Yimg);
+  XB_LAUNCH_CHECK();
+  CUtensorMap mx;
+  int rc = make_map16(&mx, A16, S, T, ldc, kb * 64 + 8, TC_TILE);
+  if (rc) return rc;
+  TcParams p{};
+  p.T = T; p.S = S; p.lp = lp;
+  p.stages = sh.stages; p.dcols = sh.dcols; p.tmem_cols = sh.tmem_cols;
+  p.nchunks_total = g.chunks_total;
+  p.chunks_per_cta = g.chunks_per_cta;
+  p.out = part; p.ldo = lp;
+  p.bimg_hi = (const float*)Yimg;
+  p.b_bulk = 1;
+  p.cl = 1;
+  dim3 grid((unsigned)g.t_tiles, (unsigned)g.splits);
+  rc = launch_T_mode<MODE_H16>(kb, true, mx, mx, p, grid, sh.smem, stream);
+  if (rc) return rc;
+  reduce_partials_kernel<<<(unsigned)ceil_div(T * lp, 256), 256, 0, stream>>>(part, g.splits, g.rows_pad, lp, T, nullptr, nullptr,
+                                                                              Z, ldz, igs);
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
 }

@@ -122,6 +122,17 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem], kind::f16 (fp16 operands, fp32 accumulator, K = 16), one CTA
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -177,6 +188,17 @@ __device__ __forceinline__ float lds32(uint32_t a) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return (uint32_t)v;
+}
+// two floats -> packed fp16 pair (first value in the low half), round to nearest, saturating at +-65504
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 __device__ __forceinline__ float4 lds128(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
@@ -202,6 +224,11 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 }
 
 
+
+// instruction descriptor: D fp32, A/B fp16, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
+}
 
 // Offset (in floats) of element (row j, k) inside the image of one 32-wide K slab: [rows][32 k], 16-byte chunks
 // XOR-swizzled by (row & 7) — the K-major SWIZZLE_128B layout the UMMA descriptor names.
