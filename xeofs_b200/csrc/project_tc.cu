@@ -144,7 +144,11 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   uint8_t* xs = smem;                                   // [stages][XB]
   uint8_t* bs = xs + (size_t)stages * XB;               // [stages][BPART][KB][bbytes]
   uint8_t* pd = bs + (size_t)stages * BPART * KB * bbytes;  // [stages][pivot KB*128 B | dscale KB*128 B] (SIDE_T)
-  uint64_t* bars = (uint64_t*)(pd + (SIDE_T ? (size_t)stages * KB * 256 : 0));
+  // MODE_WCOPY: two staging tiles [128 rows][KB*64 (+16) bytes] through which the fp16 values of a stage leave as whole
+  // 128-byte row segments (a thread owns 32 bytes of a row: stored directly they are scattered 16-byte writes)
+  constexpr int CPITCH = KB * 64 + 16;
+  uint8_t* cst = pd + (SIDE_T ? (size_t)stages * KB * 256 : 0);
+  uint64_t* bars = (uint64_t*)(cst + (MODE == MODE_WCOPY ? 2 * TC_TILE * CPITCH : 0));
   uint64_t* full = bars;                       // TMA bytes landed
   uint64_t* empty = bars + TC_MAX_STAGES;      // MMAs of the stage retired
   uint64_t* aready = bars + 2 * TC_MAX_STAGES; // A operand of the stage is in TMEM
@@ -457,16 +461,35 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
               cw[cc * 2 + 1] = pack_h2(wv[2] * da[2], wv[3] * da[3]);
             }
           }
-          if (MODE == MODE_WCOPY && tile0 + row < p.T) {
-            // this thread's KW values of the slab: KW * 2 contiguous bytes of its row of the copy
-            uint16_t* dst = p.copy16 + (tile0 + row) * p.ldc16 + ((int64_t)(chunk0 + c) * KB + kb) * TC_KC + part * KW;
+          if (MODE == MODE_WCOPY) {
+            // this thread's KW values of the slab: KW * 2 contiguous bytes of its row of the staging tile
+            const uint32_t dst = smem_u32(cst) + (c & 1) * (TC_TILE * CPITCH) + row * CPITCH + kb * 64 + part * KW * 2;
 #pragma unroll
             for (int i = 0; i < KW / 8; ++i)
-              *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(cw[i * 4], cw[i * 4 + 1], cw[i * 4 + 2], cw[i * 4 + 3]);
+              sts128(dst + i * 16, make_float4(__uint_as_float(cw[i * 4]), __uint_as_float(cw[i * 4 + 1]),
+                                               __uint_as_float(cw[i * 4 + 2]), __uint_as_float(cw[i * 4 + 3])));
           }
         }
         tmem_st<KW>(a_slot + kb * TC_KC, hi);
         if (NS >= 2) tmem_st<KW>(a_slot + kb * TC_KC + TC_KC * KB, lo);
+      }
+      if (MODE == MODE_WCOPY) {
+        // all operand warps have written the stage's tile: every warp stores 16 of its rows, 4 rows (4 x KB*64 bytes
+        // of contiguous global memory each) per instruction
+        asm volatile("bar.sync 1, %0;" ::"r"(128 * NW) : "memory");
+        const uint32_t tile = smem_u32(cst) + (c & 1) * (TC_TILE * CPITCH);
+        constexpr int CHUNKS = KB * 4;                 // 16-byte chunks per row
+        constexpr int RPI = 32 / CHUNKS;               // rows per instruction
+        const int w8 = warp - 2;                       // 0 .. 4*NW-1
+        const int rows_per_warp = TC_TILE / (4 * NW);
+        const int64_t s0 = ((int64_t)(chunk0 + c) * KB) * TC_KC;
+#pragma unroll
+        for (int i = 0; i < rows_per_warp / RPI; ++i) {
+          const int r = w8 * rows_per_warp + i * RPI + lane / CHUNKS, ch = lane % CHUNKS;
+          const float4 v = lds128(tile + r * CPITCH + ch * 16);
+          if (tile0 + r < p.T)
+            *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(p.copy16 + (tile0 + r) * p.ldc16 + s0) + ch * 16) = v;
+        }
       }
       tmem_wait_st();
       tc_fence_before();
@@ -849,7 +872,7 @@ struct Shape {
   uint32_t tmem_cols;
   size_t smem;
 };
-static Shape pick_shape(int lp, int ns, bool side_t, int kb, bool rn = false) {
+static Shape pick_shape(int lp, int ns, bool side_t, int kb, bool rn = false, bool wcopy = false) {
   Shape sh;
   const int npart = ns >= 2 ? 2 : 1, bpart = ns == 3 ? 2 : 1;
   const bool two_ctas = !side_t && ns == 1 && !rn;  // project_S x1: two CTAs per SM share the 512 TMEM columns
@@ -861,22 +884,23 @@ static Shape pick_shape(int lp, int ns, bool side_t, int kb, bool rn = false) {
   sh.tmem_cols = two_ctas ? 256 : 512;
   const int ring = (int)sh.tmem_cols - (pk ? 1 : (ns >= 2 || rn) ? 2 : 1) * sh.dcols;
   const int by_tmem = ring / (TC_KC * kb * npart);
-  const int budget = (two_ctas ? 110 : 222) * 1024 - 2048;
+  const int extra = wcopy ? 2 * TC_TILE * (kb * 64 + 16) : 0;  // the staging tiles of the pass that writes the fp16 copy
+  const int budget = (two_ctas ? 110 : 222) * 1024 - 2048 - extra;
   int st = budget / per_stage;
   if (st > by_tmem) st = by_tmem;
   if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
   sh.stages = st;
-  sh.smem = (size_t)(st > 0 ? st : 1) * per_stage + 1024 /*alignment*/ + 256 /*barriers*/;
+  sh.smem = (size_t)(st > 0 ? st : 1) * per_stage + extra + 1024 /*alignment*/ + 256 /*barriers*/;
   return sh;
 }
-static Shape pick_shape_T(int lp, int ns, int64_t S, int64_t ldx, bool rn = false) {
+static Shape pick_shape_T(int lp, int ns, int64_t S, int64_t ldx, bool rn = false, bool wcopy = false) {
   int kb = env_int("XEOFS_TC_KB", 2);
   if (kb != 1 && kb != 2 && kb != 4) kb = 2;
   (void)S; (void)ldx;
-  Shape sh = pick_shape(lp, ns, true, kb, rn);
+  Shape sh = pick_shape(lp, ns, true, kb, rn, wcopy);
   while (sh.stages < 2 && kb > 1) {
     kb >>= 1;
-    sh = pick_shape(lp, ns, true, kb, rn);
+    sh = pick_shape(lp, ns, true, kb, rn, wcopy);
   }
   return sh;
 }
@@ -1119,7 +1143,7 @@ int project_T_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const float*
   (void)workspace_bytes;
   const int lp = (int)lpad(l);
   const int ns = algo_ns(algo);
-  const Shape sh = pick_shape_T(lp, ns, S, ldx, algo_rn(algo) != 0);
+  const Shape sh = pick_shape_T(lp, ns, S, ldx, algo_rn(algo) != 0, copy16 != nullptr);
   XB_CHECK_ARG(sh.stages >= 1, "project_T: no pipeline shape fits lp=%d", lp);
   const int kb = sh.kb;
   const int cl = pick_cluster();
