@@ -129,14 +129,39 @@ def _slow_decay(T, S, decay, seed):
     return (280 + (U * (1000 * decay ** np.arange(r))) @ V.T + 0.5 * rng.standard_normal((T, S))).astype(np.float32)
 
 
+@pytest.fixture
+def force_h16(monkeypatch):
+    """Run the power iterations on the fp16 copy of the preprocessed matrix whatever the field's size (the copy is
+    normally skipped below 256 MB)."""
+    from xeofs_b200._cuda_ops import CudaOps
+    monkeypatch.setattr(CudaOps, "h16_min_bytes", 0)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(standardize=True, use_coslat=True)])
+def test_planted_wide_through_the_half_precision_copy(kw, force_h16):
+    """test_planted_wide_with_land_mask with the fp16 copy forced on: statistics + first product fused, the second
+    pass writes the copy, the other power-iteration passes stream it; same oracle, same tolerances."""
+    T, nlat, nlon, k = 600, 40, 90, 12
+    X = planted(T, nlat * nlon, 2 * k, seed=1).reshape(T, nlat, nlon)
+    X[:, np.random.default_rng(9).random((nlat, nlon)) < 0.1] = np.nan
+    coords = {"lat": np.linspace(88, -88, nlat), "lon": np.arange(nlon) * 4.0}
+    o, m = _fit_both(X, coords, k, random_state=5, solver_kwargs={"n_iter": 4}, **kw)
+    assert m.preprocessor.fitted.field.h16 is not None, "the fp16 copy was not used"
+    _compare(o, m, k)
+
+
+@pytest.mark.parametrize("h16", [False, True])
 @pytest.mark.parametrize("n_iter", [4, "auto"])
 @pytest.mark.parametrize("kind", ["white", "slow0.99"])
-def test_flat_spectra_match_oracle(kind, n_iter):
+def test_flat_spectra_match_oracle(kind, n_iter, h16, monkeypatch):
     """The reference's own benchmark input is white noise (docs/perf/xeofs_timings.py:18-20): no spectral gap, the
     randomized SVD is far from converged (5 % off the exact singular values) and the result is a function of the
     sketch and of every step of the iteration.  With the shared sketch the device path must still land on the oracle's
     numbers: singular values / explained variance ratio rtol 1e-4, every mode's pattern |<v_ref, v>| >= 1 - 1e-4.
     Same for a slowly decaying spectrum (ratio 0.99 between consecutive singular values)."""
+    if h16:  # the same through the fp16 copy of the preprocessed matrix (normally skipped for fields this small)
+        from xeofs_b200._cuda_ops import CudaOps
+        monkeypatch.setattr(CudaOps, "h16_min_bytes", 0)
     T, nlat, nlon, k = 2000, 64, 128, 10
     S = nlat * nlon
     if kind == "white":
@@ -146,4 +171,5 @@ def test_flat_spectra_match_oracle(kind, n_iter):
     X = X.reshape(T, nlat, nlon)
     coords = {"lat": np.linspace(80, -80, nlat), "lon": np.arange(nlon) * 2.0}
     o, m = _fit_both(X, coords, k, random_state=5, solver_kwargs={"n_iter": n_iter})
+    assert (m.preprocessor.fitted.field.h16 is not None) == h16
     _compare(o, m, k, vec_tol=1e-4, elem_atol=5e-3)

@@ -479,3 +479,26 @@ def test_feature_sharded_fit_two_gpus(tmp_path):
     assert (dots >= 1 - 1e-4).all(), dots
     ro = orot.eof_rotator_fit(o["components_2d"], o["explained_variance"], o["scores"], o["norms"], o["A"].shape[0], n_modes=6)
     np.testing.assert_allclose(r0["rot_ev"], ro["explained_variance"], rtol=1e-4)
+
+
+def test_mca_through_the_half_precision_copies(monkeypatch):
+    """The implicit cross-covariance products of the power iterations on the fp16 copies of both fields (forced on for
+    this small case) against the explicit-C oracle: same tolerances as test_mca_matches_explicit_cross_covariance_oracle."""
+    import xeofs_b200 as xb
+    from xeofs_b200._cuda_ops import CudaOps
+    monkeypatch.setattr(CudaOps, "h16_min_bytes", 0)
+    T, S1, S2, k = 400, 40 * 30, 60 * 50, 8
+    X, Y = _coupled_fields(T, S1, S2, 2 * k, seed=5)
+    X, Y = X.reshape(T, 40, 30), Y.reshape(T, 60, 50)
+    cx = {"lat": np.linspace(80, -80, 40), "lon": np.arange(30) * 1.0}
+    cy = {"lat": np.linspace(60, -60, 60), "lon": np.arange(50) * 1.0}
+    kw = dict(standardize=True, use_coslat=True)
+    o = omca.mca_fit(X, Y, DIMS, DIMS, "time", coords_x=cx, coords_y=cy, n_modes=k, random_state=3, **kw)
+    m = xb.cross.MCA(n_modes=k, random_state=3, use_pca=False, **kw)
+    m.fit(xb.DataArray(X, DIMS, cx), xb.DataArray(Y, DIMS, cy), dim="time")
+    assert m._f1.field.h16 is not None and m._f2.field.h16 is not None
+    np.testing.assert_allclose(m.singular_values().values, o["singular_values"], rtol=1e-4)
+    c1, c2 = m.components()
+    for c, oc in ((c1, o["components1_2d"]), (c2, o["components2_2d"])):
+        dots = (c.values.reshape(-1, k) * oc).sum(axis=0)
+        assert (dots >= 1 - 1e-4).all(), dots
