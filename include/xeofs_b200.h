@@ -237,19 +237,32 @@ int xeofs_b200_materialize(const float* X, int64_t T, int64_t S, int64_t ldx, co
  * h16_scales:        e16[s], ic16[s] = 1/c[s] from the Scaler vectors (0 for dropped features).
  * project_T_h16copy: xeofs_b200_project_T(XEOFS_ALGO_TF32X1) that also writes A16 (T x ldc halves, ldc >= S rounded
  *                    up to 128, ldc % 8 == 0); no_nan as XEOFS_ALGO_FLAG_NO_NAN.
- * project_S16 / project_T16: Yt = A^T W / Z = A Y with A[t,s] = A16[t,s] ic16[s] (same layouts and workspace size as
- *                    project_S / project_T with XEOFS_ALGO_TF32X1).                                                  */
+ * project_S16 / project_T16: Yt = A^T W / Z = A Y with A[t,s] = A16[t,s] ic16[s] (+ cc16[s], see below) (same layouts
+ *                    and workspace size as project_S / project_T with XEOFS_ALGO_TF32X1).                            */
 int xeofs_b200_h16_scales(const float* dscale, const float* std, int64_t S, float* e16, float* ic16, void* stream);
 int xeofs_b200_project_T_h16copy(const float* X, int64_t T, int64_t S, int64_t ldx, const float* pivot,
                                  const float* dscale, const float* Yt, int64_t ldy, int64_t l, float* Z, int64_t ldz,
                                  void* workspace, int64_t workspace_bytes, int no_nan, const float* e16, void* copy16,
                                  int64_t ldc, void* stream);
-int xeofs_b200_project_S16(const void* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* W,
-                           int64_t ldw, int64_t l, float* Yt, int64_t ldy, void* workspace, int64_t workspace_bytes,
-                           void* stream);
-int xeofs_b200_project_T16(const void* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* Yt,
-                           int64_t ldy, int64_t l, float* Z, int64_t ldz, void* workspace, int64_t workspace_bytes,
-                           void* stream);
+int xeofs_b200_project_S16(const void* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* cc16,
+                           const float* W, int64_t ldw, int64_t l, float* Yt, int64_t ldy, void* workspace,
+                           int64_t workspace_bytes, void* stream);
+int xeofs_b200_project_T16(const void* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* cc16,
+                           const float* Yt, int64_t ldy, int64_t l, float* Z, int64_t ldz, void* workspace,
+                           int64_t workspace_bytes, void* stream);
+/* The statistics pass itself can write the copy (then the first project_T pass is already a half-precision one): the
+ * mean is not known yet, so the copy holds the field shifted by its first sample,
+ *     A16[t,s] = fp16( (X[t,s] - X[0,s]) c0[s] ),   c0 = the power of two that puts the largest deviation met in 64
+ *     samples spread over the record at 512 (deviations 128 times larger still fit),
+ * and the fitted matrix is A[t,s] = A16[t,s] ic16[s] + cc16[s] with ic16 = dscale / c0 and the rank-1 term
+ * cc16 = (X[0,s] - mean[s]) dscale[s], both written by the pass.  project_S16 / project_T16 take cc16 (NULL for a
+ * centred copy written by project_T_h16copy).  Same arguments as xeofs_b200_project_S_stats plus the copy.       */
+int xeofs_b200_project_S_stats_h16copy(const float* X, int64_t T, int64_t S, int64_t ldx, const double* featw,
+                                       int flags, const float* W, int64_t ldw, int64_t l, float* mean, float* std,
+                                       uint8_t* valid, float* pivot, float* dscale, float* ccorr, double* scalars_out,
+                                       int32_t* row_nan, float* Yt, int64_t ldy, void* workspace,
+                                       int64_t workspace_bytes, void* copy16, int64_t ldc, float* c0, float* ic16,
+                                       float* cc16, void* stream);
 
 /* ---- M3: the sample Gram matrix A A^T of a preprocessed field as a plain tcgen05 GEMM (kind::f16 on a bf16 copy) ----
  * materialize_bf16: the preprocessed matrix (as xeofs_b200_materialize) rounded to bf16, rows_out x cols_out with zero

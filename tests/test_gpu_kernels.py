@@ -378,7 +378,8 @@ def test_half_precision_copy_passes(T, S, l, standardize):
     assert f.h16 is not None and not f.want_h16
     np.testing.assert_allclose(Z.cpu().numpy()[:, :l] / colT, wantT / colT, atol=3e-3)
     # the copy itself: A16 ic16 == A to fp16 accuracy (11 bits), zero at the NaN features
-    A16, ic16 = f.h16
+    A16, ic16, cc16 = f.h16
+    assert cc16 is None
     got = (A16.view(torch.float16)[:, :S].double() * ic16.double()[None, :]).cpu().numpy()
     scale = np.abs(A).max(axis=0) + 1e-30
     assert np.max(np.abs(got - A) / scale) < 1e-3
@@ -392,3 +393,49 @@ def test_half_precision_copy_passes(T, S, l, standardize):
     # the accurate products never take the copy
     Z3 = tc_ops.project_T(f, Y, l, algo=_lib.ALGO_TF32X3)
     np.testing.assert_allclose(Z3.cpu().numpy()[:, :l] / colT, wantT / colT, atol=2e-5)
+
+
+@pytest.mark.parametrize("T,S,l,center,standardize", [(300, 1000, 10, True, False), (1000, 4100, 60, True, True)])
+def test_statistics_pass_writes_the_half_precision_copy(T, S, l, center, standardize, monkeypatch):
+    """xeofs_b200_project_S_stats_h16copy: the fused statistics + first product pass also writes the fp16 copy of the
+    field shifted by its first sample, with the factor ic16 and the rank-1 term cc16 that turn it into the fitted matrix:
+    A = A16 ic16 + cc16.  Checked: the statistics and the product as without the copy, the copy against the fp64
+    preprocessed matrix, and project_S16 / project_T16 with the rank-1 term against fp64 (single-TF32 accuracy).  The
+    record has a trend, so that samples far from the first one are much larger than the pre-sample suggests locally."""
+    from xeofs_b200 import _lib
+    from xeofs_b200._cuda_ops import CudaOps, Field
+    from xeofs_b200._lib import lpad
+    monkeypatch.setattr(CudaOps, "h16_min_bytes", 0)
+    ops = CudaOps(algo="auto")
+    rng = np.random.default_rng(T + S)
+    X = (280 + 3 * rng.standard_normal((T, S)) + np.linspace(0, 40, T)[:, None] * rng.random(S)[None, :]).astype(np.float32)
+    X[:, rng.random(S) < 0.1] = np.nan
+    lp = lpad(l)
+    W = np.zeros((T, lp), np.float32)
+    W[:, :l] = np.linalg.qr(rng.standard_normal((T, l)))[0]
+    Xd = ops.space_side(T, S)
+    Xd.copy_(torch.from_numpy(X))
+    Wd = torch.from_numpy(W).cuda()
+    row_nan, fin, Yt = ops.stats_project_S(Xd, None, center, standardize, Wd, l)
+    assert fin.get("h16") is not None
+    A16, ic16, cc16 = fin["h16"]
+    A = np.nan_to_num(_A_ref(X, None, center, standardize), nan=0.0)
+    v = fin["valid"].cpu().numpy().astype(bool)
+    np.testing.assert_array_equal(v, ~np.isnan(X).all(axis=0))
+    want = (A.T @ W[:, :l].astype(np.float64)).T
+    np.testing.assert_allclose(Yt.cpu().numpy()[:l], want, atol=3e-3 * np.abs(want).max())
+    rec = (A16.view(torch.float16)[:, :S].double() * ic16.double()[None, :] + cc16.double()[None, :]).cpu().numpy()
+    d = fin["dscale"].cpu().numpy().astype(np.float64)
+    span = np.nanmax(np.abs(X - X[0]), axis=0, initial=0.0, where=~np.isnan(X)) * np.abs(d) + 1e-30
+    assert np.max(np.abs(rec[:, v] - A[:, v]) / span[v]) < 1e-3   # 11 bits of the largest deviation from the first sample
+    assert (rec[:, ~v] == 0).all()
+    f = Field(Xd, fin["pivot"], fin["dscale"], None, fin["valid"], fin["mean"], fin["std"], None, no_nan=False)
+    f.h16 = fin["h16"]
+    Y = ops.space_side(lp, S, zero=True)
+    Y[:l] = torch.randn((l, S), device="cuda") * torch.logspace(0, -3, l, device="cuda")[:, None]
+    wantT = A @ Y[:l].double().cpu().numpy().T
+    colT = np.abs(wantT).max(axis=0)
+    Z = ops.project_T(f, Y, l, algo=_lib.ALGO_TF32X1)
+    np.testing.assert_allclose(Z.cpu().numpy()[:, :l] / colT, wantT / colT, atol=4e-3)
+    Yt2 = ops.project_S(f, Wd, l, algo=_lib.ALGO_TF32X1)
+    np.testing.assert_allclose(Yt2.cpu().numpy()[:l], want, atol=4e-3 * np.abs(want).max())

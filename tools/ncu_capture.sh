@@ -14,15 +14,18 @@ for wl in "$@"; do
       # warm-up fit = 14 project_tc launches (10 passes + 4 k-column applies); capture the 14 of the timed fit
       timeout 1500 ncu --set full --clock-control none --import-source on -k regex:project_tc_kernel -s 14 -c 14 -f \
           -o gpurun_out/${tag}_full_c2 python bench.py $Q > gpurun_out/${tag}_full_c2.log 2>&1
-      ncu -i gpurun_out/${tag}_full_c2.ncu-rep --page raw --csv > gpurun_out/${tag}_full_c2_raw.csv 2>/dev/null ;;
+      ncu -i gpurun_out/${tag}_full_c2.ncu-rep --page raw --csv > gpurun_out/${tag}_full_c2_raw.csv 2>/dev/null
+      rm -f gpurun_out/${tag}_full_c2.ncu-rep ;;   # (gpurun brings back at most 64 MiB: the CSV pages are what is kept)
     c3)
-      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:project_tc_kernel -s 60 -c 8 -f \
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"project_tc_kernel|gram_bf16_kernel" -s 70 -c 12 -f \
           -o gpurun_out/${tag}_full_c3 python bench.py --workload c3 --steps 1 --warmup 1 --no-cpu > gpurun_out/${tag}_full_c3.log 2>&1
-      ncu -i gpurun_out/${tag}_full_c3.ncu-rep --page raw --csv > gpurun_out/${tag}_full_c3_raw.csv 2>/dev/null ;;
+      ncu -i gpurun_out/${tag}_full_c3.ncu-rep --page raw --csv > gpurun_out/${tag}_full_c3_raw.csv 2>/dev/null
+      rm -f gpurun_out/${tag}_full_c3.ncu-rep ;;
     c5)
       timeout 1500 ncu --set full --clock-control none --import-source on -k regex:varimax_tc_kernel -s 20 -c 2 -f \
           -o gpurun_out/${tag}_full_c5 python bench.py --workload c5 --steps 2 --warmup 3 --no-cpu > gpurun_out/${tag}_full_c5.log 2>&1
-      ncu -i gpurun_out/${tag}_full_c5.ncu-rep --page raw --csv > gpurun_out/${tag}_full_c5_raw.csv 2>/dev/null ;;
+      ncu -i gpurun_out/${tag}_full_c5.ncu-rep --page raw --csv > gpurun_out/${tag}_full_c5_raw.csv 2>/dev/null
+      rm -f gpurun_out/${tag}_full_c5.ncu-rep ;;
   esac
 done
 ls -la gpurun_out/${tag}_* | head -20

@@ -25,7 +25,7 @@ class Field:
     def __init__(self, X, pivot, dscale, ccorr, valid, mean=None, std=None, row_valid=None, no_nan=False):
         self.no_nan = no_nan  # True: no NaN anywhere in X (every feature and every sample valid), known to the caller
         self.want_h16 = False  # set by fit_field: the power iterations may run on an fp16 copy of the matrix
-        self.h16 = None        # (copy (T x pitch) int16 view, ic16) once the first fast project_T has written it
+        self.h16 = None        # (copy (T x pitch) int16, ic16, cc16 or None) once a pass has written it
         self.X = X
         self.T, self.S = int(X.shape[0]), int(X.shape[1])
         self.ldx = int(X.stride(0))
@@ -60,6 +60,7 @@ class CudaOps:
         self._vws = None
         self._unit = None
         self.use_h16 = os.environ.get("XEOFS_H16", "1") != "0"  # fp16 copy of the matrix for the power iterations
+        self.h16_stats_copy = os.environ.get("XEOFS_H16_STATS", "1") != "0"  # written by the statistics pass already
         self.launches = 0  # kernels enqueued through this object (bench.py reports it)
         self.time_products = False  # bench.py: CUDA events around every streaming product on the launch stream
         self._prod_events = []
@@ -163,6 +164,25 @@ class CudaOps:
         Yt = self.space_side(lp, S)
         ws = self.workspace(T, S, l, _lib.ALGO_TF32X1)
         flags = (_lib.F_CENTER if center else 0) | (_lib.F_STANDARDIZE if standardize else 0)
+        # where it pays and fits, the same pass writes the fp16 copy of the (shifted) field for the power iterations
+        copy = None
+        if center and self.use_h16 and self.h16_stats_copy and T * S * 4 >= self.h16_min_bytes:
+            pitch = (S + 127) // 128 * 128
+            free, _ = torch.cuda.mem_get_info(self.device)
+            cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+            if T * pitch * 2 + (4 << 30) <= free + cached:
+                copy = (torch.empty((T, pitch), dtype=torch.int16, device=self.device), self.empty(S), self.empty(S),
+                        self.empty(S))
+        if copy is not None:
+            A16, c0, ic16, cc16 = copy
+            check(self._timed("project_S_stats_wcopy", l, lambda: self.lib.xeofs_b200_project_S_stats_h16copy(
+                ptr(X), T, S, ldx, ptr(featw), flags, ptr(W), int(W.stride(0)), l, ptr(out["mean"]), ptr(out["std"]),
+                ptr(out["valid"]), ptr(out["pivot"]), ptr(out["dscale"]), ptr(out["ccorr"]), ptr(out["scalars"]),
+                ptr(row_nan), ptr(Yt), int(Yt.stride(0)), ptr(ws), ws.numel(), ptr(A16), pitch, ptr(c0), ptr(ic16),
+                ptr(cc16), self._stream())), "project_S_stats_h16copy")
+            out["h16"] = (A16, ic16, cc16)
+            self.launches += 6
+            return row_nan, out, Yt
         check(self._timed("project_S_stats", l, lambda: self.lib.xeofs_b200_project_S_stats(
             ptr(X), T, S, ldx, ptr(featw), flags, ptr(W), int(W.stride(0)), l, ptr(out["mean"]), ptr(out["std"]),
             ptr(out["valid"]), ptr(out["pivot"]), ptr(out["dscale"]), ptr(out["ccorr"]), ptr(out["scalars"]),
@@ -182,10 +202,10 @@ class CudaOps:
                 self.project_S(f, W[:, j0:], w, algo=algo, out=Yt[j0:j0 + lpad(w)], tag=tag)
             return Yt
         if f.h16 is not None and algo in self._fast_algos and tag == "project_S":
-            A16, ic16 = f.h16
+            A16, ic16, cc16 = f.h16
             ws = self.workspace(f.T, f.S, l, _lib.ALGO_TF32X1)
             check(self._timed("project_S_h16", l, lambda: self.lib.xeofs_b200_project_S16(
-                ptr(A16), f.T, f.S, int(A16.stride(0)), ptr(ic16), ptr(W), int(W.stride(0)), l, ptr(Yt),
+                ptr(A16), f.T, f.S, int(A16.stride(0)), ptr(ic16), ptr(cc16), ptr(W), int(W.stride(0)), l, ptr(Yt),
                 int(Yt.stride(0)), ptr(ws), ws.numel(), self._stream())), "project_S16")
             self.launches += 6
             return Yt
@@ -210,9 +230,9 @@ class CudaOps:
         if algo in self._fast_algos and (f.h16 is not None or f.want_h16):
             ws = self.workspace(f.T, f.S, l, _lib.ALGO_TF32X1)
             if f.h16 is not None:
-                A16, ic16 = f.h16
+                A16, ic16, cc16 = f.h16
                 check(self._timed("project_T_h16", l, lambda: self.lib.xeofs_b200_project_T16(
-                    ptr(A16), f.T, f.S, int(A16.stride(0)), ptr(ic16), ptr(Yt), int(Yt.stride(0)), l, ptr(Z),
+                    ptr(A16), f.T, f.S, int(A16.stride(0)), ptr(ic16), ptr(cc16), ptr(Yt), int(Yt.stride(0)), l, ptr(Z),
                     int(Z.stride(0)), ptr(ws), ws.numel(), self._stream())), "project_T16")
                 self.launches += 7
                 return Z
@@ -223,7 +243,7 @@ class CudaOps:
                     ptr(f.X), f.T, f.S, f.ldx, ptr(f.pivot), ptr(f.dscale), ptr(Yt), int(Yt.stride(0)), l, ptr(Z),
                     int(Z.stride(0)), ptr(ws), ws.numel(), int(f.no_nan), ptr(e16), ptr(A16), int(A16.stride(0)),
                     self._stream())), "project_T_h16copy")
-                f.h16 = (A16, ic16)
+                f.h16 = (A16, ic16, None)
                 self.launches += 3
                 return Z
         ws = self.workspace(f.T, f.S, l, algo)

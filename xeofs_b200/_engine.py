@@ -140,8 +140,11 @@ def fit_field(ops, X, featw=None, center=True, standardize=False, check_nans=Tru
     ff.field = Field(X, fin["pivot"], fin["dscale"], ccorr, fin["valid"], fin["mean"], fin["std"], row_valid,
                      no_nan=(n_valid == S_global and n_samples == T))
     # the power iterations may stream an fp16 copy of the preprocessed matrix (written by their first time-side pass)
-    ff.field.want_h16 = bool(center and row_valid is None and T * S * 4 >= getattr(ops, "h16_min_bytes", 1 << 62)
-                             and getattr(ops, "use_h16", True))
+    if fin.get("h16") is not None and row_valid is None:
+        ff.field.h16 = fin["h16"]  # the statistics pass wrote it (shifted by the first sample: with its rank-1 term)
+    else:
+        ff.field.want_h16 = bool(center and row_valid is None and T * S * 4 >= getattr(ops, "h16_min_bytes", 1 << 62)
+                                 and getattr(ops, "use_h16", True))
     ff.mean, ff.std, ff.valid, ff.featw = fin["mean"], fin["std"], fin["valid"], featw
     ff.valid_sample, ff.n_samples, ff.n_features = valid_sample, n_samples, n_valid
     ff.total_variance = total_variance

@@ -37,8 +37,10 @@ SIGNATURES = {
     "xeofs_b200_h16_scales": (_int, [_p, _p, _i64, _p, _p, _p]),
     "xeofs_b200_project_T_h16copy": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _int, _p, _p,
                                             _i64, _p]),
-    "xeofs_b200_project_S16": (_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _p]),
-    "xeofs_b200_project_T16": (_int, [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _p]),
+    "xeofs_b200_project_S16": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _p]),
+    "xeofs_b200_project_T16": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _p]),
+    "xeofs_b200_project_S_stats_h16copy": (_int, [_p, _i64, _i64, _i64, _p, _int, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p,
+                                                  _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p]),
     "xeofs_b200_round_tf32": (_int, [_p, _i64, _i64, _i64, _p]),
     "xeofs_b200_gram": (_int, [_p, _i64, _i64, _i64, _int, _p, _int, _p]),
     "xeofs_b200_chol_inv": (_int, [_p, _i64, _p, _p, _p]),

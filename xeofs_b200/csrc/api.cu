@@ -44,13 +44,14 @@ int project_T_tc(const float*, int64_t, int64_t, int64_t, const float*, const fl
                  const float*, int64_t, int64_t, float*, int64_t, void*, int64_t, int, bool, cudaStream_t, uint16_t*, int64_t,
                  const float*);
 int h16_scales(const float*, const float*, int64_t, float*, float*, cudaStream_t);
-int project_S16_tc(const uint16_t*, int64_t, int64_t, int64_t, const float*, const float*, int64_t, int64_t, float*, int64_t,
-                   void*, cudaStream_t);
-int project_T16_tc(const uint16_t*, int64_t, int64_t, int64_t, const float*, const float*, int64_t, int64_t, float*, int64_t,
-                   void*, cudaStream_t);
+int project_S16_tc(const uint16_t*, int64_t, int64_t, int64_t, const float*, const float*, const float*, int64_t, int64_t, float*,
+                   int64_t, void*, cudaStream_t);
+int project_T16_tc(const uint16_t*, int64_t, int64_t, int64_t, const float*, const float*, const float*, int64_t, int64_t, float*,
+                   int64_t, void*, cudaStream_t);
 
 int project_S_stats_tc(const float*, int64_t, int64_t, int64_t, const double*, int, const float*, int64_t, int64_t, float*,
-                       float*, uint8_t*, float*, float*, float*, double*, int32_t*, float*, int64_t, void*, cudaStream_t);
+                       float*, uint8_t*, float*, float*, float*, double*, int32_t*, float*, int64_t, void*, cudaStream_t,
+                       uint16_t*, int64_t, float*, float*, float*);
 }  // namespace xb
 
 using namespace xb;
@@ -198,22 +199,22 @@ static int check_h16_args(const char* who, const void* A16, int64_t T, int64_t S
   return XEOFS_OK;
 }
 
-extern "C" int xeofs_b200_project_S16(const void* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* W,
-                                      int64_t ldw, int64_t l, float* Yt, int64_t ldy, void* workspace, int64_t workspace_bytes,
-                                      void* stream_) {
+extern "C" int xeofs_b200_project_S16(const void* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* cc16,
+                                      const float* W, int64_t ldw, int64_t l, float* Yt, int64_t ldy, void* workspace,
+                                      int64_t workspace_bytes, void* stream_) {
   int rc = check_h16_args("project_S16", A16, T, S, ldc, ic16, W, Yt, l, workspace, workspace_bytes);
   if (rc) return rc;
   XB_CHECK_ARG(ldw >= lpad(l) && ldy >= S, "project_S16: ldw=%lld must be >= lp and ldy=%lld >= S", (long long)ldw, (long long)ldy);
-  return project_S16_tc((const uint16_t*)A16, T, S, ldc, ic16, W, ldw, l, Yt, ldy, workspace, (cudaStream_t)stream_);
+  return project_S16_tc((const uint16_t*)A16, T, S, ldc, ic16, cc16, W, ldw, l, Yt, ldy, workspace, (cudaStream_t)stream_);
 }
 
-extern "C" int xeofs_b200_project_T16(const void* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* Yt,
-                                      int64_t ldy, int64_t l, float* Z, int64_t ldz, void* workspace, int64_t workspace_bytes,
-                                      void* stream_) {
+extern "C" int xeofs_b200_project_T16(const void* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* cc16,
+                                      const float* Yt, int64_t ldy, int64_t l, float* Z, int64_t ldz, void* workspace,
+                                      int64_t workspace_bytes, void* stream_) {
   int rc = check_h16_args("project_T16", A16, T, S, ldc, ic16, Yt, Z, l, workspace, workspace_bytes);
   if (rc) return rc;
   XB_CHECK_ARG(ldz >= lpad(l) && ldy >= S, "project_T16: ldz=%lld must be >= lp and ldy=%lld >= S", (long long)ldz, (long long)ldy);
-  return project_T16_tc((const uint16_t*)A16, T, S, ldc, ic16, Yt, ldy, l, Z, ldz, workspace, (cudaStream_t)stream_);
+  return project_T16_tc((const uint16_t*)A16, T, S, ldc, ic16, cc16, Yt, ldy, l, Z, ldz, workspace, (cudaStream_t)stream_);
 }
 
 extern "C" int xeofs_b200_project_S_stats(const float* X, int64_t T, int64_t S, int64_t ldx, const double* featw, int flags,
@@ -234,5 +235,30 @@ extern "C" int xeofs_b200_project_S_stats(const float* X, int64_t T, int64_t S, 
     return XEOFS_E_UNSUPPORTED;
   }
   return project_S_stats_tc(X, T, S, ldx, featw, flags, W, ldw, l, mean, std, valid, pivot, dscale, ccorr, scalars_out,
-                            row_nan, Yt, ldy, workspace, stream);
+                            row_nan, Yt, ldy, workspace, stream, nullptr, 0, nullptr, nullptr, nullptr);
+}
+
+extern "C" int xeofs_b200_project_S_stats_h16copy(const float* X, int64_t T, int64_t S, int64_t ldx, const double* featw,
+                                                  int flags, const float* W, int64_t ldw, int64_t l, float* mean, float* std,
+                                                  uint8_t* valid, float* pivot, float* dscale, float* ccorr,
+                                                  double* scalars_out, int32_t* row_nan, float* Yt, int64_t ldy,
+                                                  void* workspace, int64_t workspace_bytes, void* copy16, int64_t ldc,
+                                                  float* c0, float* ic16, float* cc16, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  XB_CHECK_ARG(X && W && mean && std && valid && pivot && dscale && ccorr && scalars_out && row_nan && Yt && workspace &&
+                   copy16 && c0 && ic16 && cc16,
+               "project_S_stats_h16copy: null pointer");
+  XB_CHECK_ARG(T > 0 && S > 0 && ldx >= S && l > 0 && l <= 128 && ldw >= lpad(l) && ldy >= S && ldw % 4 == 0 && ldc >= S &&
+                   ldc % 8 == 0 && ((uintptr_t)copy16 % 16 == 0),
+               "project_S_stats_h16copy: bad shape");
+  if (workspace_bytes < xeofs_b200_project_workspace_bytes(T, S, l, XEOFS_ALGO_TF32X1)) {
+    set_error("project_S_stats_h16copy: workspace too small");
+    return XEOFS_E_WORKSPACE;
+  }
+  if (!xeofs_b200_has_tcgen05() || !tc_supported(T, S, ldx, X, l)) {
+    set_error("project_S_stats_h16copy: needs the tcgen05 path (sm_100, 16-byte aligned X, ldx %% 4 == 0)");
+    return XEOFS_E_UNSUPPORTED;
+  }
+  return project_S_stats_tc(X, T, S, ldx, featw, flags, W, ldw, l, mean, std, valid, pivot, dscale, ccorr, scalars_out,
+                            row_nan, Yt, ldy, workspace, stream, (uint16_t*)copy16, ldc, c0, ic16, cc16);
 }

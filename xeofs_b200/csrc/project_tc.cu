@@ -78,6 +78,10 @@ struct TcParams {
   int cl;               // CTAs per cluster (1, 2 or 4): they share the operand image through TMA multicast
   uint16_t* copy16;     // MODE_WCOPY: the fp16 copy this pass writes (T x ldc16)
   int64_t ldc16;
+  const float* c0;      // statistics pass writing the copy: the power of two of every feature (from a pre-sample)
+  float* ic16_out;      //   [S] what the copy has to be multiplied with: dscale / c0
+  float* cc16_out;      //   [S] the rank-1 term of the copy: (first sample - mean) dscale
+  const float* igs;     // MODE_H16: 1 / the power-of-two column scale of the small operand's fp16 image
 };
 
 
@@ -114,8 +118,9 @@ template <int NS, bool SIDE_T, int KB, bool STATS = false, int RN = 0, bool PK =
 __global__ void __launch_bounds__(tc_threads(tc_wide(NS, SIDE_T, RN != 0)), (NS == 1 && !SIDE_T && RN == 0) ? 2 : 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapBhi,
                   const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
-  static_assert(MODE == MODE_F32 || (NS == 1 && RN == 0 && !STATS && !PK), "the fp16 copy serves the single-product passes");
-  static_assert(MODE != MODE_WCOPY || SIDE_T, "the copy is written by the first project_T pass");
+  static_assert(MODE == MODE_F32 || (NS == 1 && RN == 0 && !PK && (!STATS || MODE == MODE_WCOPY)),
+                "the fp16 copy serves the single-product passes");
+  static_assert(MODE != MODE_WCOPY || SIDE_T || STATS, "the copy is written by the statistics pass or the first project_T pass");
   constexpr bool H16 = MODE == MODE_H16;
   constexpr int KEL = H16 ? 2 * TC_KC : TC_KC;      // K values per slab (32 fp32 or 64 fp16: 128 bytes either way)
   static_assert(SIDE_T || KB == 1, "project_S stages are 32 rows of t");
@@ -297,6 +302,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     bool n0 = false;           // the first sample of this feature is NaN
     double sum1 = 0.0, sum2 = 0.0;
     int cnt = 0;
+    float c0 = 0.f;            // statistics pass that also writes the fp16 copy: this feature's power of two
+    if (STATS && MODE == MODE_WCOPY) c0 = (tile0 + row < p.S) ? p.c0[tile0 + row] : 0.f;
     if (STATS) {
       const float x0 = (tile0 + row < p.S) ? p.X[tile0 + row] : 0.f;
       n0 = !(x0 == x0);
@@ -408,6 +415,13 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             sum1 += (double)s1;
             sum2 += (double)s2;
             cnt += cn;
+            if (MODE == MODE_WCOPY && tile0 + row < p.S) {
+              // A16[t, s] = fp16((x - first sample) c0): 32 lanes = 64 contiguous bytes of a row of the copy
+              uint16_t* dst = p.copy16 + t0 * p.ldc16 + tile0 + row;
+#pragma unroll
+              for (int r = 0; r < KW; ++r)
+                if (!ragged || t0 + r < p.T) dst[(int64_t)r * p.ldc16] = (uint16_t)(pack_h2(v[r] * c0, 0.f) & 0xffffu);
+            }
           } else if (check) {
 #pragma unroll
             for (int r = 0; r < KW; ++r) v[r] = (v[r] == v[r]) ? v[r] : 0.f;
@@ -545,6 +559,10 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         p.pivot_out[rrow] = newpiv;
         p.dscale_out[rrow] = d32;
         p.ccorr_out[rrow] = val ? (newpiv - mu_eff) * d32 : 0.f;
+        if (MODE == MODE_WCOPY) {
+          p.ic16_out[rrow] = (val && c0 != 0.f) ? d32 / c0 : 0.f;
+          p.cc16_out[rrow] = cs;  // (first sample - mean_eff) dscale: what the shifted copy lacks
+        }
       }
       if (part != 0) { tv = 0.0; nv = 0; cmax = 0; cmin = 0x7fffffff; }
       tv = warp_sum(tv);
@@ -581,7 +599,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             // an invalid feature (dscale 0) gives a zero row even if its accumulator holds NaN
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              if (H16) v[e] *= p.wsum[j0 + e];  // undo the power-of-two column scale of the fp16 operand image
+              if (H16) v[e] *= p.igs[j0 + e];  // undo the power-of-two column scale of the fp16 operand image
               p.out[(int64_t)(j0 + e) * p.ldo + rrow] =
                   ds != 0.f ? fmaf(ds, v[e], (STATS || p.ccorr) ? cs * p.wsum[j0 + e] : 0.f) : 0.f;
             }
@@ -680,9 +698,11 @@ __global__ void reduce_partials_kernel(const float* __restrict__ P, int splits, 
   if (i >= T * lp) return;
   const int64_t t = i / lp;
   const int j = (int)(i % lp);
-  float acc = (r && (!row_valid || row_valid[t])) ? r[j] : 0.f;
+  float acc = 0.f;
   for (int s = 0; s < splits; ++s) acc += P[((int64_t)s * rows_pad + t) * lp + j];
-  Z[t * ldz + j] = colfac ? acc * colfac[j] : acc;
+  if (colfac) acc *= colfac[j];
+  if (r && (!row_valid || row_valid[t])) acc += r[j];
+  Z[t * ldz + j] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------ fp16 path helpers
@@ -706,6 +726,25 @@ __global__ void h16_scales_kernel(const float* __restrict__ dscale, const float*
   }
   e16[i] = e;
   ic16[i] = ic;
+}
+
+// c0[s] = the power of two that puts the largest |x - first sample| met in 64 samples spread over the record at 512
+// (fp16 then holds deviations 128 times larger before it saturates)
+__global__ void h16_prescale_kernel(const float* __restrict__ X, int64_t T, int64_t S, int64_t ldx, float* __restrict__ c0) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  float x0 = X[s];
+  if (!(x0 == x0)) x0 = 0.f;
+  float amax = 0.f;
+  for (int i = 1; i <= 64; ++i) {
+    const int64_t t = (i * T) / 65;
+    const float d = X[t * ldx + s] - x0;
+    if (d == d) amax = fmaxf(amax, fabsf(d));
+  }
+  if (!(amax > 0.f) || !(amax < 3.0e38f)) amax = fmaxf(fabsf(x0) * 2.44e-4f, 1e-30f);
+  int k = (int)floorf(log2f(512.f / amax));
+  k = max(-100, min(100, k));
+  c0[s] = ldexpf(1.f, k);
 }
 
 // amax[j] = max_n |M(n, j) f(n)| over a k-column matrix (side 0: time-side n x ld, f = 1; side 1: space-side, f = fac)
@@ -1093,7 +1132,7 @@ __global__ void row_nan_kernel(const int32_t* __restrict__ row_delta, const int3
 int project_S_stats_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const double* featw, int flags, const float* W,
                        int64_t ldw, int64_t l, float* mean, float* stdv, uint8_t* valid, float* pivot, float* dscale,
                        float* ccorr, double* scalars, int32_t* row_nan, float* Yt, int64_t ldy, void* workspace,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, uint16_t* copy16, int64_t ldc16, float* c0, float* ic16, float* cc16) {
   const int lp = (int)lpad(l);
   const int64_t Tpad = round_up(T, TC_KC);
   uint8_t* ws = (uint8_t*)workspace;
@@ -1129,7 +1168,16 @@ int project_S_stats_tc(const float* X, int64_t T, int64_t S, int64_t ldx, const 
   p.mean_out = mean; p.std_out = stdv; p.valid_out = valid; p.pivot_out = pivot; p.dscale_out = dscale; p.ccorr_out = ccorr;
   p.scalars_out = scalars; p.row_delta = row_delta; p.base_nan = base_nan;
   dim3 grid((unsigned)round_up(ceil_div(S, TC_TILE), p.cl));
-  rc = launch_kernel(project_tc_kernel<1, false, 1, true>, tc_threads(false), mx, mh, mh, p, grid, sh.smem, stream);
+  if (copy16) {
+    // the pass also writes the fp16 copy of the (shifted) field: per-feature power of two from a pre-sample first
+    h16_prescale_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, stream>>>(X, T, S, ldx, c0);
+    XB_LAUNCH_CHECK();
+    p.copy16 = copy16; p.ldc16 = ldc16; p.c0 = c0; p.ic16_out = ic16; p.cc16_out = cc16;
+    rc = launch_kernel(project_tc_kernel<1, false, 1, true, 0, false, false, MODE_WCOPY>, tc_threads(false), mx, mh, mh, p, grid,
+                       sh.smem, stream);
+  } else {
+    rc = launch_kernel(project_tc_kernel<1, false, 1, true>, tc_threads(false), mx, mh, mh, p, grid, sh.smem, stream);
+  }
   if (rc) return rc;
   row_nan_kernel<<<(unsigned)ceil_div(T, 256), 256, 0, stream>>>(row_delta, base_nan, T, row_nan);
   XB_LAUNCH_CHECK();
@@ -1219,15 +1267,20 @@ int h16_scales(const float* dscale, const float* stdv, int64_t S, float* e16, fl
   return XEOFS_OK;
 }
 
-int project_S16_tc(const uint16_t* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* W, int64_t ldw,
-                   int64_t l, float* Yt, int64_t ldy, void* workspace, cudaStream_t stream) {
+int project_S16_tc(const uint16_t* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* cc16, const float* W,
+                   int64_t ldw, int64_t l, float* Yt, int64_t ldy, void* workspace, cudaStream_t stream) {
   const int lp = (int)lpad(l);
   const int64_t Tpad = round_up(T, 64);
   uint8_t* ws = (uint8_t*)workspace;
   float* amax = (float*)ws; ws += align256(lp * 4);
   float* gs = (float*)ws; ws += align256(lp * 4);
   float* igs = (float*)ws; ws += align256(lp * 4);
+  float* wsum = (float*)ws; ws += align256(lp * 4);
   uint16_t* Wimg = (uint16_t*)ws;
+  if (cc16) {  // the copy is shifted, not centred: rank-1 term cc16[s] * colsum(W)[j]
+    int rc0 = launch_colsum(W, T, ldw, lp, nullptr, wsum, stream);
+    if (rc0) return rc0;
+  }
   XB_CUDA(cudaMemsetAsync(amax, 0, lp * 4, stream));
   absmax_cols_kernel<<<(unsigned)imin(T, 512), 128, 0, stream>>>(W, T, ldw, lp, 0, nullptr, amax);
   h16_colscale_kernel<<<1, 128, 0, stream>>>(amax, lp, gs);
@@ -1243,7 +1296,7 @@ int project_S16_tc(const uint16_t* A16, int64_t T, int64_t S, int64_t ldc, const
   p.stages = sh.stages; p.dcols = sh.dcols; p.tmem_cols = sh.tmem_cols;
   p.nchunks_total = (int)(Tpad / 64);
   p.chunks_per_cta = p.nchunks_total;
-  p.dscale = ic16; p.wsum = igs;
+  p.dscale = ic16; p.igs = igs; p.ccorr = cc16; p.wsum = wsum;
   p.out = Yt; p.ldo = ldy;
   p.bimg_hi = (const float*)Wimg;
   p.b_bulk = 1;
@@ -1252,8 +1305,8 @@ int project_S16_tc(const uint16_t* A16, int64_t T, int64_t S, int64_t ldc, const
   return launch_tc<1, false, 1, 0, false, false, MODE_H16>(mx, mx, mx, p, grid, sh.smem, stream);
 }
 
-int project_T16_tc(const uint16_t* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* Yt, int64_t ldy,
-                   int64_t l, float* Z, int64_t ldz, void* workspace, cudaStream_t stream) {
+int project_T16_tc(const uint16_t* A16, int64_t T, int64_t S, int64_t ldc, const float* ic16, const float* cc16, const float* Yt,
+                   int64_t ldy, int64_t l, float* Z, int64_t ldz, void* workspace, cudaStream_t stream) {
   const int lp = (int)lpad(l);
   const Shape sh = pick_shape_T(lp, 1, S, ldc);
   XB_CHECK_ARG(sh.stages >= 1, "project_T16: no pipeline shape fits lp=%d", lp);
@@ -1265,8 +1318,13 @@ int project_T16_tc(const uint16_t* A16, int64_t T, int64_t S, int64_t ldc, const
   float* amax = (float*)ws; ws += align256(lp * 4);
   float* gs = (float*)ws; ws += align256(lp * 4);
   float* igs = (float*)ws; ws += align256(lp * 4);
+  float* rvec = (float*)ws; ws += align256(lp * 4);
   float* part = (float*)ws; ws += align256((int64_t)g.splits * g.rows_pad * lp * 4);
   uint16_t* Yimg = (uint16_t*)ws;
+  if (cc16) {  // rank-1 term of the shifted copy: r[j] = sum_s cc16[s] Yt[j,s]
+    int rc0 = launch_ccorr_dot(Yt, S, ldy, cc16, lp, rvec, stream);
+    if (rc0) return rc0;
+  }
   XB_CUDA(cudaMemsetAsync(amax, 0, lp * 4, stream));
   absmax_cols_kernel<<<dim3((unsigned)imin(ceil_div(S, 256 * 8), 2 * (int64_t)num_sms()), (unsigned)lp), 256, 0, stream>>>(
       Yt, S, ldy, lp, 1, ic16, amax);
@@ -1289,8 +1347,8 @@ int project_T16_tc(const uint16_t* A16, int64_t T, int64_t S, int64_t ldc, const
   dim3 grid((unsigned)g.t_tiles, (unsigned)g.splits);
   rc = launch_T_mode<MODE_H16>(kb, true, mx, mx, p, grid, sh.smem, stream);
   if (rc) return rc;
-  reduce_partials_kernel<<<(unsigned)ceil_div(T * lp, 256), 256, 0, stream>>>(part, g.splits, g.rows_pad, lp, T, nullptr, nullptr,
-                                                                              Z, ldz, igs);
+  reduce_partials_kernel<<<(unsigned)ceil_div(T * lp, 256), 256, 0, stream>>>(part, g.splits, g.rows_pad, lp, T,
+                                                                              cc16 ? rvec : nullptr, nullptr, Z, ldz, igs);
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
 }
