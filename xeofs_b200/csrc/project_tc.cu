@@ -153,7 +153,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   // 128-byte row segments (a thread owns 32 bytes of a row: stored directly they are scattered 16-byte writes)
   constexpr int CPITCH = KB * 64 + 16;
   uint8_t* cst = pd + (SIDE_T ? (size_t)stages * KB * 256 : 0);
-  uint64_t* bars = (uint64_t*)(cst + (MODE == MODE_WCOPY ? 2 * TC_TILE * CPITCH : 0));
+  uint64_t* bars = (uint64_t*)(cst + ((MODE == MODE_WCOPY && SIDE_T) ? 2 * TC_TILE * CPITCH : 0));
   uint64_t* full = bars;                       // TMA bytes landed
   uint64_t* empty = bars + TC_MAX_STAGES;      // MMAs of the stage retired
   uint64_t* aready = bars + 2 * TC_MAX_STAGES; // A operand of the stage is in TMEM
