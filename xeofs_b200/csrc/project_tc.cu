@@ -487,7 +487,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         tmem_st<KW>(a_slot + kb * TC_KC, hi);
         if (NS >= 2) tmem_st<KW>(a_slot + kb * TC_KC + TC_KC * KB, lo);
       }
-      if (MODE == MODE_WCOPY) {
+      if (MODE == MODE_WCOPY && SIDE_T) {
         // all operand warps have written the stage's tile: every warp stores 16 of its rows, 4 rows (4 x KB*64 bytes
         // of contiguous global memory each) per instruction
         asm volatile("bar.sync 1, %0;" ::"r"(128 * NW) : "memory");
