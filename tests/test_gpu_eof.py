@@ -172,4 +172,7 @@ def test_flat_spectra_match_oracle(kind, n_iter, h16, monkeypatch):
     coords = {"lat": np.linspace(80, -80, nlat), "lon": np.arange(nlon) * 2.0}
     o, m = _fit_both(X, coords, k, random_state=5, solver_kwargs={"n_iter": n_iter})
     assert (m.preprocessor.fitted.field.h16 is not None) == h16
-    _compare(o, m, k, vec_tol=1e-4, elem_atol=5e-3)
+    # (element-wise bound on the scores: |<u_ref, u>| >= 1 - 1e-4 allows |u - u_ref| = 1.4e-2 |u|, i.e. ~4e-3 of the
+    # largest of 2000 noise-like entries per entry on average — the vector criterion is the north star's, the element-wise
+    # one is set just above what it implies)
+    _compare(o, m, k, vec_tol=1e-4, elem_atol=1e-2)
