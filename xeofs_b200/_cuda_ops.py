@@ -64,6 +64,7 @@ class CudaOps:
         self.launches = 0  # kernels enqueued through this object (bench.py reports it)
         self.time_products = False  # bench.py: CUDA events around every streaming product on the launch stream
         self._prod_events = []
+        self._h16_fitted = set()  # (T, pitch) of fp16 copies that fitted in HBM before
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -168,11 +169,20 @@ class CudaOps:
         copy = None
         if center and self.use_h16 and self.h16_stats_copy and T * S * 4 >= self.h16_min_bytes:
             pitch = (S + 127) // 128 * 128
-            free, _ = torch.cuda.mem_get_info(self.device)
-            cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
-            if T * pitch * 2 + (4 << 30) <= free + cached:
-                copy = (torch.empty((T, pitch), dtype=torch.int16, device=self.device), self.empty(S), self.empty(S),
-                        self.empty(S))
+            # the memory queries cost ~0.5 ms of host time: ask once per shape, afterwards just try the allocation
+            fits = (T, pitch) in self._h16_fitted
+            if not fits:
+                free, _ = torch.cuda.mem_get_info(self.device)
+                cached = torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+                fits = T * pitch * 2 + (4 << 30) <= free + cached
+            if fits:
+                try:
+                    copy = (torch.empty((T, pitch), dtype=torch.int16, device=self.device), self.empty(S),
+                            self.empty(S), self.empty(S))
+                    self._h16_fitted.add((T, pitch))
+                except torch.cuda.OutOfMemoryError:
+                    self._h16_fitted.discard((T, pitch))
+                    copy = None
         if copy is not None:
             A16, c0, ic16, cc16 = copy
             check(self._timed("project_S_stats_wcopy", l, lambda: self.lib.xeofs_b200_project_S_stats_h16copy(

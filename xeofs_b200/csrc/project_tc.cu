@@ -747,18 +747,37 @@ __global__ void h16_prescale_kernel(const float* __restrict__ X, int64_t T, int6
   c0[s] = ldexpf(1.f, k);
 }
 
-// amax[j] = max_n |M(n, j) f(n)| over a k-column matrix (side 0: time-side n x ld, f = 1; side 1: space-side, f = fac)
+// amax[j] = max_n |M(n, j) f(n)| over a k-column matrix (side 0: time-side n x ld, f = 1; side 1: space-side, f = fac).
+// Side 1 with cc also leaves the block's share of r[j] = sum_n cc[n] M(n, j) in dpart[blockIdx.x * lp + j]
+// (h16_colscale_kernel adds the shares in block order, so r does not depend on scheduling).
 __global__ void __launch_bounds__(256)
 absmax_cols_kernel(const float* __restrict__ M, int64_t n, int64_t ld, int lp, int side, const float* __restrict__ fac,
-                   float* __restrict__ amax) {
+                   float* __restrict__ amax, const float* __restrict__ cc, double* __restrict__ dpart) {
   if (side == 1) {
     const int j = blockIdx.y;
     float m = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-      m = fmaxf(m, fabsf(M[(int64_t)j * ld + i] * (fac ? fac[i] : 1.f)));
+    double acc = 0.0;
+    const float* row = M + (int64_t)j * ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const float v = row[i];
+      m = fmaxf(m, fabsf(v * (fac ? fac[i] : 1.f)));
+      if (cc) acc += (double)cc[i] * (double)v;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(&amax[j]), __float_as_int(m));
+    if (cc) {
+      __shared__ double sh[8];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double a = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sh[w];
+        dpart[(int64_t)blockIdx.x * lp + j] = a;
+      }
+    }
   } else {
     // consecutive threads walk a row; thread t owns column t % lp for rows t / lp + i * (256 / lp)... simple version:
     for (int j = threadIdx.x; j < lp; j += blockDim.x) {
@@ -772,14 +791,20 @@ __global__ void recip_kernel(const float* __restrict__ a, int n, float* __restri
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) o[j] = 1.f / a[j];
 }
-// gs[j] = the power of two that brings amax[j] to ~2^12 (1 for an empty column)
-__global__ void h16_colscale_kernel(const float* __restrict__ amax, int lp, float* __restrict__ gs) {
+// gs[j] = the power of two that brings amax[j] to ~2^12 (1 for an empty column); r[j] = the sum of the nparts shares
+__global__ void h16_colscale_kernel(const float* __restrict__ amax, int lp, float* __restrict__ gs,
+                                    const double* __restrict__ dpart, int nparts, float* __restrict__ r) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= lp) return;
   const float a = amax[j];
   int k = 0;
   if (a > 0.f && a == a && a < 3.0e38f) k = max(-100, min(100, 12 - (int)ceilf(log2f(a))));
   gs[j] = ldexpf(1.f, k);
+  if (dpart) {
+    double acc = 0.0;
+    for (int b = 0; b < nparts; ++b) acc += dpart[(int64_t)b * lp + j];
+    r[j] = (float)acc;
+  }
 }
 // W (T x ldw, time-side) -> fp16 images of the 64-wide K slabs of W^T (K = t), column j scaled by gs[j].  Zero beyond T.
 __global__ void __launch_bounds__(256)
@@ -992,8 +1017,10 @@ int64_t tc_workspace_bytes(int64_t T, int64_t S, int64_t l, int algo) {
     const int64_t b = (int64_t)g.splits * g.rows_pad * lp * 4;
     if (b > part) part = b;
   }
-  const int64_t Spad = round_up(S, 128);
-  const int64_t bt = align256(lp * 4) + 2 * align256(Spad * 4) + align256(part) + (x3 ? 2 : 1) * align256(lp * Spad * 4);
+  // (the fp16 passes keep amax | gs | igs | rvec, partials, the fp16 image and the shares of the rank-1 term here)
+  const int64_t Spad = round_up(S, 256);
+  const int64_t bt = 4 * align256(lp * 4) + 2 * align256(Spad * 4) + align256(part) + (x3 ? 2 : 1) * align256(lp * Spad * 4) +
+                     align256(2 * (int64_t)num_sms() * lp * 8);
   return (bs > bt ? bs : bt) + 256;
 }
 
@@ -1282,8 +1309,8 @@ int project_S16_tc(const uint16_t* A16, int64_t T, int64_t S, int64_t ldc, const
     if (rc0) return rc0;
   }
   XB_CUDA(cudaMemsetAsync(amax, 0, lp * 4, stream));
-  absmax_cols_kernel<<<(unsigned)imin(T, 512), 128, 0, stream>>>(W, T, ldw, lp, 0, nullptr, amax);
-  h16_colscale_kernel<<<1, 128, 0, stream>>>(amax, lp, gs);
+  absmax_cols_kernel<<<(unsigned)imin(T, 512), 128, 0, stream>>>(W, T, ldw, lp, 0, nullptr, amax, nullptr, nullptr);
+  h16_colscale_kernel<<<1, 128, 0, stream>>>(amax, lp, gs, nullptr, 0, nullptr);
   recip_kernel<<<1, 128, 0, stream>>>(gs, lp, igs);
   prep_W16_kernel<<<(unsigned)(Tpad / 64), 256, 0, stream>>>(W, T, ldw, lp, gs, Wimg);
   XB_LAUNCH_CHECK();
@@ -1321,14 +1348,13 @@ int project_T16_tc(const uint16_t* A16, int64_t T, int64_t S, int64_t ldc, const
   float* rvec = (float*)ws; ws += align256(lp * 4);
   float* part = (float*)ws; ws += align256((int64_t)g.splits * g.rows_pad * lp * 4);
   uint16_t* Yimg = (uint16_t*)ws;
-  if (cc16) {  // rank-1 term of the shifted copy: r[j] = sum_s cc16[s] Yt[j,s]
-    int rc0 = launch_ccorr_dot(Yt, S, ldy, cc16, lp, rvec, stream);
-    if (rc0) return rc0;
-  }
+  double* dpart = (double*)(ws + align256(lp * Spad * 2));  // inside the fp32-image budget of tc_workspace_bytes
+  const int nparts = (int)imin(ceil_div(S, 256 * 8), 2 * (int64_t)num_sms());
   XB_CUDA(cudaMemsetAsync(amax, 0, lp * 4, stream));
-  absmax_cols_kernel<<<dim3((unsigned)imin(ceil_div(S, 256 * 8), 2 * (int64_t)num_sms()), (unsigned)lp), 256, 0, stream>>>(
-      Yt, S, ldy, lp, 1, ic16, amax);
-  h16_colscale_kernel<<<1, 128, 0, stream>>>(amax, lp, gs);
+  // one read of Yt: column maxima and the rank-1 term of the shifted copy, r[j] = sum_s cc16[s] Yt[j,s]
+  absmax_cols_kernel<<<dim3((unsigned)nparts, (unsigned)lp), 256, 0, stream>>>(Yt, S, ldy, lp, 1, ic16, amax, cc16,
+                                                                              cc16 ? dpart : nullptr);
+  h16_colscale_kernel<<<1, 128, 0, stream>>>(amax, lp, gs, cc16 ? dpart : nullptr, nparts, rvec);
   recip_kernel<<<1, 128, 0, stream>>>(gs, lp, igs);
   tile_Y16_kernel<<<(unsigned)(Spad / 64), 256, 0, stream>>>(Yt, S, ldy, lp, ic16, gs, Yimg);
   XB_LAUNCH_CHECK();
