@@ -200,7 +200,11 @@ class TorchCpuOps:
         dsum.fill_(float(sv.sum()))
         return dsum
 
-    def varimax_accumulate(self, L, S, m, R, power=3.0, colscale=None, want_absmax=False, exact=False, products=3):
+    def varimax_pack(self, L, S, m):
+        return None
+
+    def varimax_accumulate(self, L, S, m, R, power=3.0, colscale=None, want_absmax=False, exact=False, products=3,
+                           packed=None):
         X = L[:m, :S].double().t()
         B = X @ R
         Bc = B * colscale.double()[None, :] if colscale is not None else B

@@ -1,4 +1,6 @@
 """GPU: every C-ABI kernel against a float64 numpy/torch statement of the same operation."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -298,7 +300,8 @@ def test_varimax_accumulate_fp64(ops, S, m):
     ops.varimax_algo = "auto"
 
 
-@pytest.mark.parametrize("S,m", [(64, 8), (4096, 20), (20000, 50), (100037, 100), (30011, 128), (65536 + 17, 97)])
+@pytest.mark.parametrize("S,m", [(64, 8), (33, 5), (4096, 20), (20000, 50), (100037, 100), (30011, 128), (65536 + 17, 97),
+                                 (70001, 104), (9999, 112)])
 def test_varimax_sweep_tcgen05(S, m):
     """The same sweep on the tensor cores (both products kind::tf32 with hi/lo split operands, fp64 accumulation
     across tiles): fp32-level agreement with the fp64 statement."""
@@ -306,18 +309,26 @@ def test_varimax_sweep_tcgen05(S, m):
     ops = CudaOps()
     ops.varimax_algo = "tc"
     Ln, R, Gref, Wref = _varimax_case(ops, S, m, seed=m)
-    G, W, _ = ops.varimax_accumulate(Ln, S, m, R)
+    packed = ops.varimax_pack(Ln, S, m)  # tiles of 64 features from the packed copy (three-product mode: m <= 104)
+    assert packed is not None
+    G, W, _ = ops.varimax_accumulate(Ln, S, m, R, packed=packed)
     scale = float(Gref.abs().max())
     np.testing.assert_allclose(G.cpu().numpy(), Gref.cpu().numpy(), atol=2e-6 * scale)
     np.testing.assert_allclose(W.cpu().numpy(), Wref.cpu().numpy(), rtol=2e-6)
     # the sweep is deterministic (fixed tile order per CTA, partial sums added in a fixed order)
-    G2, W2, _ = ops.varimax_accumulate(Ln, S, m, R)
+    G2, W2, _ = ops.varimax_accumulate(Ln, S, m, R, packed=packed)
     assert torch.equal(G, G2) and torch.equal(W, W2)
     # single-TF32 mode (the first phase of the iteration): operands rounded to 11 bits, errors of ~1e-3 per term that
     # average out over the features
-    G1, W1, _ = ops.varimax_accumulate(Ln, S, m, R, products=1)
-    np.testing.assert_allclose(G1.cpu().numpy(), Gref.cpu().numpy(), atol=3e-3 * scale)
-    np.testing.assert_allclose(W1.cpu().numpy(), Wref.cpu().numpy(), rtol=3e-3)
+    for pk in (packed, None):
+        G1, W1, _ = ops.varimax_accumulate(Ln, S, m, R, products=1, packed=pk)
+        np.testing.assert_allclose(G1.cpu().numpy(), Gref.cpu().numpy(), atol=3e-3 * scale)
+        np.testing.assert_allclose(W1.cpu().numpy(), Wref.cpu().numpy(), rtol=3e-3)
+    # without the packed copy: tiles of 32 features through tensor maps (also what m > 104 falls back to in the
+    # three-product mode)
+    G3, W3, _ = ops.varimax_accumulate(Ln, S, m, R)
+    np.testing.assert_allclose(G3.cpu().numpy(), Gref.cpu().numpy(), atol=2e-6 * scale)
+    np.testing.assert_allclose(W3.cpu().numpy(), Wref.cpu().numpy(), rtol=2e-6)
 
 
 @pytest.mark.parametrize("T,S,nan_cols", [(700, 70000, 0), (300, 66001, 37)])

@@ -18,6 +18,8 @@ for step in "$@"; do
     clchk)    XEOFS_TC_CLUSTER=2 timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "tcgen05 or fused" > gpurun_out/${tag}_clchk.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_clchk.log ;;
     small)    { timeout 300 python tools/bench_small.py; timeout 300 python tools/bench_small.py 518400 110; } > gpurun_out/${tag}_small.log 2>&1 ;;
     profile_c4) timeout 900 python tools/profile_fit.py c4 > gpurun_out/${tag}_profile_c4.log 2>&1 ;;
+    vt)       { timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "varimax"; echo "pytest exit $?";
+                timeout 300 python tools/bench_varimax.py; } > gpurun_out/${tag}_vt.log 2>&1 ;;
     profile_c3) timeout 600 python tools/profile_fit.py c3 > gpurun_out/${tag}_profile_c3.log 2>&1 ;;
     profile_c5) timeout 600 python tools/profile_fit.py c5 > gpurun_out/${tag}_profile_c5.log 2>&1 ;;
     two)      { timeout 600 python -m pytest tests -m gpu -q -k "two_gpus"; echo "pytest exit $?";

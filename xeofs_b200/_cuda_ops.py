@@ -533,9 +533,25 @@ class CudaOps:
         self.launches += 12
         return dsum
 
-    def varimax_accumulate(self, L, S, m, R, power=3.0, colscale=None, want_absmax=False, exact=False, products=3):
+    def varimax_pack(self, L, S, m):
+        """The tile-by-tile copy of the normalised loadings the tensor-core sweeps read (made once per rotation), or
+        None where the packed kernel does not apply."""
+        if not self._varimax_tc_applies(L, S, m, False):
+            return None
+        need = int(self.lib.xeofs_b200_varimax_pack_bytes(S, m))
+        if need <= 0:
+            return None
+        packed = torch.empty(need // 4, dtype=torch.float32, device=self.device)
+        check(self.lib.xeofs_b200_varimax_pack(ptr(L), S, m, int(L.stride(0)), ptr(packed), need, self._stream()),
+              "varimax_pack")
+        self.launches += 1
+        return packed
+
+    def varimax_accumulate(self, L, S, m, R, power=3.0, colscale=None, want_absmax=False, exact=False, products=3,
+                           packed=None):
         """One sweep over the normalised loadings (linalg/_numpy/_rotation.py:166-170): Gout = Ln^T f(Ln R), W = colsum
-        ((Ln R)^2).  exact=True keeps every product in fp64 (stopping thresholds below ~1e-9)."""
+        ((Ln R)^2).  exact=True keeps every product in fp64 (stopping thresholds below ~1e-9).  packed: what
+        varimax_pack returned for the same L."""
         G = self.empty((m, m), torch.float64)
         Wv = self.empty(m, torch.float64)
         if power == 3.0 and colscale is None and not want_absmax and self._varimax_tc_applies(L, S, m, exact):
@@ -544,7 +560,7 @@ class CudaOps:
                 self._vws = torch.empty(need, dtype=torch.uint8, device=self.device)
             check(self._timed("varimax_sweep" if products == 3 else "varimax_sweep_x1", m,
                               lambda: self.lib.xeofs_b200_varimax_sweep(
-                ptr(L), S, m, int(L.stride(0)), ptr(R), ptr(G), ptr(Wv), 0, int(products), ptr(self._vws),
+                ptr(L), ptr(packed), S, m, int(L.stride(0)), ptr(R), ptr(G), ptr(Wv), 0, int(products), ptr(self._vws),
                 self._vws.numel(), self._stream())), "varimax_sweep")
             self.launches += 4
             return G, Wv, None

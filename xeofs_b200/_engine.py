@@ -260,23 +260,28 @@ def orthonormalize(ops, M, dim, l, comm, passes, infos):
 _SKETCH_CACHE = {}
 
 
-def draw_sketch(random_state, rows, l):
+def draw_sketch(random_state, rows, l, f32=False):
     """The host draw of sklearn's range finder, rng.normal(size=(rows, l)) with numpy's legacy RandomState (the
     stream the reference uses, so both sides project on the same sketch).  The generator fills row-major, so the
     first n rows of a larger draw are the draw for n rows.  The draw is a pure function of an integer seed and the
-    shape (about 30 ns per number, single-threaded): the last few are memoised."""
-    if isinstance(random_state, np.random.RandomState):
-        return random_state.normal(size=(rows, l))
-    if random_state is None:
-        return np.random.RandomState(None).normal(size=(rows, l))
+    shape (about 30 ns per number, single-threaded): the last few are memoised, and so is their fp32 image (f32=True:
+    what goes to the device; the conversion of a wide sketch costs milliseconds)."""
+    if isinstance(random_state, np.random.RandomState) or random_state is None:
+        rs = random_state if random_state is not None else np.random.RandomState(None)
+        hit = rs.normal(size=(rows, l))
+        return hit.astype(np.float32) if f32 else hit
     key = (int(random_state), int(rows), int(l))
     hit = _SKETCH_CACHE.get(key)
     if hit is None:
-        hit = np.random.RandomState(key[0]).normal(size=(rows, l))
+        hit = [np.random.RandomState(key[0]).normal(size=(rows, l)), None]
         if len(_SKETCH_CACHE) >= 4:
             _SKETCH_CACHE.pop(next(iter(_SKETCH_CACHE)))
         _SKETCH_CACHE[key] = hit
-    return hit
+    if not f32:
+        return hit[0]
+    if hit[1] is None:
+        hit[1] = hit[0].astype(np.float32)
+    return hit[1]
 
 
 def sketch_matrix(ops, op, l, random_state, comm=NO_COMM, predrawn=None):
@@ -288,7 +293,7 @@ def sketch_matrix(ops, op, l, random_state, comm=NO_COMM, predrawn=None):
     if predrawn is not None and predrawn.shape[0] >= n_valid_global and predrawn.shape[1] == l:
         Om = predrawn[:n_valid_global]
     else:
-        Om = draw_sketch(random_state, n_valid_global, l)
+        Om = draw_sketch(random_state, n_valid_global, l, f32=True)
     n_loc_valid = n_local if mask is None else int(mask.sum().item())
     offset = 0
     if side == 1 and comm.active:  # features are sharded: this rank's first valid feature in the global order

@@ -50,7 +50,9 @@ SIGNATURES = {
     "xeofs_b200_finish_components": (_int, [_p, _i64, _i64, _i64, _p, _p, _p]),
     "xeofs_b200_varimax_accumulate": (_int, [_p, _i64, _i64, _i64, _p, _p, C.c_double, _p, _p, _p, _p, _int, _p]),
     "xeofs_b200_varimax_workspace_bytes": (_i64, [_i64, _i64]),
-    "xeofs_b200_varimax_sweep": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _int, _int, _p, _i64, _p]),
+    "xeofs_b200_varimax_pack_bytes": (_i64, [_i64, _i64]),
+    "xeofs_b200_varimax_pack": (_int, [_p, _i64, _i64, _i64, _p, _i64, _p]),
+    "xeofs_b200_varimax_sweep": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _int, _int, _p, _i64, _p]),
     "xeofs_b200_varimax_update_workspace_bytes": (_i64, [_i64]),
     "xeofs_b200_varimax_update": (_int, [_p, _p, _p, C.c_double, _i64, _p, _p, _p, C.c_double, _p, _i64, _p]),
     "xeofs_b200_col_norms": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),

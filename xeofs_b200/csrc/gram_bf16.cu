@@ -173,22 +173,58 @@ __global__ void gram_bf16_reduce_kernel(const float* __restrict__ part, int spli
   *reinterpret_cast<float4*>(G + (row0 + r) * ldg + col0 + j) = a;
 }
 
+// out[t, s] = bf16 of the preprocessed value (zeros in the padding).  VEC: eight features per thread — two 16-byte
+// loads, one 16-byte store (X 16-byte aligned with ldx % 4 == 0, out 16-byte aligned with ldo % 8 == 0); else one.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 materialize_bf16_kernel(const float* __restrict__ X, int64_t T, int64_t S, int64_t ldx, const float* __restrict__ pivot,
                         const float* __restrict__ dscale, const float* __restrict__ ccorr,
                         const uint8_t* __restrict__ row_valid, int64_t rows_out, int64_t cols_out,
                         __nv_bfloat16* __restrict__ out, int64_t ldo) {
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= cols_out) return;
-  const bool in = s < S;
-  const float p = in ? pivot[s] : 0.f, d = in ? dscale[s] : 0.f, c = (in && ccorr) ? ccorr[s] : 0.f;
+  constexpr int W = VEC ? 8 : 1;
+  const int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * W;
+  if (s0 >= cols_out) return;
+  float p[W], d[W], c[W];
+#pragma unroll
+  for (int e = 0; e < W; ++e) {
+    const bool in = s0 + e < S;
+    p[e] = in ? pivot[s0 + e] : 0.f;
+    d[e] = in ? dscale[s0 + e] : 0.f;
+    c[e] = (in && ccorr) ? ccorr[s0 + e] : 0.f;
+  }
+  const bool full = s0 + W <= S;  // (a vector never straddles cols_out: both are multiples of 8)
   for (int64_t t = blockIdx.y; t < rows_out; t += gridDim.y) {
-    float v = 0.f;
-    if (in && t < T && (!row_valid || row_valid[t])) {
-      const float x = X[t * ldx + s] - p;
-      v = ((x == x) ? x * d : 0.f) + c;
+    float v[W];
+#pragma unroll
+    for (int e = 0; e < W; ++e) v[e] = 0.f;
+    if (t < T && (!row_valid || row_valid[t])) {
+      float x[W];
+      if (VEC && full) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(X + t * ldx + s0));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(X + t * ldx + s0 + 4));
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+        if (W == 8) { x[W - 4] = b.x; x[W - 3] = b.y; x[W - 2] = b.z; x[W - 1] = b.w; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < W; ++e) x[e] = s0 + e < S ? X[t * ldx + s0 + e] : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < W; ++e) {
+        const float y = x[e] - p[e];
+        v[e] = s0 + e < S ? ((y == y) ? y * d[e] : 0.f) + c[e] : 0.f;
+      }
     }
-    out[t * ldo + s] = __float2bfloat16_rn(v);
+    if (VEC) {
+      uint4 o;
+      __nv_bfloat162 h;
+      h = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(v[2 % W], v[3 % W]); o.y = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(v[4 % W], v[5 % W]); o.z = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(v[6 % W], v[7 % W]); o.w = *reinterpret_cast<uint32_t*>(&h);
+      *reinterpret_cast<uint4*>(out + t * ldo + s0) = o;
+    } else {
+      out[t * ldo + s0] = __float2bfloat16_rn(v[0]);
+    }
   }
 }
 
@@ -238,8 +274,16 @@ extern "C" int xeofs_b200_materialize_bf16(const float* X, int64_t T, int64_t S,
   cudaStream_t stream = (cudaStream_t)stream_;
   XB_CHECK_ARG(X && pivot && dscale && out, "materialize_bf16: null pointer");
   XB_CHECK_ARG(T > 0 && S > 0 && ldx >= S && rows_out >= T && cols_out >= S && ldo >= cols_out, "materialize_bf16: bad shape");
-  materialize_bf16_kernel<<<dim3((unsigned)ceil_div(cols_out, 256), (unsigned)imin(rows_out, 4096)), 256, 0, stream>>>(
-      X, T, S, ldx, pivot, dscale, ccorr, row_valid, rows_out, cols_out, (__nv_bfloat16*)out, ldo);
+  const bool vec = ldx % 4 == 0 && (uintptr_t)X % 16 == 0 && ldo % 8 == 0 && (uintptr_t)out % 16 == 0 && cols_out % 8 == 0;
+  if (vec) {
+    const unsigned gx = (unsigned)ceil_div(cols_out, 256 * 8);
+    const unsigned gy = (unsigned)imin(rows_out, ceil_div(16 * (int64_t)num_sms(), gx) + 1);
+    materialize_bf16_kernel<true><<<dim3(gx, gy), 256, 0, stream>>>(X, T, S, ldx, pivot, dscale, ccorr, row_valid, rows_out,
+                                                                    cols_out, (__nv_bfloat16*)out, ldo);
+  } else {
+    materialize_bf16_kernel<false><<<dim3((unsigned)ceil_div(cols_out, 256), (unsigned)imin(rows_out, 4096)), 256, 0, stream>>>(
+        X, T, S, ldx, pivot, dscale, ccorr, row_valid, rows_out, cols_out, (__nv_bfloat16*)out, ldo);
+  }
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
 }

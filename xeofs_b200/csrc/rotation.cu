@@ -129,8 +129,11 @@ varimax_accumulate_kernel(const float* __restrict__ L, int64_t S, int m, int64_t
 // rotation_tc.cu
 int64_t varimax_tc_workspace_bytes(int64_t S, int64_t m);
 bool varimax_tc_supported(const float* L, int64_t S, int64_t m, int64_t ld);
-int varimax_sweep_tc(const float* L, int64_t S, int64_t m, int64_t ld, const double* R, double* Gout, double* Wout,
-                     int accumulate, int products, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+int varimax_sweep_tc(const float* L, const float* packed, int64_t S, int64_t m, int64_t ld, const double* R, double* Gout,
+                     double* Wout, int accumulate, int products, void* workspace, int64_t workspace_bytes,
+                     cudaStream_t stream);
+int64_t varimax_pack_bytes(int64_t S, int64_t m);
+int varimax_pack(const float* L, int64_t S, int64_t m, int64_t ld, float* packed, cudaStream_t stream);
 
 }  // namespace xb
 
@@ -138,9 +141,23 @@ using namespace xb;
 
 extern "C" int64_t xeofs_b200_varimax_workspace_bytes(int64_t S, int64_t m) { return varimax_tc_workspace_bytes(S, m); }
 
-extern "C" int xeofs_b200_varimax_sweep(const float* Ln, int64_t S, int64_t m, int64_t ld, const double* R, double* Gout,
-                                        double* Wout, int accumulate, int products, void* workspace,
-                                        int64_t workspace_bytes, void* stream_) {
+extern "C" int64_t xeofs_b200_varimax_pack_bytes(int64_t S, int64_t m) {
+  return xeofs_b200_has_tcgen05() ? varimax_pack_bytes(S, m) : 0;
+}
+
+extern "C" int xeofs_b200_varimax_pack(const float* Ln, int64_t S, int64_t m, int64_t ld, float* packed,
+                                       int64_t packed_bytes, void* stream_) {
+  XB_CHECK_ARG(Ln && packed && S > 0 && ld >= S && m >= 2 && m <= 128, "varimax_pack: bad arguments");
+  XB_CHECK_ARG(ld % 4 == 0 && (uintptr_t)Ln % 16 == 0 && (uintptr_t)packed % 128 == 0, "varimax_pack: misaligned pointers");
+  const int64_t need = xeofs_b200_varimax_pack_bytes(S, m);
+  XB_CHECK_ARG(need > 0 && packed_bytes >= need, "varimax_pack: buffer too small (%lld < %lld bytes) or unsupported shape",
+               (long long)packed_bytes, (long long)need);
+  return varimax_pack(Ln, S, m, ld, packed, (cudaStream_t)stream_);
+}
+
+extern "C" int xeofs_b200_varimax_sweep(const float* Ln, const float* packed, int64_t S, int64_t m, int64_t ld,
+                                        const double* R, double* Gout, double* Wout, int accumulate, int products,
+                                        void* workspace, int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   XB_CHECK_ARG(Ln && R && Gout && Wout && workspace && S > 0 && ld >= S, "varimax_sweep: bad arguments");
   XB_CHECK_ARG(products == 1 || products == 3, "varimax_sweep: products must be 1 (single TF32) or 3 (3xTF32)");
@@ -150,7 +167,8 @@ extern "C" int xeofs_b200_varimax_sweep(const float* Ln, int64_t S, int64_t m, i
     set_error("varimax_sweep: needs the tcgen05 path (sm_100, 16-byte aligned Ln, ld %% 4 == 0)");
     return XEOFS_E_UNSUPPORTED;
   }
-  return varimax_sweep_tc(Ln, S, m, ld, R, Gout, Wout, accumulate, products, workspace, workspace_bytes, stream);
+  XB_CHECK_ARG(!packed || (uintptr_t)packed % 128 == 0, "varimax_sweep: misaligned packed copy");
+  return varimax_sweep_tc(Ln, packed, S, m, ld, R, Gout, Wout, accumulate, products, workspace, workspace_bytes, stream);
 }
 
 extern "C" int xeofs_b200_col_norms(const float* L, int64_t S, int64_t m, int64_t ld, float* h, float* rownorm,

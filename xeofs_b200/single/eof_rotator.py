@@ -63,12 +63,15 @@ class EOFRotator:
         # Far from convergence the tensor-core phase starts with single-TF32 sweeps (a third of the tensor work): their
         # rounding noise (1e-3 per term, averaged over the features) is far below the change of the rotation there.
         x1 = use_tc and rtol < X1_RTOL
+        # the loadings are constant over the iterations: the tensor-core sweeps read a tile-by-tile copy of them
+        packed = ops.varimax_pack(Ln, S_local, m) if use_tc else None
         hist, read, d, d_old, converged, it = [], 0, None, None, False, 0
         self.n_iter_tc_ = self.n_iter_x1_ = 0
         for it in range(1, max_iter + 1):
             if use_tc and not test and it > max_iter - 2:
                 use_tc, self.n_iter_tc_ = False, it - 1
-            G3, W, _ = ops.varimax_accumulate(Ln, S_local, m, R, exact=not use_tc, products=1 if (use_tc and x1) else 3)
+            G3, W, _ = ops.varimax_accumulate(Ln, S_local, m, R, exact=not use_tc, products=1 if (use_tc and x1) else 3,
+                                              packed=packed)
             comm.sum_(G3)
             comm.sum_(W)
             ops.varimax_update(G3, W, XtX, alpha, R, basis, hist_dev[it - 1:it],
