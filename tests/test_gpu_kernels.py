@@ -289,9 +289,9 @@ def _varimax_case(ops, S, m, seed):
     return Ln, R, X.t() @ B**3, (B * B).sum(0)
 
 
-@pytest.mark.parametrize("S,m", [(40, 3), (1001, 10), (5000, 33)])
+@pytest.mark.parametrize("S,m", [(40, 3), (1001, 10), (5000, 33), (777, 64), (20011, 100), (130, 104), (3000, 110)])
 def test_varimax_accumulate_fp64(ops, S, m):
-    """linalg/_numpy/_rotation.py:166-170, the fp64 CUDA-core sweep."""
+    """linalg/_numpy/_rotation.py:166-170, the fp64 sweep (CUDA cores; 32 < m <= 104: the fp64 mma.sync kernel)."""
     ops.varimax_algo = "simt"
     Ln, R, Gref, Wref = _varimax_case(ops, S, m, seed=S)
     G, W, _ = ops.varimax_accumulate(Ln, S, m, R)

@@ -39,5 +39,29 @@ def main():
                   f"({tf:.0f} TFLOP/s tf32, {S * m * 4 / ms / 1e6:.0f} GB/s)", flush=True)
 
 
+def exact():
+    """the fp64 sweep (the last iterations of a rotation), mma.sync kernel and the CUDA-core one"""
+    S, m = 1440 * 2880, 100
+    ops = CudaOps()
+    ops.varimax_algo = "simt"
+    g = torch.Generator(device="cuda").manual_seed(1)
+    Ln = ops.space_side((m + 15) // 16 * 16, S, zero=True)
+    Ln[:m] = torch.randn((m, S), generator=g, device="cuda") / S**0.5
+    R = torch.linalg.qr(torch.randn((m, m), generator=g, device="cuda", dtype=torch.float64))[0].contiguous()
+    for mma in ("1", "0"):
+        os.environ["XEOFS_VX_MMA"] = mma
+        ops.varimax_accumulate(Ln, S, m, R, exact=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            G, W, _ = ops.varimax_accumulate(Ln, S, m, R, exact=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print(f"fp64 sweep, mma.sync={mma}: {ms:.2f} ms ({4.0 * S * m * m / ms / 1e9:.1f} TFLOP/s fp64)", flush=True)
+    del os.environ["XEOFS_VX_MMA"]
+
+
 if __name__ == "__main__":
+    exact()
     main()

@@ -126,6 +126,138 @@ varimax_accumulate_kernel(const float* __restrict__ L, int64_t S, int m, int64_t
   }
 }
 
+// The varimax case of the same pass (power 3, no column scale) on the fp64 tensor-core path: both products as
+// mma.sync m8n8k4 (IEEE fp64 FMAs, so the arithmetic is the one of the kernel above), 64 features per turn.
+//   GEMM1  B[s, j] = sum_i L[s, i] R[i, j]      warp w owns the 8 features 8w.., all MT column tiles
+//   f = b^3 (in the accumulator registers), W[j] += b^2 (shuffle over the 8 rows, shared-memory atomics)
+//   GEMM2  G[i, j] += sum_s L[s, i] f[s, j]     warp w owns the row tiles w and w + 8, accumulators live in registers
+//                                               over all the turns of the CTA
+// Shared memory: R, the chunk of loadings and f, all fp64, rows padded to a pitch of 4 mod 16 doubles (the fragment
+// loads of a half-warp then fall into 16 different bank pairs).
+constexpr int VX_CH = 64;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int MT>  // 8-wide tiles of the mode axis (m <= 8 MT)
+__global__ void __launch_bounds__(256, 1)
+varimax_exact_mma_kernel(const float* __restrict__ L, int64_t S, int m, int64_t ld, const float* __restrict__ rownorm,
+                         const double* __restrict__ R, double* __restrict__ Gout, double* __restrict__ Wout) {
+  constexpr int MP = 8 * MT, LDP = MP + 4, MW = (MT + 7) / 8;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* Rs = reinterpret_cast<double*>(smraw);  // [MP][LDP]
+  double* Ls = Rs + MP * LDP;                     // [VX_CH][LDP]
+  double* Fs = Ls + VX_CH * LDP;                  // [VX_CH][LDP]
+  double* Wsh = Fs + VX_CH * LDP;                 // [MP]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;
+  for (int idx = tid; idx < MP * MP; idx += 256) {
+    const int i = idx / MP, j = idx % MP;
+    Rs[i * LDP + j] = (i < m && j < m) ? R[(int64_t)i * m + j] : 0.0;
+  }
+  if (tid < MP) Wsh[tid] = 0.0;
+  double acc2[MW][MT][2];
+#pragma unroll
+  for (int a = 0; a < MW; ++a)
+#pragma unroll
+    for (int b = 0; b < MT; ++b) acc2[a][b][0] = acc2[a][b][1] = 0.0;
+  const int ksteps = (m + 3) >> 2;
+
+  const int64_t n_chunks = (S + VX_CH - 1) / VX_CH;
+  for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const int64_t s0 = ch * VX_CH;
+    __syncthreads();  // GEMM2 of the previous turn has read Ls and Fs (first turn: Rs is written)
+    {
+      const int sl = tid & 63, w4 = tid >> 6;
+      const int64_t s = s0 + sl;
+      const float rn = (s < S) ? (rownorm ? rownorm[s] : 1.f) : 0.f;
+      for (int j = w4; j < MP; j += 4) {
+        float v = 0.f;
+        if (j < m && s < S) v = L[(int64_t)j * ld + s] * rn;
+        Ls[sl * LDP + j] = (double)v;
+      }
+    }
+    __syncthreads();
+    {
+      double acc1[MT][2];
+#pragma unroll
+      for (int b = 0; b < MT; ++b) acc1[b][0] = acc1[b][1] = 0.0;
+      const double* arow = Ls + (8 * warp + lr) * LDP + lc;
+      const double* bcol = Rs + lc * LDP + lr;
+      for (int k = 0; k < ksteps; ++k) {
+        const double a = arow[4 * k];
+#pragma unroll
+        for (int b = 0; b < MT; ++b) dmma884(acc1[b][0], acc1[b][1], a, bcol[4 * k * LDP + 8 * b]);
+      }
+      // accumulator element e of tile b: feature 8 warp + lr, mode 8 b + 2 lc + e
+#pragma unroll
+      for (int b = 0; b < MT; ++b) {
+        const double b0 = acc1[b][0], b1 = acc1[b][1];
+        double w0 = b0 * b0, w1 = b1 * b1;
+        *reinterpret_cast<double2*>(Fs + (8 * warp + lr) * LDP + 8 * b + 2 * lc) = make_double2(w0 * b0, w1 * b1);
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          w0 += __shfl_xor_sync(0xffffffffu, w0, o);
+          w1 += __shfl_xor_sync(0xffffffffu, w1, o);
+        }
+        if (lr == 0) {
+          atomicAdd(&Wsh[8 * b + 2 * lc], w0);
+          atomicAdd(&Wsh[8 * b + 2 * lc + 1], w1);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int k = 0; k < VX_CH / 4; ++k) {
+      double a[MW];
+#pragma unroll
+      for (int x = 0; x < MW; ++x) {
+        const int mt = warp + 8 * x;
+        a[x] = mt < MT ? Ls[(4 * k + lc) * LDP + 8 * mt + lr] : 0.0;
+      }
+      const double* frow = Fs + (4 * k + lc) * LDP + lr;
+#pragma unroll
+      for (int b = 0; b < MT; ++b) {
+        const double fb = frow[8 * b];
+#pragma unroll
+        for (int x = 0; x < MW; ++x)
+          if (warp + 8 * x < MT) dmma884(acc2[x][b][0], acc2[x][b][1], a[x], fb);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int x = 0; x < MW; ++x) {
+    const int mt = warp + 8 * x;
+    if (mt >= MT) continue;
+    const int i = 8 * mt + lr;
+#pragma unroll
+    for (int b = 0; b < MT; ++b) {
+      const int j = 8 * b + 2 * lc;
+      if (i < m && j < m) atomicAdd(&Gout[(int64_t)i * m + j], acc2[x][b][0]);
+      if (i < m && j + 1 < m) atomicAdd(&Gout[(int64_t)i * m + j + 1], acc2[x][b][1]);
+    }
+  }
+  if (tid < m) atomicAdd(&Wout[tid], Wsh[tid]);
+}
+
+template <int MT>
+static int launch_exact_mma(const float* L, int64_t S, int m, int64_t ld, const float* rownorm, const double* R,
+                            double* Gout, double* Wout, cudaStream_t stream) {
+  constexpr int MP = 8 * MT, LDP = MP + 4;
+  const size_t smem = ((size_t)MP * LDP + 2 * (size_t)VX_CH * LDP + MP) * sizeof(double);
+  XB_CUDA(cudaFuncSetAttribute(varimax_exact_mma_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int blocks = (int)imin(ceil_div(S, VX_CH), (int64_t)num_sms());
+  varimax_exact_mma_kernel<MT><<<blocks, 256, smem, stream>>>(L, S, m, ld, rownorm, R, Gout, Wout);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
+// project_tc.cu
+int env_int(const char* name, int dflt);
 // rotation_tc.cu
 int64_t varimax_tc_workspace_bytes(int64_t S, int64_t m);
 bool varimax_tc_supported(const float* L, int64_t S, int64_t m, int64_t ld);
@@ -194,6 +326,9 @@ extern "C" int xeofs_b200_varimax_accumulate(const float* L, int64_t S, int64_t 
     if (absmax) XB_CUDA(cudaMemsetAsync(absmax, 0, (size_t)m * sizeof(float), stream));
   }
   XB_CHECK_ARG(power >= 1.0, "varimax_accumulate: power must be >= 1");
+  if (power == 3.0 && !colscale && !absmax && m > 32 && m <= 104 && env_int("XEOFS_VX_MMA", 1))
+    return m <= 64 ? launch_exact_mma<8>(L, S, (int)m, ld, rownorm, R, Gout, Wout, stream)
+                   : launch_exact_mma<13>(L, S, (int)m, ld, rownorm, R, Gout, Wout, stream);
   const int ti = m <= 16 ? 1 : m <= 32 ? 2 : m <= 64 ? 4 : 8;
   const int MP = 16 * ti;
   const size_t smem = ((size_t)MP * (MP + 1) + (size_t)VM_CHUNK * (MP + 4)) * sizeof(double) +

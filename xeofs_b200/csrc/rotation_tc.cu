@@ -65,23 +65,36 @@ vt_prep_R_kernel(const double* __restrict__ R, int m, float* __restrict__ rhi, f
   }
 }
 
-// Gout[i, j'] (+)= sum_blocks gpart[b][j'][i];  Wout[j'] (+)= sum_blocks wpart[b][0..wparts-1][j']
+// Gout[i, j'] (+)= sum_blocks gpart[b][j'][i];  Wout[j'] (+)= sum_blocks wpart[b][0..wparts-1][j'].  One warp per four
+// consecutive entries: the lanes share the blocks (8 lanes per entry, every lane a fixed subset in a fixed order, then a
+// shuffle tree — the result does not depend on scheduling).
 __global__ void __launch_bounds__(256)
 vt_reduce_kernel(const double* __restrict__ gpart, const double* __restrict__ wpart, int nblk, int m, int ng,
                  double* __restrict__ Gout, double* __restrict__ Wout, int accumulate, int wparts) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < m * m) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int sub = lane >> 2, e = lane & 3;  // 8 subsets of the blocks x 4 entries
+  const int idx = warp * 4 + e;
+  const int n_g = m * m;
+  if (warp * 4 >= n_g + m) return;
+  double a = 0.0;
+  if (idx < n_g) {
     const int j = idx / m, i = idx % m;
-    double a = 0.0;
-    for (int b = 0; b < nblk; ++b) a += gpart[((int64_t)b * 128 + j) * ng + i];
-    double* o = &Gout[(int64_t)i * m + j];
-    *o = accumulate ? *o + a : a;
+    for (int b = sub; b < nblk; b += 8) a += gpart[((int64_t)b * 128 + j) * ng + i];
+  } else if (idx < n_g + m) {
+    const int j = idx - n_g;
+    for (int b = sub; b < nblk; b += 8)
+      for (int h = 0; h < wparts; ++h) a += wpart[((int64_t)b * wparts + h) * 128 + j];
   }
-  if (idx < m) {
-    double w = 0.0;
-    for (int b = 0; b < nblk; ++b)
-      for (int h = 0; h < wparts; ++h) w += wpart[((int64_t)b * wparts + h) * 128 + idx];
-    Wout[idx] = accumulate ? Wout[idx] + w : w;
+  a += __shfl_xor_sync(0xffffffffu, a, 4);
+  a += __shfl_xor_sync(0xffffffffu, a, 8);
+  a += __shfl_xor_sync(0xffffffffu, a, 16);
+  if (sub == 0) {
+    if (idx < n_g) {
+      double* o = &Gout[(int64_t)(idx % m) * m + idx / m];
+      *o = accumulate ? *o + a : a;
+    } else if (idx < n_g + m) {
+      Wout[idx - n_g] = accumulate ? Wout[idx - n_g] + a : a;
+    }
   }
 }
 
@@ -761,7 +774,7 @@ int varimax_sweep_tc(const float* L, const float* packed, int64_t S, int64_t m, 
     }
 #undef XB_VT2
     XB_LAUNCH_CHECK();
-    vt_reduce_kernel<<<(unsigned)ceil_div(m * m, 256), 256, 0, stream>>>(gpart2, q.wpart, grid2, (int)m, ng, Gout, Wout,
+    vt_reduce_kernel<<<(unsigned)ceil_div((m * m + m + 3) / 4 * 32, 256), 256, 0, stream>>>(gpart2, q.wpart, grid2, (int)m, ng, Gout, Wout,
                                                                          accumulate, 4);
     XB_LAUNCH_CHECK();
     return XEOFS_OK;
@@ -790,7 +803,7 @@ int varimax_sweep_tc(const float* L, const float* packed, int64_t S, int64_t m, 
   }
 #undef XB_VT
   XB_LAUNCH_CHECK();
-  vt_reduce_kernel<<<(unsigned)ceil_div(m * m, 256), 256, 0, stream>>>(gpart, wpart, grid, (int)m, ng, Gout, Wout, accumulate, 2);
+  vt_reduce_kernel<<<(unsigned)ceil_div((m * m + m + 3) / 4 * 32, 256), 256, 0, stream>>>(gpart, wpart, grid, (int)m, ng, Gout, Wout, accumulate, 2);
   XB_LAUNCH_CHECK();
   return XEOFS_OK;
 }
