@@ -300,6 +300,46 @@ def test_varimax_accumulate_fp64(ops, S, m):
     ops.varimax_algo = "auto"
 
 
+@pytest.mark.parametrize("m", [2, 7, 50, 100, 101, 118, 128])
+@pytest.mark.parametrize("kind", ["random", "clustered", "warm"])
+def test_varimax_update_polar_factor(ops, m, kind):
+    """The m x m step of a varimax iteration (_rotation.py:170-175): G = G3 - alpha (XtX R) diag(W), R <- U V^T of
+    svd(G), delta = sum(svals) — one-sided Jacobi on G V0 for m <= 118, G^T G + sym_eig above — against LAPACK."""
+    g = torch.Generator(device="cuda").manual_seed(m)
+    rnd = lambda *sh: torch.randn(sh, generator=g, device="cuda", dtype=torch.float64)  # noqa: E731
+    Q0 = torch.linalg.qr(rnd(m, m))[0]
+    Q1 = torch.linalg.qr(rnd(m, m))[0]
+    if kind == "clustered":  # nearly equal singular values (the planted patterns of config 5) and a far one
+        sv = 1.0 + 1e-9 * torch.arange(m, device="cuda", dtype=torch.float64)
+        sv[0] = 50.0
+    else:
+        sv = torch.logspace(0, -3, m, device="cuda", dtype=torch.float64)
+    G3 = (Q0 * sv[None, :]) @ Q1.t()
+    W = torch.rand(m, generator=g, device="cuda", dtype=torch.float64)
+    XtX = rnd(m, m)
+    XtX = XtX @ XtX.t() / m
+    R = torch.linalg.qr(rnd(m, m))[0].contiguous()
+    alpha = 1e-3
+    G = G3 - alpha * (XtX @ R) * W[None, :]
+    U, s, Vh = torch.linalg.svd(G)
+    basis = torch.eye(m, dtype=torch.float64, device="cuda")
+    if kind == "warm":  # the right singular vectors, slightly rotated: what the previous iteration leaves behind
+        K = 1e-3 * rnd(m, m)
+        basis = (Vh.t() @ torch.linalg.matrix_exp(K - K.t())).contiguous()
+    dsum = torch.zeros(1, dtype=torch.float64, device="cuda")
+    Rn = R.clone()
+    ops.varimax_update(G3.contiguous(), W, XtX.contiguous(), alpha, Rn, basis, dsum)
+    ref = U @ Vh
+    tol = 1e-6 if kind == "clustered" else 1e-9  # (the polar factor is as well conditioned as the smallest singular value)
+    assert float((Rn - ref).abs().max()) < tol
+    assert abs(float(dsum.item()) / float(s.sum()) - 1.0) < 1e-12
+    assert float((Rn.t() @ Rn - torch.eye(m, dtype=torch.float64, device="cuda")).abs().max()) < 1e-11
+    # the basis handed to the next iteration diagonalises G^T G
+    D = basis.t() @ (G.t() @ G) @ basis
+    off = D - torch.diag(torch.diagonal(D))
+    assert float(off.norm() / torch.diagonal(D).norm()) < 1e-9
+
+
 @pytest.mark.parametrize("S,m", [(64, 8), (33, 5), (4096, 20), (20000, 50), (100037, 100), (30011, 128), (65536 + 17, 97),
                                  (70001, 104), (9999, 112)])
 def test_varimax_sweep_tcgen05(S, m):

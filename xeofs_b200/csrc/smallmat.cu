@@ -424,6 +424,141 @@ sym_eig_kernel(const double* __restrict__ G, int l, double* __restrict__ evals, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Polar factor of a square matrix by ONE-SIDED Jacobi (Hestenes), one block, fp64 — the m x m step of a varimax
+// iteration (dense64.cu: xeofs_b200_varimax_update).  Input: Gb = G V0 with V0 orthogonal (the right singular vectors
+// of the previous iteration's G: the columns of Gb are then nearly orthogonal and two sweeps finish the job).  Column
+// pairs (round-robin seating as above) are rotated until orthogonal, the same rotations applied to V; at the end
+// Gb = U diag(sigma), so  polar(G) = U V^T,  sum(svals) = sum sigma.  Against the route through G^T G and sym_eig:
+// no squared condition number, one block-wide barrier per round instead of two, every element of the two matrices
+// read and written once per round with conflict-free (column-contiguous) accesses and no parameter traffic — the
+// two-sided kernel is bound by exactly that shared-memory traffic.  One warp per column pair; lanes own rows
+// lane + 32 k.  Both matrices live in shared memory column-major (m <= 118).
+constexpr int PJ_MAX_M = 118;
+
+__global__ void __launch_bounds__(1024, 1)
+polar_jacobi_kernel(const double* __restrict__ Gb_in, double* __restrict__ V_io, int m, double* __restrict__ U_out,
+                    double* __restrict__ dsum, int32_t* __restrict__ info, double eps_stop) {
+  extern __shared__ double sh[];
+  const int le = (m + 1) & ~1, half = le / 2;
+  const int ldc = (m + 1) & ~1;
+  double* Gt = sh;                        // [le][ldc]  column p of Gb at Gt + p ldc
+  double* Vt = Gt + (size_t)le * ldc;     // [le][ldc]
+  __shared__ unsigned long long mxbits;
+  __shared__ double ssum[32];
+  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  for (int idx = tid; idx < le * ldc; idx += nt) {
+    const int p = idx % le, r = idx / le;  // consecutive threads read a row of the row-major inputs
+    const bool in = p < m && r < m;
+    if (r < ldc) {
+      Gt[p * ldc + r] = in ? Gb_in[(int64_t)r * m + p] : 0.0;
+      Vt[p * ldc + r] = in ? V_io[(int64_t)r * m + p] : 0.0;
+    }
+  }
+  if (tid == 0) mxbits = 0ull;
+  __syncthreads();
+
+  int sweeps_done = 0;
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double mx = 0.0;
+    for (int round = 0; round < le - 1; ++round) {
+      for (int q = warp; q < half; q += nw) {
+        int p, r;
+        eig_pair(q, round, le, p, r);
+        if (r >= m) continue;  // the padding column of an odd m
+        double* gp = Gt + p * ldc;
+        double* gq = Gt + r * ldc;
+        double* vp = Vt + p * ldc;
+        double* vq = Vt + r * ldc;
+        double a[4], b[4], x[4], y[4];
+        double al = 0.0, be = 0.0, ga = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int row = lane + 32 * k;
+          const bool in = row < m;
+          a[k] = in ? gp[row] : 0.0;
+          b[k] = in ? gq[row] : 0.0;
+          x[k] = in ? vp[row] : 0.0;
+          y[k] = in ? vq[row] : 0.0;
+          al = fma(a[k], a[k], al);
+          be = fma(b[k], b[k], be);
+          ga = fma(a[k], b[k], ga);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          al += __shfl_xor_sync(0xffffffffu, al, o);
+          be += __shfl_xor_sync(0xffffffffu, be, o);
+          ga += __shfl_xor_sync(0xffffffffu, ga, o);
+        }
+        const double ab = al * be;
+        if (ga * ga > 1e-32 * ab) {  // (also false for a zero column)
+          mx = fmax(mx, fabs(ga) * rsqrt(ab));
+          const double zeta = (be - al) / (2.0 * ga);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = rsqrt(1.0 + t * t), sn = c * t;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int row = lane + 32 * k;
+            if (row < m) {
+              gp[row] = c * a[k] - sn * b[k];
+              gq[row] = sn * a[k] + c * b[k];
+              vp[row] = c * x[k] - sn * y[k];
+              vq[row] = sn * x[k] + c * y[k];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    sweeps_done = sweep + 1;
+    // the largest normalised inner product this sweep met: what is left after it is of the order of its square
+    if (lane == 0) atomicMax(&mxbits, (unsigned long long)__double_as_longlong(mx));
+    __syncthreads();
+    const double seen = __longlong_as_double((long long)mxbits);
+    __syncthreads();
+    if (tid == 0) mxbits = 0ull;
+    if (seen <= eps_stop) break;
+  }
+  __syncthreads();
+  // sigma_p = |column p|, U = Gb diag(1 / sigma), sum sigma; outputs row-major
+  double part = 0.0;
+  for (int p = warp; p < m; p += nw) {
+    double s2 = 0.0;
+    for (int row = lane; row < m; row += 32) s2 = fma(Gt[p * ldc + row], Gt[p * ldc + row], s2);
+    s2 = warp_sum(s2);
+    const double sg = sqrt(s2), inv = sg > 0.0 ? 1.0 / sg : 0.0;
+    for (int row = lane; row < m; row += 32) Gt[p * ldc + row] *= inv;
+    part += sg;
+  }
+  if (lane == 0) ssum[warp] = part;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += ssum[w];
+    *dsum = t;
+    info[0] = sweeps_done;
+  }
+  for (int idx = tid; idx < m * m; idx += nt) {
+    const int r = idx / m, p = idx % m;
+    U_out[idx] = Gt[p * ldc + r];
+    V_io[idx] = Vt[p * ldc + r];
+  }
+}
+
+int polar_jacobi_launch(const double* Gb, double* V, int64_t m, double* U, double* dsum, int32_t* info, double eps_stop,
+                        cudaStream_t stream) {
+  XB_CHECK_ARG(Gb && V && U && dsum && info && m >= 2 && m <= PJ_MAX_M, "polar_jacobi: bad arguments (m=%lld must be in 2..%d)",
+               (long long)m, PJ_MAX_M);
+  const int le = ((int)m + 1) & ~1, half = le / 2;
+  const int per = (half + 31) / 32;                  // pairs per warp and round
+  const int warps = (half + per - 1) / per;
+  const size_t smem = (size_t)2 * le * le * sizeof(double);
+  XB_CUDA(cudaFuncSetAttribute(polar_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  polar_jacobi_kernel<<<1, warps * 32, smem, stream>>>(Gb, V, (int)m, U, dsum, info, eps_stop);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   // ordered-int trick, valid for any finite floats
   if (v >= 0) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
