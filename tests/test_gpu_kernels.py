@@ -304,7 +304,8 @@ def test_varimax_accumulate_fp64(ops, S, m):
 @pytest.mark.parametrize("kind", ["random", "clustered", "warm"])
 def test_varimax_update_polar_factor(ops, m, kind):
     """The m x m step of a varimax iteration (_rotation.py:170-175): G = G3 - alpha (XtX R) diag(W), R <- U V^T of
-    svd(G), delta = sum(svals) — one-sided Jacobi on G V0 for m <= 118, G^T G + sym_eig above — against LAPACK."""
+    svd(G), delta = sum(svals) — through the eigen-decomposition of G^T G in the previous iteration's basis — against
+    LAPACK."""
     g = torch.Generator(device="cuda").manual_seed(m)
     rnd = lambda *sh: torch.randn(sh, generator=g, device="cuda", dtype=torch.float64)  # noqa: E731
     Q0 = torch.linalg.qr(rnd(m, m))[0]
@@ -330,7 +331,7 @@ def test_varimax_update_polar_factor(ops, m, kind):
     Rn = R.clone()
     ops.varimax_update(G3.contiguous(), W, XtX.contiguous(), alpha, Rn, basis, dsum)
     ref = U @ Vh
-    tol = 1e-6 if kind == "clustered" else 1e-9  # (the polar factor is as well conditioned as the smallest singular value)
+    tol = 1e-6 if kind == "clustered" else 1e-8  # (the route through G^T G squares the condition number: 1e6 here)
     assert float((Rn - ref).abs().max()) < tol
     assert abs(float(dsum.item()) / float(s.sum()) - 1.0) < 1e-12
     assert float((Rn.t() @ Rn - torch.eye(m, dtype=torch.float64, device="cuda")).abs().max()) < 1e-11

@@ -18,10 +18,9 @@ for step in "$@"; do
     clchk)    XEOFS_TC_CLUSTER=2 timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "tcgen05 or fused" > gpurun_out/${tag}_clchk.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_clchk.log ;;
     small)    { timeout 300 python tools/bench_small.py; timeout 300 python tools/bench_small.py 518400 110; } > gpurun_out/${tag}_small.log 2>&1 ;;
     profile_c4) timeout 900 python tools/profile_fit.py c4 > gpurun_out/${tag}_profile_c4.log 2>&1 ;;
-    vt)       { timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "varimax"; echo "pytest exit $?"; timeout 300 python -m pytest tests/test_gpu_models.py -x -q -m gpu -k "rotat"; echo "pytest exit $?";
-                timeout 300 python tools/bench_varimax.py; } > gpurun_out/${tag}_vt.log 2>&1 ;;
+    vt)       { timeout 150 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "varimax or gram"; echo "pytest exit $?"; timeout 150 python -m pytest tests/test_gpu_models.py -x -q -m gpu -k "rotat"; echo "pytest exit $?";
+                timeout 120 python tools/bench_varimax.py; } > gpurun_out/${tag}_vt.log 2>&1 ;;
     eig)      timeout 600 python tools/diag_eig.py > gpurun_out/${tag}_eig.log 2>&1 ;;
-    c5stop)   { for v in 16 4; do echo "== XEOFS_VU_STOP4=$v"; XEOFS_VU_STOP4=$v timeout 600 python bench.py --workload c5 --steps 4 --warmup 3 --no-cpu; done; } > gpurun_out/${tag}_c5stop.log 2>&1 ;;
     profile_c3) timeout 600 python tools/profile_fit.py c3 > gpurun_out/${tag}_profile_c3.log 2>&1 ;;
     profile_c5) timeout 600 python tools/profile_fit.py c5 > gpurun_out/${tag}_profile_c5.log 2>&1 ;;
     two)      { timeout 600 python -m pytest tests -m gpu -q -k "two_gpus"; echo "pytest exit $?";

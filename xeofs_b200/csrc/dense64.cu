@@ -319,9 +319,6 @@ static void dgemm_sq(int m, const double* A, const double* B, double* C, cudaStr
 namespace xb {
 int sym_eig_launch(const double* G, int64_t l, double* evals, double* evecs, double* work, int32_t* info, double tol2,
                    cudaStream_t stream);
-int polar_jacobi_launch(const double* Gb, double* V, int64_t m, double* U, double* dsum, int32_t* info, double eps_stop,
-                        cudaStream_t stream);
-int env_int(const char* name, int dflt);
 }
 
 extern "C" int64_t xeofs_b200_varimax_update_workspace_bytes(int64_t m) {
@@ -352,18 +349,6 @@ extern "C" int xeofs_b200_varimax_update(const double* G3, const double* W, cons
   const unsigned eb = (unsigned)ceil_div(mm, 256);
   dgemm_sq<false, false>(mi, XtX, R, T1, stream);                       // XtX R
   vu_form_G_kernel<<<eb, 256, 0, stream>>>(G3, T1, W, alpha, mi, G);    // G
-  if (m <= 118 && env_int("XEOFS_VU_ONESIDED", 1)) {
-    // one-sided Jacobi on G basis: its columns are nearly orthogonal already.  A sweep that met normalised inner
-    // products up to e leaves ~e^2 behind: it is the last one when 16 e^2 <= the tolerance on the off-diagonal norm
-    dgemm_sq<false, false>(mi, G, basis, M, stream);                    // G basis
-    XB_LAUNCH_CHECK();
-    const double tol = eig_tol > 0.0 ? eig_tol : 3e-15;
-    int rc1 = polar_jacobi_launch(M, basis, m, T3, dsum, info, sqrt(tol) / (0.25 * env_int("XEOFS_VU_STOP4", 16)), stream);  // U, V (= basis), delta
-    if (rc1) return rc1;
-    dgemm_sq<false, true>(mi, T3, basis, R, stream);                    // R = U V^T
-    XB_LAUNCH_CHECK();
-    return XEOFS_OK;
-  }
   dgemm_sq<true, false>(mi, G, G, M, stream);                           // G^T G
   dgemm_sq<false, false>(mi, M, basis, T2, stream);                     // (G^T G) basis
   dgemm_sq<true, false>(mi, basis, T2, Mp, stream);                     // basis^T (G^T G) basis

@@ -9,6 +9,7 @@
 
 namespace xb {
 
+int env_int(const char* name, int dflt);  // project_tc.cu
 
 // ------------------------------------------------------------------------------------------------
 // Gram matrix in fp64 (CholeskyQR needs the Gram to cond^2 accuracy).  Persistent blocks sweep chunks of n; the
@@ -267,6 +268,93 @@ apply_kernel(const float* __restrict__ In, int64_t n, int l, int64_t ld_in, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// The space-side Gram matrix (M = l rows of n contiguous values) on the fp64 tensor-core path: mma.sync m8n8k4,
+// IEEE fp64 FMAs as in gram_kernel.  A chunk of 64 values per turn, converted to fp64 on its way into shared memory
+// ([n][8 MT + 4] doubles: the fragment loads of a half-warp fall into 16 different bank pairs); the l x l result is
+// cut into 8 x 8 tiles, only those on or above the diagonal are computed, and warp w owns the tile rows w and
+// MT - 1 - w (MT + 1 tiles each), accumulators in registers over all the turns of the CTA.
+constexpr int GM_CH = 64;
+
+__device__ __forceinline__ void dmma884_g(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int MT>
+__global__ void __launch_bounds__(256)
+gram_mma_kernel(const float* __restrict__ M, int64_t n, int l, int64_t ld, double* __restrict__ G) {
+  constexpr int MP = 8 * MT, LDP = MP + 4;
+  extern __shared__ __align__(16) unsigned char gm_raw[];
+  double* Ms = reinterpret_cast<double*>(gm_raw);  // [GM_CH][LDP]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int mt0 = warp, mt1 = MT - 1 - warp;  // the two tile rows of this warp (the same one in the middle of an odd MT)
+  const bool has0 = mt0 <= mt1, has1 = mt0 < mt1;
+  double acc[2][MT][2];
+#pragma unroll
+  for (int x = 0; x < 2; ++x)
+#pragma unroll
+    for (int b = 0; b < MT; ++b) acc[x][b][0] = acc[x][b][1] = 0.0;
+
+  const int64_t n_chunks = (n + GM_CH - 1) / GM_CH;
+  for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const int64_t s0 = ch * GM_CH;
+    __syncthreads();
+    {
+      const int sl = tid & 63, w4 = tid >> 6;
+      const int64_t s = s0 + sl;
+      for (int j = w4; j < MP; j += 4) Ms[sl * LDP + j] = (j < l && s < n) ? (double)M[(int64_t)j * ld + s] : 0.0;
+    }
+    __syncthreads();
+    if (has0) {
+#pragma unroll 2
+      for (int k = 0; k < GM_CH / 4; ++k) {
+        const double* row = Ms + (4 * k + lc) * LDP + lr;
+        const double a0 = row[8 * mt0], a1 = row[8 * mt1];
+#pragma unroll
+        for (int b = 0; b < MT; ++b) {
+          if (b < mt0) continue;
+          const double fb = row[8 * b];
+          dmma884_g(acc[0][b][0], acc[0][b][1], a0, fb);
+          if (has1 && b >= mt1) dmma884_g(acc[1][b][0], acc[1][b][1], a1, fb);
+        }
+      }
+    }
+  }
+  // element e of tile (mt, b): G[8 mt + lr][8 b + 2 lc + e], mirrored below the diagonal
+#pragma unroll
+  for (int x = 0; x < 2; ++x) {
+    if (x == 0 ? !has0 : !has1) continue;
+    const int mt = x == 0 ? mt0 : mt1;
+    const int i = 8 * mt + lr;
+#pragma unroll
+    for (int b = 0; b < MT; ++b) {
+      if (b < mt) continue;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = 8 * b + 2 * lc + e;
+        if (i < l && j < l) {
+          if (b > mt || j >= i) atomicAdd(&G[(int64_t)i * l + j], acc[x][b][e]);
+          if (b > mt || j > i) atomicAdd(&G[(int64_t)j * l + i], acc[x][b][e]);
+        }
+      }
+    }
+  }
+}
+
+template <int MT>
+static int launch_gram_mma(const float* M, int64_t n, int l, int64_t ld, double* G, cudaStream_t stream) {
+  constexpr int LDP = 8 * MT + 4;
+  const size_t smem = (size_t)GM_CH * LDP * sizeof(double);
+  XB_CUDA(cudaFuncSetAttribute(gram_mma_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int blocks = (int)imin(ceil_div(n, GM_CH), 2 * (int64_t)num_sms());
+  gram_mma_kernel<MT><<<blocks, 256, smem, stream>>>(M, n, l, ld, G);
+  XB_LAUNCH_CHECK();
+  return XEOFS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Symmetric eigen-decomposition by parallel cyclic Jacobi (round-robin pairing), one block, fp64.
 // A (l x l) lives in dynamic smem; the eigenvector matrix is accumulated TRANSPOSED (row p = eigenvector p) in
 // shared memory when both fit (VS: l <= 118), else in `work` (global), and written out as columns at the end, sorted
@@ -424,141 +512,6 @@ sym_eig_kernel(const double* __restrict__ G, int l, double* __restrict__ evals, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Polar factor of a square matrix by ONE-SIDED Jacobi (Hestenes), one block, fp64 — the m x m step of a varimax
-// iteration (dense64.cu: xeofs_b200_varimax_update).  Input: Gb = G V0 with V0 orthogonal (the right singular vectors
-// of the previous iteration's G: the columns of Gb are then nearly orthogonal and two sweeps finish the job).  Column
-// pairs (round-robin seating as above) are rotated until orthogonal, the same rotations applied to V; at the end
-// Gb = U diag(sigma), so  polar(G) = U V^T,  sum(svals) = sum sigma.  Against the route through G^T G and sym_eig:
-// no squared condition number, one block-wide barrier per round instead of two, every element of the two matrices
-// read and written once per round with conflict-free (column-contiguous) accesses and no parameter traffic — the
-// two-sided kernel is bound by exactly that shared-memory traffic.  One warp per column pair; lanes own rows
-// lane + 32 k.  Both matrices live in shared memory column-major (m <= 118).
-constexpr int PJ_MAX_M = 118;
-
-__global__ void __launch_bounds__(1024, 1)
-polar_jacobi_kernel(const double* __restrict__ Gb_in, double* __restrict__ V_io, int m, double* __restrict__ U_out,
-                    double* __restrict__ dsum, int32_t* __restrict__ info, double eps_stop) {
-  extern __shared__ double sh[];
-  const int le = (m + 1) & ~1, half = le / 2;
-  const int ldc = (m + 1) & ~1;
-  double* Gt = sh;                        // [le][ldc]  column p of Gb at Gt + p ldc
-  double* Vt = Gt + (size_t)le * ldc;     // [le][ldc]
-  __shared__ unsigned long long mxbits;
-  __shared__ double ssum[32];
-  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-  for (int idx = tid; idx < le * ldc; idx += nt) {
-    const int p = idx % le, r = idx / le;  // consecutive threads read a row of the row-major inputs
-    const bool in = p < m && r < m;
-    if (r < ldc) {
-      Gt[p * ldc + r] = in ? Gb_in[(int64_t)r * m + p] : 0.0;
-      Vt[p * ldc + r] = in ? V_io[(int64_t)r * m + p] : 0.0;
-    }
-  }
-  if (tid == 0) mxbits = 0ull;
-  __syncthreads();
-
-  int sweeps_done = 0;
-  for (int sweep = 0; sweep < 30; ++sweep) {
-    double mx = 0.0;
-    for (int round = 0; round < le - 1; ++round) {
-      for (int q = warp; q < half; q += nw) {
-        int p, r;
-        eig_pair(q, round, le, p, r);
-        if (r >= m) continue;  // the padding column of an odd m
-        double* gp = Gt + p * ldc;
-        double* gq = Gt + r * ldc;
-        double* vp = Vt + p * ldc;
-        double* vq = Vt + r * ldc;
-        double a[4], b[4], x[4], y[4];
-        double al = 0.0, be = 0.0, ga = 0.0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int row = lane + 32 * k;
-          const bool in = row < m;
-          a[k] = in ? gp[row] : 0.0;
-          b[k] = in ? gq[row] : 0.0;
-          x[k] = in ? vp[row] : 0.0;
-          y[k] = in ? vq[row] : 0.0;
-          al = fma(a[k], a[k], al);
-          be = fma(b[k], b[k], be);
-          ga = fma(a[k], b[k], ga);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          al += __shfl_xor_sync(0xffffffffu, al, o);
-          be += __shfl_xor_sync(0xffffffffu, be, o);
-          ga += __shfl_xor_sync(0xffffffffu, ga, o);
-        }
-        const double ab = al * be;
-        if (ga * ga > 1e-32 * ab) {  // (also false for a zero column)
-          mx = fmax(mx, fabs(ga) * rsqrt(ab));
-          const double zeta = (be - al) / (2.0 * ga);
-          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double c = rsqrt(1.0 + t * t), sn = c * t;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int row = lane + 32 * k;
-            if (row < m) {
-              gp[row] = c * a[k] - sn * b[k];
-              gq[row] = sn * a[k] + c * b[k];
-              vp[row] = c * x[k] - sn * y[k];
-              vq[row] = sn * x[k] + c * y[k];
-            }
-          }
-        }
-      }
-      __syncthreads();
-    }
-    sweeps_done = sweep + 1;
-    // the largest normalised inner product this sweep met: what is left after it is of the order of its square
-    if (lane == 0) atomicMax(&mxbits, (unsigned long long)__double_as_longlong(mx));
-    __syncthreads();
-    const double seen = __longlong_as_double((long long)mxbits);
-    __syncthreads();
-    if (tid == 0) mxbits = 0ull;
-    if (seen <= eps_stop) break;
-  }
-  __syncthreads();
-  // sigma_p = |column p|, U = Gb diag(1 / sigma), sum sigma; outputs row-major
-  double part = 0.0;
-  for (int p = warp; p < m; p += nw) {
-    double s2 = 0.0;
-    for (int row = lane; row < m; row += 32) s2 = fma(Gt[p * ldc + row], Gt[p * ldc + row], s2);
-    s2 = warp_sum(s2);
-    const double sg = sqrt(s2), inv = sg > 0.0 ? 1.0 / sg : 0.0;
-    for (int row = lane; row < m; row += 32) Gt[p * ldc + row] *= inv;
-    part += sg;
-  }
-  if (lane == 0) ssum[warp] = part;
-  __syncthreads();
-  if (tid == 0) {
-    double t = 0.0;
-    for (int w = 0; w < nw; ++w) t += ssum[w];
-    *dsum = t;
-    info[0] = sweeps_done;
-  }
-  for (int idx = tid; idx < m * m; idx += nt) {
-    const int r = idx / m, p = idx % m;
-    U_out[idx] = Gt[p * ldc + r];
-    V_io[idx] = Vt[p * ldc + r];
-  }
-}
-
-int polar_jacobi_launch(const double* Gb, double* V, int64_t m, double* U, double* dsum, int32_t* info, double eps_stop,
-                        cudaStream_t stream) {
-  XB_CHECK_ARG(Gb && V && U && dsum && info && m >= 2 && m <= PJ_MAX_M, "polar_jacobi: bad arguments (m=%lld must be in 2..%d)",
-               (long long)m, PJ_MAX_M);
-  const int le = ((int)m + 1) & ~1, half = le / 2;
-  const int per = (half + 31) / 32;                  // pairs per warp and round
-  const int warps = (half + per - 1) / per;
-  const size_t smem = (size_t)2 * le * le * sizeof(double);
-  XB_CUDA(cudaFuncSetAttribute(polar_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  polar_jacobi_kernel<<<1, warps * 32, smem, stream>>>(Gb, V, (int)m, U, dsum, info, eps_stop);
-  XB_LAUNCH_CHECK();
-  return XEOFS_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   // ordered-int trick, valid for any finite floats
   if (v >= 0) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
@@ -632,6 +585,10 @@ extern "C" int xeofs_b200_gram(const float* M, int64_t n, int64_t l, int64_t ld,
   XB_CHECK_ARG(M && G && n > 0 && l > 0 && l <= 128, "gram: bad arguments (l=%lld must be in 1..128)", (long long)l);
   XB_CHECK_ARG(side == 0 || side == 1, "gram: side must be 0 (time-side) or 1 (space-side)");
   if (!accumulate) XB_CUDA(cudaMemsetAsync(G, 0, (size_t)l * l * sizeof(double), stream));
+  if (side == 1 && l > 32 && n >= 4096 && env_int("XEOFS_GRAM_MMA", 1))
+    return l <= 64    ? launch_gram_mma<8>(M, n, (int)l, ld, G, stream)
+           : l <= 104 ? launch_gram_mma<13>(M, n, (int)l, ld, G, stream)
+                      : launch_gram_mma<16>(M, n, (int)l, ld, G, stream);
   const int64_t chunks = ceil_div(n, GR_CHUNK);
   const int blocks = (int)imin(chunks, (l <= 64 ? 6 : 3) * (int64_t)num_sms());
 #define XB_GRAM(TI, NT, KG)                                                                      \
