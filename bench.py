@@ -683,7 +683,9 @@ def rotator_case(d, args, cpu=True):
     l0 = int(model.ops.launches)
     one_fit()
     launches = (int(model.ops.launches) - l0) * max(2, args.steps // 2)
-    sweeps = [t for n, t, _ in model.ops.product_times() if n == "varimax_sweep"]
+    times = model.ops.product_times()
+    sweeps = [t for n, t, _ in times if n == "varimax_sweep"]
+    sweeps_x1 = [t for n, t, _ in times if n == "varimax_sweep_x1"]
     model.ops.time_products = False
     sweep_ms = float(np.mean(sweeps)) if sweeps else None
     alg = S * k * 4
@@ -697,7 +699,10 @@ def rotator_case(d, args, cpu=True):
                 "traffic": (load_traffic("c5") or {}).get("varimax_sweep"), "launch_ms": sweep_ms,
                 "launches_timed": len(sweeps), "algorithmic_bytes_per_launch": alg,
                 "hbm": {"achieved": alg / (sweep_ms * 1e-3) / 1e9, "peak": peak, "frac": alg / (sweep_ms * 1e-3) / 1e9 / peak},
-                "ms_per_iteration": ms / max(iters, 1), "share_of_step": float(sum(sweeps) / ms)}
+                "ms_per_iteration": ms / max(iters, 1), "share_of_step": float((sum(sweeps) + sum(sweeps_x1)) / ms),
+                "single_tf32_sweep_ms": float(np.mean(sweeps_x1)) if sweeps_x1 else None,
+                "single_tf32_sweeps": len(sweeps_x1),
+                "tiles": "64 features per tile from the packed copy of the loadings (one bulk copy per tile)"}
     # parity inside the run: rotation conserves the explained variance (tests/models/single/test_eof_rotator.py:98-137)
     ev_rot = float(r.explained_variance().values.sum())
     ev_eof = float(model.explained_variance().values[:k].sum())

@@ -11,7 +11,7 @@ for wl in "$@"; do
     c2)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${tag}_launches_c2.csv \
           python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-strong-c4 --no-models > gpurun_out/${tag}_launches_c2.log 2>&1
-      # warm-up fit = 14 project_tc launches (10 passes + 4 k-column applies); capture the 14 of the timed fit
+      # a fit = 14 project_tc launches (10 passes + 4 k-column applies); capture the 14 of the timed fit
       timeout 1500 ncu --set full --clock-control none --import-source on -k regex:project_tc_kernel -s 14 -c 14 -f \
           -o gpurun_out/${tag}_full_c2 python bench.py $Q > gpurun_out/${tag}_full_c2.log 2>&1
       ncu -i gpurun_out/${tag}_full_c2.ncu-rep --page raw --csv > gpurun_out/${tag}_full_c2_raw.csv 2>/dev/null
@@ -22,7 +22,7 @@ for wl in "$@"; do
       ncu -i gpurun_out/${tag}_full_c3.ncu-rep --page raw --csv > gpurun_out/${tag}_full_c3_raw.csv 2>/dev/null
       rm -f gpurun_out/${tag}_full_c3.ncu-rep ;;
     c5)
-      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:varimax_tc_kernel -s 20 -c 2 -f \
+      timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"varimax_tc2_kernel|varimax_exact_mma_kernel" -s 40 -c 3 -f \
           -o gpurun_out/${tag}_full_c5 python bench.py --workload c5 --steps 2 --warmup 3 --no-cpu > gpurun_out/${tag}_full_c5.log 2>&1
       ncu -i gpurun_out/${tag}_full_c5.ncu-rep --page raw --csv > gpurun_out/${tag}_full_c5_raw.csv 2>/dev/null
       rm -f gpurun_out/${tag}_full_c5.ncu-rep ;;

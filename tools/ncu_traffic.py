@@ -18,15 +18,25 @@ UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "msecond": 1e-3, 
 
 
 def tag_of(name):
-    """bench.py's product tags from the kernel's template arguments <NS, SIDE_T, KB, STATS, RN, PK, TFAST>."""
-    m = re.search(r"project_tc_kernel<(\d+), (true|false|[01]), (\d+), (true|false|[01]), (\d+|true|false)", name)
+    """bench.py's product tags from the kernel's template arguments <NS, SIDE_T, KB, STATS, RN, PK, TFAST, MODE>."""
+    m = re.search(r"project_tc_kernel<([^>]*)>", name)
     if m:
-        ns, side_t, stats = int(m.group(1)), m.group(2) in ("true", "1"), m.group(4) in ("true", "1")
-        rn = m.group(5)
+        a = [x.strip() for x in m.group(1).split(",")]
+        tru = lambda x: x in ("true", "1")  # noqa: E731
+        ns, side_t, stats, rn = int(a[0]), tru(a[1]), tru(a[3]), a[4]
+        mode = int(a[7]) if len(a) > 7 and a[7].isdigit() else 0  # 0 fp32 field, 1 also writes the fp16 copy, 2 reads it
         t = "project_T" if side_t else ("project_S_stats" if stats else "project_S")
+        if mode == 2:
+            return t + "_h16"
+        if mode == 1:
+            return t + "_wcopy"
         return t + {1: "", 2: "_x2", 3: "_x3"}[ns] + ("_x1r" if rn in ("1", "true") else "_x1f" if rn == "2" else "")
-    if "varimax_tc_kernel" in name:
+    if "varimax_tc2_kernel" in name or "varimax_tc_kernel" in name:
         return "varimax_sweep"
+    if "varimax_exact_mma_kernel" in name:
+        return "varimax_sweep_fp64"
+    if "gram_bf16_kernel" in name:
+        return "gram_rows_bf16"
     return name.split("(")[0][-40:]
 
 
