@@ -273,10 +273,14 @@ def load_peak():
 def load_traffic(key):
     """DRAM bytes per launch (ncu --set full, dram read + write) of the kernels of workload `key`, generated from the
     ncu CSV by tools/ncu_traffic.py; None if not captured."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(key)
-    except Exception:
-        return None
+    for name in ("r02b_traffic.json", "r02_traffic.json"):  # the capture of the final code of the round, else the first one
+        try:
+            hit = json.load(open(os.path.join(ROOT, "profiles", name))).get(key)
+        except Exception:
+            hit = None
+        if hit:
+            return dict(hit, _file="profiles/" + name)
+    return None
 
 
 def timed_steps(d, fn, warmup, steps, clock=True):
@@ -337,8 +341,8 @@ def roofline_of(by, ms_step, alg_bytes, peak, peak_src, traffic, field_bytes=0):
     ach = alg_bytes / (avg_ms * 1e-3) / 1e9
     tr = (traffic or {}).get(dom)
     return {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": tr, "traffic_source": "profiles/r02_traffic.json (ncu --set full on this code, dram read + "
-                                             "write per launch)" if tr else None,
+            "traffic": tr, "traffic_source": (traffic or {}).get("_file", "profiles") + " (ncu --set full on this code, "
+                                             "dram read + write per launch, tools/ncu_traffic.py)" if tr else None,
             "peak_source": peak_src, "launch_ms": avg_ms, "launches_timed": len(by[dom]),
             "algorithmic_bytes_per_launch": alg_bytes,
             "per_kernel_ms": {n: float(np.mean(v)) for n, v in by.items()},

@@ -7,7 +7,7 @@ echo "# cuobjdump -sass $SO  ($(date -u +%Y-%m-%dT%H:%MZ), git $(git rev-parse -
 echo "# arch: $(cuobjdump -lelf $SO | head -3 | tr '\n' ' ')"
 cuobjdump -sass $SO > /tmp/xeofs_sass.txt
 echo "# tensor-core / TMEM / TMA / bulk-copy opcodes (count over all kernels)"
-for op in UTCHMMA UTCQMMA UTCBAR LDTM STTM UTMALDG UTMASTG UBLKCP UTCATOMSWS SYNCS ELECT; do
+for op in UTCHMMA UTCQMMA UTCBAR LDTM STTM UTMALDG UTMASTG UBLKCP UBLKPF UTCATOMSWS SYNCS ELECT DMMA; do
   printf "%-12s %6d\n" $op $(grep -c -E "[[:space:]]$op(\.|[[:space:]])" /tmp/xeofs_sass.txt)
 done
 echo "# kernels holding UTCHMMA (tcgen05.mma):"
