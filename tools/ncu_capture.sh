@@ -8,8 +8,12 @@ mkdir -p gpurun_out
 Q="--steps 1 --warmup 1 --no-e2e --no-cpu --no-strong-c4 --no-models"
 for wl in "$@"; do
   case $wl in
+    launches) wl=c2
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:xb:: -c 1200 --csv --log-file gpurun_out/${tag}_launches_c2.csv \
+          python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-strong-c4 --no-models > gpurun_out/${tag}_launches_c2.log 2>&1 ;;
     c2)
-      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${tag}_launches_c2.csv \
+      # (the library's kernels only — namespace xb: the synthetic field alone is built by ~3000 torch launches)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:xb:: -c 1200 --csv --log-file gpurun_out/${tag}_launches_c2.csv \
           python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-strong-c4 --no-models > gpurun_out/${tag}_launches_c2.log 2>&1
       # a fit = 14 project_tc launches (10 passes + 4 k-column applies); capture the 14 of the timed fit
       timeout 1500 ncu --set full --clock-control none --import-source on -k regex:project_tc_kernel -s 14 -c 14 -f \
