@@ -131,32 +131,67 @@ def shard_rows(n_lat, world, rank, scaling):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line), every 100 ms.  The
+    samples are NVML queries made in this process (what nvidia-smi prints); forking one nvidia-smi per sample, as this
+    class first did, cost the timed region ~10 % (52.7 -> 59.4 ms per config-2 fit in the same session).  Without the
+    NVML binding: ONE background `nvidia-smi -lms 100`, started before and stopped after the region, as in the recipe."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.rows, self._stop, self._th = index, [], threading.Event(), None
+        self.index, self.rows, self._stop, self._th, self._proc, self.source = index, [], threading.Event(), None, None, None
+        self._h = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            self._h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            self._nv = pynvml
+            self.source = "nvml"
+        except Exception:
+            self._h = None
 
     def _run(self):
+        nv = self._nv
+        bits = [getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)]
+        reasons_of = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+                sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                r = int(reasons_of(self._h))
+                self.rows.append([str(sm), str(mx), "", *("Active" if r & b else "Not Active" for b in bits)])
             except Exception:
                 pass
             self._stop.wait(0.1)
 
     def __enter__(self):
-        self._th = threading.Thread(target=self._run, daemon=True)
-        self._th.start()
+        if self._h is not None:
+            self._th = threading.Thread(target=self._run, daemon=True)
+            self._th.start()
+        else:
+            try:
+                self._proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                               "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                self.source = "nvidia-smi -lms 100"
+            except Exception:
+                self._proc = None
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._th.join(timeout=6)
+        if self._th is not None:
+            self._th.join(timeout=6)
+        if self._proc is not None:
+            self._proc.terminate()
+            try:
+                out, _ = self._proc.communicate(timeout=5)
+                self.rows = [[c.strip() for c in ln.split(",")] for ln in out.strip().splitlines() if ln.strip()]
+            except Exception:
+                pass
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -164,7 +199,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs

@@ -289,7 +289,10 @@ gram_mma_kernel(const float* __restrict__ M, int64_t n, int l, int64_t ld, doubl
   double* Ms = reinterpret_cast<double*>(gm_raw);  // [GM_CH][LDP]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;
-  const int mt0 = warp, mt1 = MT - 1 - warp;  // the two tile rows of this warp (the same one in the middle of an odd MT)
+  // MT <= 8: four warps hold all the tile rows, the other four take every second K step of the same rows
+  constexpr int KSPLIT = MT <= 8 ? 2 : 1;
+  const int wq = KSPLIT == 2 ? (warp & 3) : warp, kpar = KSPLIT == 2 ? (warp >> 2) : 0;
+  const int mt0 = wq, mt1 = MT - 1 - wq;  // the two tile rows of this warp (the same one in the middle of an odd MT)
   const bool has0 = mt0 <= mt1, has1 = mt0 < mt1;
   double acc[2][MT][2];
 #pragma unroll
@@ -309,7 +312,7 @@ gram_mma_kernel(const float* __restrict__ M, int64_t n, int l, int64_t ld, doubl
     __syncthreads();
     if (has0) {
 #pragma unroll 2
-      for (int k = 0; k < GM_CH / 4; ++k) {
+      for (int k = kpar; k < GM_CH / 4; k += KSPLIT) {
         const double* row = Ms + (4 * k + lc) * LDP + lr;
         const double a0 = row[8 * mt0], a1 = row[8 * mt1];
 #pragma unroll
