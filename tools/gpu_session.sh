@@ -26,6 +26,7 @@ for step in "$@"; do
     two)      { timeout 600 python -m pytest tests -m gpu -q -k "two_gpus"; echo "pytest exit $?";
                 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3; echo "exit $?"; } > gpurun_out/${tag}_two.log 2>&1 ;;
     eight)    { timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 10 --warmup 3; echo "exit $?"; } > gpurun_out/${tag}_eight.log 2>&1 ;;
+    four)     { timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 10 --warmup 3; echo "exit $?"; } > gpurun_out/${tag}_four.log 2>&1 ;;
     refs8)    timeout 900 python bench.py --impl reference --ref-cols 129780 --steps 1 --warmup 0 > gpurun_out/${tag}_refs8.log 2>&1 ;;
     c4n1)     timeout 900 python tools/parity_full.py c4n1 > gpurun_out/${tag}_c4n1.log 2>&1 ;;
     smoke)    timeout 300 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_smoke.log ;;
