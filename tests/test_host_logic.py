@@ -671,3 +671,42 @@ def test_rotator_compute_false_runs_max_iter_without_raising():
     assert r.n_iter_ == 3
     with pytest.raises(RuntimeError, match="did not converge"):
         xb.single.EOFRotator(n_modes=6, max_iter=3, compute=True).fit(m)
+
+
+def test_sketch_draw_is_the_reference_stream_and_memoised():
+    """The range finder's sketch is numpy's legacy RandomState stream (what sklearn draws from, the reference's call
+    at linalg/decomposer.py:141-146); the fp32 image that goes to the device is the rounded fp64 draw, made once."""
+    from xeofs_b200 import _engine as E
+    a = E.draw_sketch(5, 300, 20)
+    np.testing.assert_array_equal(a, np.random.RandomState(5).normal(size=(300, 20)))
+    b = E.draw_sketch(5, 300, 20, f32=True)
+    assert b.dtype == np.float32 and b is E.draw_sketch(5, 300, 20, f32=True)
+    np.testing.assert_array_equal(b, a.astype(np.float32))
+    # the first rows of a longer draw are the shorter draw (row-major fill)
+    np.testing.assert_array_equal(E.draw_sketch(5, 100, 20), a[:100])
+    rs = np.random.RandomState(7)
+    c = E.draw_sketch(rs, 10, 4, f32=True)  # a generator object is consumed, never memoised
+    assert c.dtype == np.float32 and not np.array_equal(c, E.draw_sketch(rs, 10, 4, f32=True))
+
+
+def test_bench_helpers_without_a_gpu():
+    """bench.py's clock sampler degrades to 'no samples' on a box without NVML / nvidia-smi, and the ncu tag parser
+    names the product kinds the bench line reports."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    bench = importlib.import_module("bench")
+    with bench.ClockSampler(0) as c:
+        pass
+    out = c.summary()
+    assert out["samples"] == 0 and out["sm_mhz"] is None and out["reasons"] == []
+    nt = importlib.import_module("ncu_traffic")
+    assert nt.tag_of("void xb::project_tc_kernel<1, true, 2, false, 0, false, true, 2>(CUtensorMap_st)") == "project_T_h16"
+    assert nt.tag_of("void xb::project_tc_kernel<1, false, 1, true, 0, false, false, 1>(CUtensorMap_st)") == "project_S_stats_wcopy"
+    assert nt.tag_of("void xb::project_tc_kernel<3, true, 2, false, 0, true, true, 0>(CUtensorMap_st)") == "project_T_x3"
+    assert nt.tag_of("void xb::varimax_tc2_kernel<28>(xb::Vt2Params)") == "varimax_sweep"
+    # the algorithmic bytes of a product kind: fp16 passes stream half the field, the copy-writing pass 1.5 x
+    assert bench.alg_bytes_of("project_T_h16", 100 + 8, 100) == 58
+    assert bench.alg_bytes_of("project_S_stats_wcopy", 100 + 8, 100) == 158
+    assert bench.alg_bytes_of("project_T_x3", 108, 100) == 108
