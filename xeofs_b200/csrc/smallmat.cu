@@ -395,14 +395,21 @@ sym_eig_kernel(const double* __restrict__ G, int l, double* __restrict__ evals, 
   __shared__ double diagnorm;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int half = le / 2;
-  // 2 x 2 blocks (row pair qa, column pair qb) of this thread: fixed for the whole kernel (EIG_THREADS threads,
-  // half <= 64: at most 4), packed qa << 8 | qb
-  constexpr int NBLK = 4;
+  // 2 x 2 blocks (row pair qa, column pair qb >= qa) of this thread: fixed for the whole kernel (EIG_THREADS threads,
+  // half <= 64: at most 3), packed qa << 8 | qb.  Only the blocks on or above the diagonal are computed; their
+  // transposes are stored along (A stays exactly symmetric, and half of the loads go away: the kernel is bound by
+  // its shared-memory traffic)
+  constexpr int NBLK = 3;
   int blk[NBLK];
 #pragma unroll
   for (int i = 0; i < NBLK; ++i) {
     const int b = tid + i * nt;
-    blk[i] = b < half * half ? ((b / half) << 8 | (b % half)) : -1;
+    blk[i] = -1;
+    if (b < half * (half + 1) / 2) {
+      int qa = 0, rem = b;
+      while (rem >= half - qa) { rem -= half - qa; ++qa; }
+      blk[i] = qa << 8 | (qa + rem);
+    }
   }
   // eigenvector rows: tpq threads share the two rows of a pair
   const int tpq = nt / half > 0 ? nt / half : 1;
@@ -461,20 +468,30 @@ sym_eig_kernel(const double* __restrict__ G, int l, double* __restrict__ evals, 
         pr[tid] = p; pr[half + tid] = r;
       }
       __syncthreads();
-      // A <- J^T A J, one 2 x 2 block (row pair qa, column pair qb) at a time: every element is touched once
+      // A <- J^T A J, one 2 x 2 block (row pair qa, column pair qb >= qa) at a time: every element is written once
 #pragma unroll
       for (int i = 0; i < NBLK; ++i) {
         if (blk[i] < 0) continue;
         const int qa = blk[i] >> 8, qb = blk[i] & 255;
-        const int pa = pr[qa], ra = pr[half + qa], pb = pr[qb], rb = pr[half + qb];
+        int pa, ra, pb, rb;  // (recomputed, not read back from pr: the kernel is bound by shared-memory traffic)
+        eig_pair(qa, round, le, pa, ra);
+        eig_pair(qb, round, le, pb, rb);
         const double ca = cs[qa], sa = cs[half + qa], cb = cs[qb], sb = cs[half + qb];
         const double a00 = A[pa * ldA + pb], a01 = A[pa * ldA + rb], a10 = A[ra * ldA + pb], a11 = A[ra * ldA + rb];
         const double b00 = ca * a00 - sa * a10, b01 = ca * a01 - sa * a11;
         const double b10 = sa * a00 + ca * a10, b11 = sa * a01 + ca * a11;
-        A[pa * ldA + pb] = cb * b00 - sb * b01;
-        A[pa * ldA + rb] = sb * b00 + cb * b01;
-        A[ra * ldA + pb] = cb * b10 - sb * b11;
-        A[ra * ldA + rb] = sb * b10 + cb * b11;
+        const double n00 = cb * b00 - sb * b01, n01 = sb * b00 + cb * b01;
+        const double n10 = cb * b10 - sb * b11, n11 = sb * b10 + cb * b11;
+        A[pa * ldA + pb] = n00;
+        A[pa * ldA + rb] = n01;
+        A[ra * ldA + pb] = n10;
+        A[ra * ldA + rb] = n11;
+        if (qa != qb) {
+          A[pb * ldA + pa] = n00;
+          A[rb * ldA + pa] = n01;
+          A[pb * ldA + ra] = n10;
+          A[rb * ldA + ra] = n11;
+        }
       }
       // eigenvector accumulator: rows p, r <- J^T rows
       for (int q = vq; q < half; q += (nt + tpq - 1) / tpq) {
