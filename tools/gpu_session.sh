@@ -21,6 +21,7 @@ for step in "$@"; do
     vt)       { timeout 150 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "varimax or gram"; echo "pytest exit $?"; timeout 150 python -m pytest tests/test_gpu_models.py -x -q -m gpu -k "rotat"; echo "pytest exit $?";
                 timeout 120 python tools/bench_varimax.py; } > gpurun_out/${tag}_vt.log 2>&1 ;;
     eig)      timeout 600 python tools/diag_eig.py > gpurun_out/${tag}_eig.log 2>&1 ;;
+    c5tol)    { for v in 1e-9 1e-8 3e-8; do echo "== XEOFS_TC_EIG_TOL=$v"; XEOFS_TC_EIG_TOL=$v timeout 300 python bench.py --workload c5 --steps 4 --warmup 3 --no-cpu; done; } > gpurun_out/${tag}_c5tol.log 2>&1 ;;
     profile_c3) timeout 600 python tools/profile_fit.py c3 > gpurun_out/${tag}_profile_c3.log 2>&1 ;;
     profile_c5) timeout 600 python tools/profile_fit.py c5 > gpurun_out/${tag}_profile_c5.log 2>&1 ;;
     two)      { timeout 600 python -m pytest tests -m gpu -q -k "two_gpus"; echo "pytest exit $?";

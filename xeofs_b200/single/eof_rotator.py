@@ -9,6 +9,8 @@ The polar factor R = U V^T of svd(G) and delta = sum(svals) come from the eigen-
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -19,6 +21,8 @@ from .. import _labels as L
 TC_WINDOW = 8  # iterations the stopping test of the tensor-core phase of the varimax iteration looks back
 TC_SYNC = 8    # tensor-core iterations between two reads of delta on the host
 X1_RTOL = 1e-5  # the single-TF32 sweeps hand over to the 3xTF32 ones when delta moves less than this per iteration
+# relative off-diagonal norm at which the Jacobi solver of the m x m step stops during the 3xTF32 phase
+TC_EIG_TOL = float(os.environ.get("XEOFS_TC_EIG_TOL", "1e-9"))
 
 
 class EOFRotator:
@@ -75,7 +79,7 @@ class EOFRotator:
             comm.sum_(G3)
             comm.sum_(W)
             ops.varimax_update(G3, W, XtX, alpha, R, basis, hist_dev[it - 1:it],
-                               eig_tol=(1e-6 if x1 else 1e-9) if use_tc else 0.0)
+                               eig_tol=(1e-6 if x1 else TC_EIG_TOL) if use_tc else 0.0)
             if use_tc:
                 if not test or (it - read < TC_SYNC and it < max_iter):
                     continue
