@@ -710,3 +710,29 @@ def test_bench_helpers_without_a_gpu():
     assert bench.alg_bytes_of("project_T_h16", 100 + 8, 100) == 58
     assert bench.alg_bytes_of("project_S_stats_wcopy", 100 + 8, 100) == 158
     assert bench.alg_bytes_of("project_T_x3", 108, 100) == 108
+
+
+@pytest.mark.parametrize("dims", [("time", "lat", "lon"), ("time", "lon", "lat")])
+def test_coslat_weights_are_broadcast_on_the_device(dims):
+    """utils/xarray_utils.py:256-270: sqrt(cos(lat)) along the latitude dim, broadcast over the other feature dims.
+    Without user weights only the latitude vector leaves the host; the result equals the host broadcast."""
+    import torch
+    import xeofs_b200 as xb
+    from xeofs_b200 import _labels as L
+    from xeofs_b200._preprocessor import Preprocessor
+    rng = np.random.default_rng(3)
+    lat, lon = np.linspace(80, -80, 7), np.arange(9) * 10.0
+    shape = (30,) + tuple({"lat": 7, "lon": 9}[d] for d in dims[1:])
+    X = (280 + rng.standard_normal(shape)).astype(np.float32)
+    coords = {"lat": lat, "lon": lon}
+    p = Preprocessor(make_ops(), with_coslat=True)
+    ff = p.fit_transform(xb.DataArray(X, dims, coords), ("time",))
+    want = np.array(L.sqrt_cos_lat_weights(dims[1:], shape[1:], coords), dtype=np.float64).reshape(-1)
+    assert isinstance(ff.featw, torch.Tensor) and ff.featw.dtype == torch.float64
+    np.testing.assert_array_equal(ff.featw.cpu().numpy(), want)
+    # user weights on top of them: the host route, same product
+    w = xb.DataArray(rng.random(7).astype(np.float64), ("lat",), {"lat": lat})
+    p2 = Preprocessor(make_ops(), with_coslat=True)
+    ff2 = p2.fit_transform(xb.DataArray(X, dims, coords), ("time",), weights=w)
+    wl = np.broadcast_to(np.asarray(w.values).reshape([7 if d == "lat" else 1 for d in dims[1:]]), shape[1:]).reshape(-1)
+    np.testing.assert_allclose(ff2.featw.cpu().numpy(), want * wl, rtol=1e-15)

@@ -84,9 +84,9 @@ def split_dims(dims, sample_dims):
     return sample_dims, feature_dims
 
 
-def sqrt_cos_lat_weights(feature_dims, feature_shape, coords):
-    """utils/xarray_utils.py:103-159, 256-270: sqrt(clip(cos(deg2rad(lat)), 0, 1)) along the ONE feature dim
-    named like a latitude, broadcast over the feature shape (float64)."""
+def sqrt_cos_lat_vector(feature_dims, coords):
+    """utils/xarray_utils.py:103-159, 256-270: sqrt(clip(cos(deg2rad(lat)), 0, 1)) along the ONE feature dim named
+    like a latitude (float64), and the shape that broadcasts it over the feature dims."""
     lat_dims = [d for d in feature_dims if d in VALID_LATITUDE_NAMES]
     if len(lat_dims) == 0:
         raise ValueError(
@@ -103,6 +103,12 @@ def sqrt_cos_lat_weights(feature_dims, feature_shape, coords):
     w = np.sqrt(np.cos(np.deg2rad(lat)).clip(0, 1))
     shape = [1] * len(feature_dims)
     shape[feature_dims.index(lat_dim)] = lat.size
+    return w, shape
+
+
+def sqrt_cos_lat_weights(feature_dims, feature_shape, coords):
+    """The same, broadcast over the feature shape on the host (a view)."""
+    w, shape = sqrt_cos_lat_vector(feature_dims, coords)
     return np.broadcast_to(w.reshape(shape), feature_shape)
 
 

@@ -95,13 +95,20 @@ class Preprocessor:
 
     # ------------------------------------------------------------------ fit
     def _prepare(self, X, sample_dims, weights=None):
-        """Labels + stacking + the per-feature weight vector (coslat * weights, fp64, host) of one array."""
+        """Labels + stacking + the per-feature weight vector (coslat * weights, fp64) of one array: a host array, or —
+        coslat weights alone — a device vector broadcast there from the latitude vector (at 4 M features the host
+        broadcast and its copy to the device cost 20-50 ms per fit)."""
         data, dims, coords, self.as_xarray = L.unpack(X)
         self._dim = sample_dims
         X2, self.sample_shape, self.feature_shape = self._to_2d(data, dims, fit=True)
         self.coords = {d: coords[d] for d in dims if d in coords}
         featw = None
-        if self.with_coslat:
+        if self.with_coslat and weights is None:
+            w, shape = L.sqrt_cos_lat_vector(self.feature_dims, self.coords)
+            if tuple(np.broadcast_shapes(tuple(shape), tuple(self.feature_shape))) != tuple(self.feature_shape):
+                raise ValueError(f"latitude coordinate of length {w.size} does not match the feature shape {self.feature_shape}")
+            featw = self.ops.to_device(w, torch.float64).reshape(shape).expand(tuple(self.feature_shape)).reshape(-1)
+        elif self.with_coslat:
             featw = np.array(L.sqrt_cos_lat_weights(self.feature_dims, self.feature_shape, self.coords), dtype=np.float64)
         if weights is not None:
             wdata, wdims, _, _ = L.unpack(weights)
@@ -122,8 +129,11 @@ class Preprocessor:
     def fit_transform(self, X, sample_dims, weights=None, overlap=None, first=None):
         """``first``: callable (T, S) -> (W, l) or None, the sketch for the fused statistics + first product pass."""
         X2, featw = self._prepare(X, sample_dims, weights)
-        self.featw_host = None if featw is None else np.ascontiguousarray(featw.reshape(-1))
-        featw_dev = None if featw is None else self.ops.to_device(self.featw_host, torch.float64)
+        if isinstance(featw, torch.Tensor):
+            self.featw_host, featw_dev = None, featw
+        else:
+            self.featw_host = None if featw is None else np.ascontiguousarray(featw.reshape(-1))
+            featw_dev = None if featw is None else self.ops.to_device(self.featw_host, torch.float64)
         self.fitted = fit_field(self.ops, X2, featw_dev, center=self.with_center, standardize=self.with_std,
                                 check_nans=self.check_nans, comm=self.comm, overlap=overlap,
                                 first=first(int(X2.shape[0]), int(X2.shape[1])) if first is not None else None)
@@ -226,6 +236,7 @@ class MultiPreprocessor:
         del mats
         featw = None
         if any(fw is not None for fw in fws):
+            fws = [fw.detach().cpu().numpy() if isinstance(fw, torch.Tensor) else fw for fw in fws]
             featw = np.concatenate([np.ones(n) if fw is None else np.ascontiguousarray(fw.reshape(-1))
                                     for fw, n in zip(fws, sizes)])
         self.featw_host = featw

@@ -80,7 +80,8 @@ class EOF:
         self._predrawn = E.draw_sketch(p["random_state"], T, l)
         lp = lpad(l)
         W = np.zeros((T, lp), dtype=np.float32)
-        W[:, :l] = self._predrawn
+        # (an integer seed: the memoised fp32 image of the same draw; no seed: the draw just made)
+        W[:, :l] = E.draw_sketch(p["random_state"], T, l, f32=True) if p["random_state"] is not None else self._predrawn
         return self.ops.to_device(W), l
 
     @staticmethod
